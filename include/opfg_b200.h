@@ -1,0 +1,213 @@
+/*
+ * opfg_b200.h -- C ABI of libopfg_b200.so: batched AC power flow + reward engine
+ * for opfgym-style environments on NVIDIA B200 (sm_100a).
+ *
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ * Every `double*` / `uint8_t*` / `int32_t*` / `float*` argument of a launch
+ * function is a DEVICE pointer unless its comment says "host".  All launches go
+ * to the caller's `cudaStream_t` (passed as void*), never synchronise, and never
+ * allocate.  Return value: 0 = ok, <0 = error (text via opfg_last_error()).
+ * Non-convergence of an environment is DATA (converged[b] == 0), not an error.
+ *
+ * Which reference interface each entry point replaces
+ * (paths relative to the opfgym reference checkout):
+ *
+ *   opfg_grid_create      pandapower `_pd2ppc`/`_ppc2ppci` output (`net._ppc`) consumed by
+ *                         `pp.runpp`, reached from opfgym/opf_env.py:703; symbolic analysis
+ *                         replaces SuperLU/KLU's per-call ordering.
+ *   opfg_set_assembly     OpfEnv._apply_actions            opfgym/opf_env.py:421-491
+ *                         + pandapower bus PD/QD summation (build_bus.py) [ext-mem]
+ *   opfg_set_scoring      opfgym/constraints.py:70-128, opfgym/objective.py:6-87,
+ *                         opfgym/reward.py:61-98, OpfEnv._get_obs opf_env.py:532-549
+ *   opfg_philox_uniform   np_random.uniform in OpfEnv._sample_from_range  opf_env.py:278
+ *   opfg_sample_uniform   OpfEnv._sample_uniform / _sample_from_range      opf_env.py:253-284
+ *   opfg_assemble         OpfEnv._apply_actions + makeSbus (kernel 1)
+ *   opfg_pf_solve         pp.runpp(net, enforce_q_lims=True)  opf_env.py:696-709
+ *                         (kernels 2-4: mismatch SpMV, Jacobian, batched sparse LU)
+ *   opfg_score            pfsoln/_extract_results + OpfEnv.calculate_reward opf_env.py:515-530
+ *                         + OpfEnv._get_obs (kernel 5)
+ *   opfg_step             OpfEnv.step                       opfgym/opf_env.py:374-419
+ */
+#ifndef OPFG_B200_H
+#define OPFG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPFG_VERSION 1
+
+/* PYPOWER column indices of the ppc matrices handed to opfg_grid_create */
+enum { OPFG_BUS_I = 0, OPFG_BUS_TYPE = 1, OPFG_PD = 2, OPFG_QD = 3, OPFG_GS = 4, OPFG_BS = 5,
+       OPFG_VM = 7, OPFG_VA = 8, OPFG_BASE_KV = 9 };
+enum { OPFG_GEN_BUS = 0, OPFG_PG = 1, OPFG_QG = 2, OPFG_QMAX = 3, OPFG_QMIN = 4, OPFG_VG = 5,
+       OPFG_GEN_STATUS = 7 };
+enum { OPFG_F_BUS = 0, OPFG_T_BUS = 1, OPFG_BR_R = 2, OPFG_BR_X = 3, OPFG_BR_B = 4, OPFG_TAP = 8,
+       OPFG_SHIFT = 9, OPFG_BR_STATUS = 10, OPFG_BR_G = 13 /* extension: shunt conductance */ };
+enum { OPFG_PQ = 1, OPFG_PV = 2, OPFG_REF = 3 };
+
+typedef struct OpfgGrid OpfgGrid; /* opaque; owns device copies of all tables */
+
+/* ---- value references -------------------------------------------------------
+ * Per-environment mutable cells live in one row-major state matrix S[B, n_state]
+ * (sampled loads, set-points, prices, per-sample bounds ... and, at its tail,
+ * the result cells written by opfg_score).  Static values shared by all
+ * environments live in a constant table C[n_const].  A value reference is an
+ * int32:  ref >= 0 -> S[b, ref];  ref < 0 -> C[-ref-1].                        */
+typedef int32_t opfg_ref;
+
+typedef struct {
+    int32_t nb, ng, nbr;
+    double base_mva;
+    const double* bus;    int32_t bus_cols;     /* host, [nb , bus_cols]    row-major */
+    const double* gen;    int32_t gen_cols;     /* host, [ng , gen_cols]              */
+    const double* branch; int32_t branch_cols;  /* host, [nbr, branch_cols] (>=14 to carry BR_G) */
+    double tol_pu;          /* ||F||_inf threshold, = tolerance_mva / base_mva          */
+    int32_t max_iter;       /* pandapower max_iteration='auto' -> 10                      */
+    int32_t init_dc;        /* 1: DC-power-flow angle start (pandapower init='dc')        */
+    int32_t enforce_q_lims; /* 1: PV->PQ outer loop of pandapower's enforce_q_lims        */
+    int32_t threads_per_env;/* 0 = choose from grid size (32/64/128)                      */
+    int32_t ordering;       /* 0 = auto (cost model), 1 = min-degree, 2 = independent-set */
+} OpfgGridDesc;
+
+typedef struct {
+    int32_t nb, n_nonref, nnz_y, n_blocks, n_fill_blocks, n_levels, threads_per_env;
+    int32_t smem_bytes_pf, smem_bytes_score;
+    int32_t n_state, n_const, n_act, n_obs, n_constraints;
+    double flops_per_iter;     /* FP64 flops of one NR iteration (mismatch+Jacobian+LU+solves+update) */
+    double flops_score;        /* FP64 flops of branch flows + scoring                                */
+    double lu_flops;           /* block LU part of flops_per_iter                                     */
+    double bytes_per_step;     /* algorithmic HBM bytes of one env step               */
+} OpfgGridInfo;
+
+/* action application + Sbus scatter (kernel 1) */
+typedef struct {
+    int32_t n_state;                 /* width of S                                   */
+    int32_t n_const; const double* consts;           /* host, C table                */
+    /* actions: S[slot] = round_kind(clamp(a*(hi-lo)+lo) / div) */
+    int32_t n_act;
+    const int32_t* act_slot;         /* host [n_act] S column written                 */
+    const opfg_ref* act_lo;          /* host [n_act]                                  */
+    const opfg_ref* act_hi;          /* host [n_act]                                  */
+    const opfg_ref* act_div;         /* host [n_act] scaling divisor                  */
+    const int32_t* act_kind;         /* host [n_act] 0 continuous, 1 bool round, 2 integer round */
+    const opfg_ref* act_clamp_lo;    /* host [n_act] or NULL: clamp after mapping (non-autoscale mode) */
+    const opfg_ref* act_clamp_hi;
+    /* injections: Sbus[bus] += coef * (P + jQ) / base_mva, in list order per bus */
+    int32_t n_inj;
+    const int32_t* inj_bus;          /* host [n_inj] ppc bus                           */
+    const opfg_ref* inj_p;           /* host [n_inj]                                   */
+    const opfg_ref* inj_q;           /* host [n_inj] (ref to a 0 constant if none)     */
+    const opfg_ref* inj_coef;        /* host [n_inj] sign*scaling*in_service           */
+} OpfgAssemblyDesc;
+
+enum { OPFG_REWARD_SUMMATION = 0, OPFG_REWARD_REPLACEMENT = 1, OPFG_REWARD_PARAMETERIZED = 2,
+       OPFG_REWARD_ONLY_OBJECTIVE = 3 };
+
+/* result cells, constraints, costs, reward, observation gather (kernel 5) */
+typedef struct {
+    /* where results go in S (-1 = not materialised) */
+    int32_t n_pp_bus;
+    const int32_t* pp_bus_lookup;    /* host [n_pp_bus] pandapower bus -> ppc bus (-1 dropped) */
+    int32_t res_bus_vm_slot, res_bus_va_slot;        /* first S column of res_bus.vm_pu / va_degree */
+    const int32_t* branch_loading_slot;              /* host [nbr] S column of loading_percent (-1 none) */
+    const int32_t* branch_flow_slot;                 /* host [nbr] first of 4 S columns p_from,q_from,p_to,q_to (-1) */
+    const double* rate_f; const double* rate_t;      /* host [nbr] loading = 100*max(|Sf|*rate_f/vm_f, |St|*rate_t/vm_t) */
+    const int32_t* gen_p_slot; const int32_t* gen_q_slot; /* host [ng] S columns of generator P/Q results (-1) */
+    /* constraints */
+    int32_t n_constraints;
+    const int32_t* con_ptr;          /* host [n_constraints+1] element ranges          */
+    const opfg_ref* con_value;       /* host [n_el]                                    */
+    const double*  con_value_scale;  /* host [n_el]                                    */
+    const opfg_ref* con_min;         /* host [n_el] (ref to NaN constant = unbounded)  */
+    const opfg_ref* con_max;         /* host [n_el]                                    */
+    const double*  con_bound_mul;    /* host [n_el] boundary multiplier (scaling)      */
+    const double*  con_autoscale;    /* host [n_constraints]                           */
+    const int32_t* con_worst_case;   /* host [n_constraints]                           */
+    const double*  con_penalty_factor; const double* con_penalty_power; const double* con_count_penalty;
+    /* polynomial costs: cost = c0 + c1*v + c2*v^2 for P and for Q of each row */
+    int32_t n_poly;
+    const opfg_ref* poly_p; const double* poly_p_mul;   /* host [n_poly] P value = mul * ref */
+    const opfg_ref* poly_q; const double* poly_q_mul;
+    const opfg_ref* poly_coef;       /* host [n_poly*6] cp0 cp1 cp2 cq0 cq1 cq2        */
+    /* piece-wise linear costs */
+    int32_t n_pwl, n_pwl_seg;        /* every row uses the first n_pwl_seg segments    */
+    const opfg_ref* pwl_v; const double* pwl_v_mul;     /* host [n_pwl]                */
+    const opfg_ref* pwl_seg;         /* host [n_pwl*n_pwl_seg*3] lo, hi, price         */
+    /* reward */
+    int32_t reward_kind;
+    double penalty_weight;           /* NaN = None (plain sum)                         */
+    double clip_lo, clip_hi;         /* NaN = no clipping                              */
+    double objective_factor, objective_bias, penalty_factor, penalty_bias;
+    double valid_reward, invalid_penalty, invalid_objective_share;
+    /* observation gather */
+    int32_t n_obs;
+    const opfg_ref* obs_ref;         /* host [n_obs]                                   */
+} OpfgScoringDesc;
+
+/* device buffers of one batch (any pointer may be NULL if the stage that needs it is not run) */
+typedef struct {
+    int64_t n_env;
+    const double* actions;   /* [B, n_act]   in  (opfg_assemble)                              */
+    double* state;           /* [B, n_state] in/out                                           */
+    double* sbus;            /* [B, nb, 2]   complex bus injections, ppc bus order, p.u.      */
+    double* vm;              /* [B, nb]      out, p.u.                                        */
+    double* va;              /* [B, nb]      out, radians                                     */
+    uint8_t* converged;      /* [B]          out                                              */
+    int32_t* iterations;     /* [B]          out                                              */
+    double* reward;          /* [B]          out (NaN if not converged)                       */
+    double* objective;       /* [B]          out  sum of -costs                               */
+    double* penalty;         /* [B]          out  sum of penalties                            */
+    double* cost;            /* [B]          out  safe-RL cost                                */
+    uint8_t* valids;         /* [B, n_constraints] out                                        */
+    double* violations;      /* [B, n_constraints] out                                        */
+    double* penalties;       /* [B, n_constraints] out                                        */
+    float*  obs_f32;         /* [B, n_obs] out (either or both)                               */
+    double* obs_f64;         /* [B, n_obs] out                                                */
+    double* stats;           /* [OPFG_N_STATS] accumulated with atomics; caller zeroes        */
+} OpfgBatch;
+
+enum { OPFG_STAT_N = 0, OPFG_STAT_CONVERGED = 1, OPFG_STAT_VALID = 2, OPFG_STAT_SUM_REWARD = 3,
+       OPFG_STAT_SUM_REWARD_SQ = 4, OPFG_STAT_SUM_OBJECTIVE = 5, OPFG_STAT_SUM_PENALTY = 6,
+       OPFG_STAT_SUM_ITERS = 7, OPFG_STAT_VIOLATED0 = 8 /* +c: envs violating constraint c */,
+       OPFG_N_STATS = 24 };
+
+int         opfg_version(void);
+const char* opfg_last_error(void);
+
+int  opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out);
+void opfg_grid_destroy(OpfgGrid* grid);
+int  opfg_set_assembly(OpfgGrid* grid, const OpfgAssemblyDesc* desc);
+int  opfg_set_scoring(OpfgGrid* grid, const OpfgScoringDesc* desc);
+int  opfg_grid_info(const OpfgGrid* grid, OpfgGridInfo* out);
+/* host copies of the symbolic analysis, for inspection/tests: perm[n_nonref] = ppc bus of pivot k,
+ * level_ptr[n_levels+1]; either pointer may be NULL */
+int  opfg_grid_symbolic(const OpfgGrid* grid, int32_t* perm, int32_t* level_ptr);
+
+/* out[b, j] = U[0,1) double from Philox4x32-10, key = seed, counter = (j/2, first_env + b, stream);
+ * independent of how environments are sharded over GPUs */
+int opfg_philox_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id,
+                        int64_t n_env, int32_t n_cols, double* out, void* cuda_stream);
+
+/* OpfEnv._sample_from_range (opfgym/opf_env.py:266-284), fused with the generator:
+ * state[b, slots[j]] = (lo[j] + (hi[j] - lo[j]) * u(b, j)) / div[j], u as in opfg_philox_uniform.
+ * slots / lo / hi / div are DEVICE arrays of length n_cols. */
+int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env,
+                        int32_t n_cols, const int32_t* slots, const double* lo, const double* hi,
+                        const double* div, double* state, int32_t n_state, void* cuda_stream);
+
+int opfg_assemble(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
+int opfg_pf_solve(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
+int opfg_score(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
+/* assemble -> pf_solve -> score, back to back on the stream */
+int opfg_step(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
+
+/* number of kernel launches issued by this library since load (for bench accounting) */
+int64_t opfg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPFG_B200_H */

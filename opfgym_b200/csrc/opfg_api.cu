@@ -1,0 +1,575 @@
+// C ABI of libopfg_b200.so (see include/opfg_b200.h) and the CUDA kernels that
+// wrap the per-environment algorithms of opfg_core.h: one CTA per environment,
+// environment working set in shared memory, shared read-only grid tables read
+// through L1/L2.
+//
+// Built twice:  nvcc -gencode arch=compute_100a,code=sm_100a  -> the product;
+//               g++ -x c++ -DOPFG_HOSTSIM                       -> tests/hostsim only.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "opfg_core.h"
+#include "symbolic.hpp"
+
+#ifndef OPFG_HOSTSIM
+#include <cuda_runtime.h>
+#endif
+
+using namespace opfg;
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<int64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return -1;
+}
+
+// ------------------------------------------------------------- memory helpers
+void* dev_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 8;
+#ifdef OPFG_HOSTSIM
+    return calloc(1, bytes);
+#else
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, bytes);
+    return p;
+#endif
+}
+void dev_free(void* p) {
+#ifdef OPFG_HOSTSIM
+    free(p);
+#else
+    cudaFree(p);
+#endif
+}
+void dev_put(void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+#ifdef OPFG_HOSTSIM
+    memcpy(dst, src, bytes);
+#else
+    cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+#endif
+}
+
+}  // namespace
+
+struct OpfgGrid {
+    GridDev d{};
+    Symbolic sym;
+    OpfgGridDesc desc{};
+    std::vector<void*> allocs;
+    std::vector<int> gen_bus_host;
+    std::vector<double> gen_q_share_host;
+    int n_result_cells = 0;
+    double flops_score = 0;
+    bool has_assembly = false, has_scoring = false;
+    size_t smem_pf = 0, smem_score = 0;
+
+    template <class T>
+    const T* up(const std::vector<T>& v) {
+        void* p = dev_alloc(v.size() * sizeof(T));
+        if (!p) throw std::runtime_error("device allocation failed");
+        allocs.push_back(p);
+        dev_put(p, v.data(), v.size() * sizeof(T));
+        return (const T*)p;
+    }
+    template <class T>
+    const T* up(const T* src, size_t n) {
+        return up(std::vector<T>(src, src + n));
+    }
+    ~OpfgGrid() {
+        for (void* p : allocs) dev_free(p);
+    }
+};
+
+// ------------------------------------------------------------------- kernels
+#ifndef OPFG_HOSTSIM
+__global__ void k_branch_y(GridDev g) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < g.nbr) branch_admittance(g.br_param + 6 * (size_t)l, g.br_y + 8 * (size_t)l);
+}
+__global__ void k_ybus(GridDev g, double* y_val) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < g.nnz_y) ybus_entry(g, g.br_y, e, y_val + 2 * (size_t)e);
+}
+__global__ void k_philox(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols, double* out) {
+    const int pairs = (n_cols + 1) / 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_env * pairs) return;
+    const int64_t b = idx / pairs;
+    const int pr = (int)(idx % pairs);
+    double u0, u1;
+    philox_two_doubles(seed, first_env + (uint64_t)b, stream, (uint32_t)pr, &u0, &u1);
+    double* row = out + b * (int64_t)n_cols;
+    row[2 * pr] = u0;
+    if (2 * pr + 1 < n_cols) row[2 * pr + 1] = u1;
+}
+__global__ void k_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols,
+                                 const int* slots, const double* lo, const double* hi, const double* dv,
+                                 double* state, int n_state) {
+    const int pairs = (n_cols + 1) / 2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_env * pairs) return;
+    const int64_t b = idx / pairs;
+    const int pr = (int)(idx % pairs);
+    double u[2];
+    philox_two_doubles(seed, first_env + (uint64_t)b, stream, (uint32_t)pr, &u[0], &u[1]);
+    double* row = state + b * (int64_t)n_state;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = 2 * pr + h;
+        if (j < n_cols) row[slots[j]] = (lo[j] + (hi[j] - lo[j]) * u[h]) / dv[j];
+    }
+}
+template <int T>
+__global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
+    Ctx<T> cx{(int)threadIdx.x, nullptr};
+    const int64_t env = blockIdx.x;
+    env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
+                 B.sbus + env * (int64_t)g.nb * 2);
+}
+template <int T>
+__global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
+    extern __shared__ __align__(16) double sm[];
+    const int64_t env = blockIdx.x;
+    Ctx<T> cx{(int)threadIdx.x, sm + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1)};
+    env_pf_solve(g, cx, sm, B.sbus + env * (int64_t)g.nb * 2, nullptr, B.vm + env * (int64_t)g.nb,
+                 B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
+}
+template <int T>
+__global__ void __launch_bounds__(T) k_score(GridDev g, OpfgBatch B) {
+    extern __shared__ __align__(16) double sm[];
+    const int64_t env = blockIdx.x;
+    Ctx<T> cx{(int)threadIdx.x, sm + score_smem_doubles(g.nb, g.nbr, T) - 2 * (T / 32 + 1)};
+    env_score(g, cx, sm, B, env, nullptr);
+}
+
+#define OPFG_DISPATCH_T(T_, ...)                                     \
+    switch (T_) {                                                    \
+        case 32: { constexpr int TT = 32; __VA_ARGS__; break; }      \
+        case 64: { constexpr int TT = 64; __VA_ARGS__; break; }      \
+        case 128: { constexpr int TT = 128; __VA_ARGS__; break; }    \
+        case 256: { constexpr int TT = 256; __VA_ARGS__; break; }    \
+        default: return fail("unsupported threads_per_env %d", T_);  \
+    }
+#endif
+
+// ------------------------------------------------------------------- C ABI
+extern "C" {
+
+int opfg_version(void) { return OPFG_VERSION; }
+const char* opfg_last_error(void) { return g_error.c_str(); }
+int64_t opfg_launch_count(void) { return g_launches.load(); }
+
+int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
+    if (!desc || !out) return fail("null argument");
+    *out = nullptr;
+    if (desc->nb <= 0 || !desc->bus || !desc->branch || !desc->gen) return fail("empty grid tables");
+    if (desc->bus_cols < 10 || desc->gen_cols < 8 || desc->branch_cols < 11) return fail("ppc tables too narrow");
+#ifndef OPFG_HOSTSIM
+    {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+            return fail("no CUDA device: libopfg_b200 has no CPU path");
+    }
+#endif
+    try {
+        auto* G = new OpfgGrid();
+        G->desc = *desc;
+        const int nb = desc->nb, nbr = desc->nbr, ng = desc->ng;
+        const double base = desc->base_mva;
+        std::vector<int> type(nb);
+        std::vector<double> ysh(2 * (size_t)nb), va_ref(nb), vm_bus(nb);
+        int n_ref = 0;
+        for (int b = 0; b < nb; ++b) {
+            const double* row = desc->bus + (size_t)b * desc->bus_cols;
+            type[b] = (int)row[OPFG_BUS_TYPE];
+            if (type[b] < 1 || type[b] > 3) { delete G; return fail("bus %d has unsupported type %d", b, type[b]); }
+            n_ref += type[b] == 3;
+            ysh[2 * b] = row[OPFG_GS] / base;
+            ysh[2 * b + 1] = row[OPFG_BS] / base;
+            vm_bus[b] = row[OPFG_VM];
+            va_ref[b] = row[OPFG_VA] * M_PI / 180.0;
+        }
+        if (n_ref == 0) { delete G; return fail("grid has no reference bus"); }
+        // generator set-points: V0[gbus] = VG (pandapower _get_pf_variables_from_ppci)
+        std::vector<int> vgens(nb, 0);
+        G->gen_bus_host.resize(ng);
+        for (int gI = 0; gI < ng; ++gI) {
+            const double* row = desc->gen + (size_t)gI * desc->gen_cols;
+            const int bus = (int)row[OPFG_GEN_BUS];
+            if (bus < 0 || bus >= nb) { delete G; return fail("generator %d on invalid bus", gI); }
+            G->gen_bus_host[gI] = bus;
+            if (row[OPFG_GEN_STATUS] > 0 && type[bus] != 1) { vm_bus[bus] = row[OPFG_VG]; vgens[bus]++; }
+        }
+        G->gen_q_share_host.resize(ng);
+        for (int gI = 0; gI < ng; ++gI) {
+            const int bus = G->gen_bus_host[gI];
+            G->gen_q_share_host[gI] = vgens[bus] ? 1.0 / vgens[bus] : 0.0;
+        }
+        // branches
+        std::vector<BranchHost> active;
+        std::vector<double> br_param(6 * (size_t)nbr);
+        std::vector<int> br_f(nbr), br_t(nbr);
+        for (int l = 0; l < nbr; ++l) {
+            const double* row = desc->branch + (size_t)l * desc->branch_cols;
+            BranchHost bh;
+            bh.f = (int)row[OPFG_F_BUS]; bh.t = (int)row[OPFG_T_BUS];
+            if (bh.f < 0 || bh.f >= nb || bh.t < 0 || bh.t >= nb) { delete G; return fail("branch %d has invalid bus", l); }
+            bh.r = row[OPFG_BR_R]; bh.x = row[OPFG_BR_X]; bh.b = row[OPFG_BR_B];
+            bh.g = desc->branch_cols > OPFG_BR_G ? row[OPFG_BR_G] : 0.0;
+            bh.tap = row[OPFG_TAP]; bh.shift_deg = row[OPFG_SHIFT];
+            br_f[l] = bh.f; br_t[l] = bh.t;
+            double* p = &br_param[6 * (size_t)l];
+            const bool on = row[OPFG_BR_STATUS] != 0.0;
+            p[0] = bh.r; p[1] = bh.x; p[2] = bh.b; p[3] = bh.g; p[4] = bh.tap; p[5] = bh.shift_deg * M_PI / 180.0;
+            if (on) active.push_back(bh);
+            else { p[0] = 1e300; p[1] = 0; p[2] = 0; p[3] = 0; }   // open branch: zero admittance
+        }
+        // map active branches back to ppc rows for Ybus contributions
+        std::vector<int> active_row;
+        for (int l = 0; l < nbr; ++l)
+            if (desc->branch[(size_t)l * desc->branch_cols + OPFG_BR_STATUS] != 0.0) active_row.push_back(l);
+
+        int T = desc->threads_per_env;
+        Symbolic& s = G->sym;
+        analyse(nb, type, active, desc->ordering, T > 0 ? T : 32, s);
+        if (T <= 0) T = s.n_blocks <= 1200 ? 32 : (s.n_blocks <= 4000 ? 64 : 128);
+        for (size_t c = 0; c < s.yc_branch.size(); ++c)
+            if (s.yc_role[c] != 4) s.yc_branch[c] = active_row[s.yc_branch[c]];
+
+        GridDev& d = G->d;
+        d.nb = nb; d.n = s.n; d.n_levels = s.n_levels; d.n_blocks = s.n_blocks; d.n_fill = (int)s.fill_ids.size();
+        d.nnz_y = (int)s.y_col.size(); d.nbr = nbr; d.ng = ng; d.n_ref = n_ref; d.threads = T;
+        d.base_mva = base; d.tol = desc->tol_pu; d.max_iter = desc->max_iter; d.init_dc = desc->init_dc;
+        std::vector<unsigned char> type_int(nb);
+        std::vector<double> vm0(nb), va0(nb);
+        for (int i = 0; i < nb; ++i) {
+            const int bus = s.bus_of_int[i];
+            type_int[i] = (unsigned char)type[bus];
+            vm0[i] = vm_bus[bus];
+            va0[i] = type[bus] == 3 ? va_ref[bus] : (desc->init_dc ? 0.0 : va_ref[bus]);
+        }
+        d.bus_of_int = G->up(s.bus_of_int); d.int_of_bus = G->up(s.int_of_bus);
+        d.type_int = G->up(type_int); d.vm0_int = G->up(vm0); d.va0_int = G->up(va0);
+        d.level_ptr = G->up(s.level_ptr); d.fill_ids = G->up(s.fill_ids);
+        d.dp_ptr = G->up(s.dp_ptr); d.dp_l = G->up(s.dp_l); d.dp_w = G->up(s.dp_w); d.dp_m = G->up(s.dp_m);
+        d.off_ptr = G->up(s.off_ptr); d.off_tgt = G->up(s.off_tgt); d.off_piv = G->up(s.off_piv);
+        d.op_ptr = G->up(s.op_ptr); d.op_l = G->up(s.op_l); d.op_w = G->up(s.op_w);
+        d.up_ptr = G->up(s.up_ptr); d.up_w = G->up(s.up_w); d.up_j = G->up(s.up_j);
+        d.y_ptr = G->up(s.y_ptr); d.y_col = G->up(s.y_col); d.y_blk = G->up(s.y_blk); d.y_diag = G->up(s.y_diag);
+        d.yc_ptr = G->up(s.yc_ptr); d.yc_branch = G->up(s.yc_branch); d.yc_role = G->up(s.yc_role);
+        d.br_param = G->up(br_param); d.bus_ysh = G->up(ysh); d.br_f = G->up(br_f); d.br_t = G->up(br_t);
+        d.br_y = (double*)G->up(std::vector<double>(8 * (size_t)nbr, 0.0));
+        double* y_val = (double*)G->up(std::vector<double>(2 * s.y_col.size(), 0.0));
+        d.y_val = y_val;
+
+        // DC start: scalar factor of B' on the same schedule + constant part of its rhs
+        std::vector<double> dc_val, dc_rhs0(s.n, 0.0);
+        bool dc_ok = true;
+        factor_dc(s, active, dc_val, dc_ok);
+        if (desc->init_dc && !dc_ok) { delete G; return fail("DC matrix B' is singular"); }
+        for (const auto& br : active) {
+            const double ratio = br.tap == 0.0 ? 1.0 : br.tap;
+            const double b = 1.0 / br.x / ratio;
+            const double pfinj = b * (-br.shift_deg * M_PI / 180.0);
+            const int f = s.int_of_bus[br.f], t = s.int_of_bus[br.t];
+            if (f < s.n) dc_rhs0[f] -= pfinj;
+            if (t < s.n) dc_rhs0[t] += pfinj;
+            // - B'[k, ref] * theta_ref
+            if (f < s.n && t >= s.n) dc_rhs0[f] += b * va_ref[br.t];
+            if (t < s.n && f >= s.n) dc_rhs0[t] += b * va_ref[br.f];
+        }
+        for (int k = 0; k < s.n; ++k) dc_rhs0[k] -= ysh[2 * s.bus_of_int[k]];
+        d.dc_val = G->up(dc_val); d.dc_rhs0 = G->up(dc_rhs0);
+
+        G->smem_pf = pf_smem_doubles(s.n_blocks, s.n, nb, T) * sizeof(double);
+        G->smem_score = score_smem_doubles(nb, nbr, T) * sizeof(double);
+        if (G->smem_pf > 227 * 1024) { delete G; return fail("grid needs %zu B shared memory per environment (> 227 KB)", G->smem_pf); }
+
+        // kernel 1a: branch admittances and Ybus values, computed on the device
+#ifdef OPFG_HOSTSIM
+        for (int l = 0; l < nbr; ++l) branch_admittance(d.br_param + 6 * (size_t)l, d.br_y + 8 * (size_t)l);
+        for (int e = 0; e < d.nnz_y; ++e) ybus_entry(d, d.br_y, e, y_val + 2 * (size_t)e);
+#else
+        k_branch_y<<<(nbr + 127) / 128, 128>>>(d);
+        k_ybus<<<(d.nnz_y + 127) / 128, 128>>>(d, y_val);
+        g_launches += 2;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { delete G; return fail("Ybus assembly failed: %s", cudaGetErrorString(e)); }
+#endif
+        *out = G;
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail("opfg_grid_create: %s", ex.what());
+    }
+}
+
+void opfg_grid_destroy(OpfgGrid* grid) { delete grid; }
+
+int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
+    if (!G || !a) return fail("null argument");
+    try {
+        GridDev& d = G->d;
+        d.n_state = a->n_state; d.n_const = a->n_const; d.n_act = a->n_act; d.n_inj = a->n_inj;
+        d.consts = G->up(a->consts, a->n_const);
+        auto check_ref = [&](const int* r, int n, const char* what) {
+            for (int i = 0; i < n; ++i)
+                if (r[i] >= a->n_state || -r[i] - 1 >= a->n_const) throw std::runtime_error(std::string("reference out of range in ") + what);
+        };
+        check_ref(a->act_lo, a->n_act, "act_lo"); check_ref(a->act_hi, a->n_act, "act_hi");
+        check_ref(a->act_div, a->n_act, "act_div");
+        check_ref(a->inj_p, a->n_inj, "inj_p"); check_ref(a->inj_q, a->n_inj, "inj_q"); check_ref(a->inj_coef, a->n_inj, "inj_coef");
+        for (int i = 0; i < a->n_act; ++i)
+            if (a->act_slot[i] < 0 || a->act_slot[i] >= a->n_state) throw std::runtime_error("act_slot out of range");
+        d.act_slot = G->up(a->act_slot, a->n_act);
+        d.act_lo = G->up(a->act_lo, a->n_act); d.act_hi = G->up(a->act_hi, a->n_act);
+        d.act_div = G->up(a->act_div, a->n_act); d.act_kind = G->up(a->act_kind, a->n_act);
+        d.act_clamp_lo = a->act_clamp_lo ? G->up(a->act_clamp_lo, a->n_act) : nullptr;
+        d.act_clamp_hi = a->act_clamp_hi ? G->up(a->act_clamp_hi, a->n_act) : nullptr;
+        // CSR by bus, list order preserved (deterministic summation order)
+        std::vector<int> ptr(d.nb + 1, 0), p(a->n_inj), q(a->n_inj), c(a->n_inj);
+        for (int e = 0; e < a->n_inj; ++e) {
+            if (a->inj_bus[e] < 0 || a->inj_bus[e] >= d.nb) throw std::runtime_error("injection on invalid bus");
+            ptr[a->inj_bus[e] + 1]++;
+        }
+        for (int b = 0; b < d.nb; ++b) ptr[b + 1] += ptr[b];
+        std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+        for (int e = 0; e < a->n_inj; ++e) {
+            const int at = fill[a->inj_bus[e]]++;
+            p[at] = a->inj_p[e]; q[at] = a->inj_q[e]; c[at] = a->inj_coef[e];
+        }
+        d.inj_ptr = G->up(ptr); d.inj_p = G->up(p); d.inj_q = G->up(q); d.inj_coef = G->up(c);
+        G->has_assembly = true;
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail("opfg_set_assembly: %s", ex.what());
+    }
+}
+
+int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
+    if (!G || !sc) return fail("null argument");
+    if (!G->has_assembly) return fail("call opfg_set_assembly first (it defines the state layout)");
+    try {
+        GridDev& d = G->d;
+        const int nbr = d.nbr, ng = d.ng;
+        d.n_pp_bus = sc->n_pp_bus;
+        d.pp_lookup = G->up(sc->pp_bus_lookup, sc->n_pp_bus);
+        d.res_vm_slot = sc->res_bus_vm_slot; d.res_va_slot = sc->res_bus_va_slot;
+        d.br_loading_slot = G->up(sc->branch_loading_slot, nbr);
+        d.br_flow_slot = G->up(sc->branch_flow_slot, nbr);
+        d.rate_f = G->up(sc->rate_f, nbr); d.rate_t = G->up(sc->rate_t, nbr);
+        d.gen_bus = G->up(G->gen_bus_host);
+        d.gen_q_share = G->up(G->gen_q_share_host);
+        d.gen_p_slot = G->up(sc->gen_p_slot, ng); d.gen_q_slot = G->up(sc->gen_q_slot, ng);
+        d.n_con = sc->n_constraints;
+        const int n_el = sc->n_constraints ? sc->con_ptr[sc->n_constraints] : 0;
+        d.con_ptr = G->up(sc->con_ptr, sc->n_constraints + 1);
+        d.con_value = G->up(sc->con_value, n_el); d.con_value_scale = G->up(sc->con_value_scale, n_el);
+        d.con_min = G->up(sc->con_min, n_el); d.con_max = G->up(sc->con_max, n_el);
+        d.con_bound_mul = G->up(sc->con_bound_mul, n_el);
+        d.con_autoscale = G->up(sc->con_autoscale, d.n_con); d.con_worst = G->up(sc->con_worst_case, d.n_con);
+        d.con_pfactor = G->up(sc->con_penalty_factor, d.n_con); d.con_ppower = G->up(sc->con_penalty_power, d.n_con);
+        d.con_pcount = G->up(sc->con_count_penalty, d.n_con);
+        d.n_poly = sc->n_poly; d.n_pwl = sc->n_pwl; d.n_pwl_seg = sc->n_pwl_seg;
+        d.poly_p = G->up(sc->poly_p, d.n_poly); d.poly_q = G->up(sc->poly_q, d.n_poly);
+        d.poly_p_mul = G->up(sc->poly_p_mul, d.n_poly); d.poly_q_mul = G->up(sc->poly_q_mul, d.n_poly);
+        d.poly_coef = G->up(sc->poly_coef, 6 * (size_t)d.n_poly);
+        d.pwl_v = G->up(sc->pwl_v, d.n_pwl); d.pwl_v_mul = G->up(sc->pwl_v_mul, d.n_pwl);
+        d.pwl_seg = G->up(sc->pwl_seg, 3 * (size_t)d.n_pwl * d.n_pwl_seg);
+        d.reward_kind = sc->reward_kind; d.penalty_weight = sc->penalty_weight;
+        d.clip_lo = sc->clip_lo; d.clip_hi = sc->clip_hi;
+        d.obj_factor = sc->objective_factor; d.obj_bias = sc->objective_bias;
+        d.pen_factor = sc->penalty_factor; d.pen_bias = sc->penalty_bias;
+        d.valid_reward = sc->valid_reward; d.invalid_penalty = sc->invalid_penalty;
+        d.invalid_obj_share = sc->invalid_objective_share;
+        d.n_obs = sc->n_obs;
+        d.obs_ref = G->up(sc->obs_ref, sc->n_obs);
+        int cells = 0;
+        if (d.res_vm_slot >= 0) cells += d.n_pp_bus;
+        if (d.res_va_slot >= 0) cells += d.n_pp_bus;
+        for (int l = 0; l < nbr; ++l) cells += (sc->branch_loading_slot[l] >= 0) + 4 * (sc->branch_flow_slot[l] >= 0);
+        for (int gI = 0; gI < ng; ++gI) cells += (sc->gen_p_slot[gI] >= 0) + (sc->gen_q_slot[gI] >= 0);
+        G->n_result_cells = cells;
+        G->flops_score = 60.0 * nbr + 30.0 * d.nb + 10.0 * n_el + 14.0 * d.n_poly + 20.0 * d.n_pwl * d.n_pwl_seg + 40.0;
+        G->has_scoring = true;
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail("opfg_set_scoring: %s", ex.what());
+    }
+}
+
+int opfg_grid_info(const OpfgGrid* G, OpfgGridInfo* o) {
+    if (!G || !o) return fail("null argument");
+    const GridDev& d = G->d;
+    memset(o, 0, sizeof *o);
+    o->nb = d.nb; o->n_nonref = d.n; o->nnz_y = d.nnz_y; o->n_blocks = d.n_blocks; o->n_fill_blocks = d.n_fill;
+    o->n_levels = d.n_levels; o->threads_per_env = d.threads;
+    o->smem_bytes_pf = (int)G->smem_pf; o->smem_bytes_score = (int)G->smem_score;
+    o->n_state = d.n_state; o->n_const = d.n_const; o->n_act = d.n_act; o->n_obs = d.n_obs; o->n_constraints = d.n_con;
+    o->flops_per_iter = G->sym.flops_per_iter; o->lu_flops = G->sym.lu_flops; o->flops_score = G->flops_score;
+    // algorithmic HBM bytes of one env step: read action + input state, write results, per-constraint
+    // metrics, reward/objective/penalty/cost, flags and the f32 observation
+    const int n_in = d.n_state - G->n_result_cells;
+    o->bytes_per_step = 8.0 * (n_in + d.n_act) + 8.0 * (2.0 * d.nb + G->n_result_cells) + 17.0 * d.n_con + 8.0 * 4 + 5
+                        + 4.0 * d.n_obs;
+    return 0;
+}
+
+int opfg_grid_symbolic(const OpfgGrid* G, int32_t* perm, int32_t* level_ptr) {
+    if (!G) return fail("null argument");
+    if (perm) for (int k = 0; k < G->sym.n; ++k) perm[k] = G->sym.bus_of_int[k];
+    if (level_ptr) for (int l = 0; l <= G->sym.n_levels; ++l) level_ptr[l] = G->sym.level_ptr[l];
+    return 0;
+}
+
+int opfg_philox_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env, int32_t n_cols,
+                        double* out, void* cuda_stream) {
+    if (!out || n_env < 0 || n_cols < 0) return fail("bad argument");
+    if (n_env == 0 || n_cols == 0) return 0;
+    const int pairs = (n_cols + 1) / 2;
+#ifdef OPFG_HOSTSIM
+    (void)cuda_stream;
+    for (int64_t b = 0; b < n_env; ++b)
+        for (int pr = 0; pr < pairs; ++pr) {
+            double u0, u1;
+            philox_two_doubles(seed, first_env + (uint64_t)b, stream_id, (uint32_t)pr, &u0, &u1);
+            out[b * n_cols + 2 * pr] = u0;
+            if (2 * pr + 1 < n_cols) out[b * n_cols + 2 * pr + 1] = u1;
+        }
+#else
+    const int64_t total = n_env * pairs;
+    k_philox<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(seed, first_env, stream_id, n_env, n_cols, out);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("philox launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env, int32_t n_cols,
+                        const int32_t* slots, const double* lo, const double* hi, const double* dv, double* state,
+                        int32_t n_state, void* cuda_stream) {
+    if (!slots || !lo || !hi || !dv || !state || n_env < 0 || n_cols < 0) return fail("bad argument");
+    if (n_env == 0 || n_cols == 0) return 0;
+    const int pairs = (n_cols + 1) / 2;
+#ifdef OPFG_HOSTSIM
+    (void)cuda_stream;
+    for (int64_t b = 0; b < n_env; ++b)
+        for (int pr = 0; pr < pairs; ++pr) {
+            double u[2];
+            philox_two_doubles(seed, first_env + (uint64_t)b, stream_id, (uint32_t)pr, &u[0], &u[1]);
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * pr + h;
+                if (j < n_cols) state[b * (int64_t)n_state + slots[j]] = (lo[j] + (hi[j] - lo[j]) * u[h]) / dv[j];
+            }
+        }
+#else
+    const int64_t total = n_env * pairs;
+    k_sample_uniform<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        seed, first_env, stream_id, n_env, n_cols, slots, lo, hi, dv, state, n_state);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("sample launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
+    if (!G || !B) return fail("null argument");
+    if (!G->has_assembly) return fail("opfg_set_assembly was not called");
+    if (!B->state || !B->sbus || (G->d.n_act > 0 && !B->actions)) return fail("opfg_assemble needs actions, state, sbus");
+    if (B->n_env <= 0) return 0;
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    Ctx<1> cx;
+    for (int64_t env = 0; env < B->n_env; ++env)
+        env_assemble(G->d, cx, B->actions ? B->actions + env * G->d.n_act : nullptr,
+                     B->state + env * (int64_t)G->d.n_state, B->sbus + env * (int64_t)G->d.nb * 2);
+#else
+    k_assemble<32><<<(unsigned)B->n_env, 32, 0, (cudaStream_t)stream>>>(G->d, *B);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("assemble launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
+    if (!G || !B) return fail("null argument");
+    if (!B->sbus || !B->vm || !B->va || !B->converged || !B->iterations) return fail("opfg_pf_solve needs sbus, vm, va, converged, iterations");
+    if (B->n_env <= 0) return 0;
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    Ctx<1> cx;
+    std::vector<double> sm(pf_smem_doubles(G->d.n_blocks, G->d.n, G->d.nb, 32));
+    for (int64_t env = 0; env < B->n_env; ++env)
+        env_pf_solve(G->d, cx, sm.data(), B->sbus + env * (int64_t)G->d.nb * 2, nullptr, B->vm + env * (int64_t)G->d.nb,
+                     B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);
+#else
+    const size_t smem = G->smem_pf;
+    OPFG_DISPATCH_T(G->d.threads, {
+        static size_t attr_smem = 48 * 1024;
+        if (smem > attr_smem) {
+            cudaFuncSetAttribute(k_pf<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_smem = smem;
+        }
+        k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
+    });
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("pf_solve launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
+    if (!G || !B) return fail("null argument");
+    if (!G->has_scoring) return fail("opfg_set_scoring was not called");
+    if (!B->state || !B->sbus || !B->vm || !B->va || !B->converged) return fail("opfg_score needs state, sbus, vm, va, converged");
+    if (B->n_env <= 0) return 0;
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    Ctx<1> cx;
+    std::vector<double> sm(score_smem_doubles(G->d.nb, G->d.nbr, 32));
+    for (int64_t env = 0; env < B->n_env; ++env) env_score(G->d, cx, sm.data(), *B, env, nullptr);
+#else
+    const size_t smem = G->smem_score;
+    OPFG_DISPATCH_T(G->d.threads, {
+        static size_t attr_smem = 48 * 1024;
+        if (smem > attr_smem) {
+            cudaFuncSetAttribute(k_score<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_smem = smem;
+        }
+        k_score<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
+    });
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("score launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_step(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
+    int rc = opfg_assemble(G, B, stream);
+    if (rc) return rc;
+    rc = opfg_pf_solve(G, B, stream);
+    if (rc) return rc;
+    return opfg_score(G, B, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Torch-facing handle on one compiled grid + one batch of environment buffers.
+
+PyTorch is plumbing here: it owns the device memory and the stream.  Every
+numeric step is a launch of a hand-written kernel in ``libopfg_b200.so`` through
+the C ABI (``include/opfg_b200.h``).  There is no CPU path: constructing an
+``Engine`` without a CUDA device, or without the built library, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .compiler import EnvProgram, fill_descs
+
+
+class Engine:
+    def __init__(self, program: EnvProgram, num_envs: int, device=None,
+                 tolerance_mva: float = 1e-8, max_iteration: int = 10, init: str = "dc",
+                 enforce_q_lims: bool = True, threads_per_env: int = 0, ordering: int = 0,
+                 obs_dtype: str = "float32", lib=None):
+        self.program = program
+        self.num_envs = int(num_envs)
+        self.lib = lib if lib is not None else capi.load()
+        self._setup_device(device)
+        gd, ad, sd, keep = fill_descs(
+            capi, program, tol_pu=tolerance_mva / program.ppc.base_mva,
+            max_iter=max_iteration, init_dc=(init == "dc"), enforce_q_lims=enforce_q_lims,
+            threads_per_env=threads_per_env, ordering=ordering)
+        handle = C.c_void_p()
+        capi.check(self.lib, self.lib.opfg_grid_create(C.byref(gd), C.byref(handle)))
+        self.handle = handle
+        capi.check(self.lib, self.lib.opfg_set_assembly(handle, C.byref(ad)))
+        capi.check(self.lib, self.lib.opfg_set_scoring(handle, C.byref(sd)))
+        del keep
+        info = capi.GridInfo()
+        capi.check(self.lib, self.lib.opfg_grid_info(handle, C.byref(info)))
+        self.info = {name: getattr(info, name) for name, _ in capi.GridInfo._fields_}
+
+        B, nb = self.num_envs, program.ppc.bus.shape[0]
+        nc, n_state = len(program.constraints), program.layout.n
+        self.obs_dtype = obs_dtype
+        self.actions = self._zeros((B, max(program.n_act, 1)), "float64")
+        self.state = self._from_numpy(np.tile(program.initial_state, (B, 1)))
+        self.sbus = self._zeros((B, nb, 2), "float64")
+        self.vm = self._zeros((B, nb), "float64")
+        self.va = self._zeros((B, nb), "float64")
+        self.converged = self._zeros((B,), "uint8")
+        self.iterations = self._zeros((B,), "int32")
+        self.reward = self._zeros((B,), "float64")
+        self.objective = self._zeros((B,), "float64")
+        self.penalty = self._zeros((B,), "float64")
+        self.cost = self._zeros((B,), "float64")
+        self.valids = self._zeros((B, max(nc, 1)), "uint8")
+        self.violations = self._zeros((B, max(nc, 1)), "float64")
+        self.penalties = self._zeros((B, max(nc, 1)), "float64")
+        self.obs = self._zeros((B, max(program.n_obs, 1)), obs_dtype)
+        self.stats = self._zeros((capi.N_STATS,), "float64")
+        self.n_constraints = nc
+        self.batch = capi.Batch(
+            n_env=B, actions=self._ptr(self.actions), state=self._ptr(self.state),
+            sbus=self._ptr(self.sbus), vm=self._ptr(self.vm), va=self._ptr(self.va),
+            converged=self._ptr(self.converged), iterations=self._ptr(self.iterations),
+            reward=self._ptr(self.reward), objective=self._ptr(self.objective),
+            penalty=self._ptr(self.penalty), cost=self._ptr(self.cost),
+            valids=self._ptr(self.valids), violations=self._ptr(self.violations),
+            penalties=self._ptr(self.penalties),
+            obs_f32=self._ptr(self.obs) if obs_dtype == "float32" else None,
+            obs_f64=self._ptr(self.obs) if obs_dtype == "float64" else None,
+            stats=self._ptr(self.stats))
+
+    # ------------------------------------------------------- device plumbing (torch)
+    def _setup_device(self, device):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("opfgym_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device(device if device is not None else "cuda:0")
+        torch.cuda.set_device(self.device)
+
+    def _zeros(self, shape, dtype):
+        return self.torch.zeros(shape, dtype=getattr(self.torch, dtype), device=self.device)
+
+    def _from_numpy(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+
+    def _ptr(self, t):
+        return C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------- launches
+    def column(self, table: str, column: str):
+        """View ``S[:, slice]`` of one (table, column): shape [B, n_rows]."""
+        return self.state[:, self.program.layout.slice(table, column)]
+
+    def sample_uniform(self, slots, lo, hi, div, seed: int, first_env: int, stream_id: int):
+        n = int(slots.shape[0])
+        capi.check(self.lib, self.lib.opfg_sample_uniform(
+            seed, first_env, stream_id, self.num_envs, n, self._ptr(slots), self._ptr(lo),
+            self._ptr(hi), self._ptr(div), self._ptr(self.state), self.program.layout.n,
+            self._stream()))
+
+    def philox_uniform(self, out, seed: int, first_env: int, stream_id: int):
+        capi.check(self.lib, self.lib.opfg_philox_uniform(
+            seed, first_env, stream_id, out.shape[0], out.shape[1], self._ptr(out), self._stream()))
+
+    def assemble(self):
+        capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(self.batch), self._stream()))
+
+    def pf_solve(self):
+        capi.check(self.lib, self.lib.opfg_pf_solve(self.handle, C.byref(self.batch), self._stream()))
+
+    def score(self):
+        capi.check(self.lib, self.lib.opfg_score(self.handle, C.byref(self.batch), self._stream()))
+
+    def step(self):
+        """assemble -> pf_solve -> score on the current stream (3 launches, no sync)."""
+        capi.check(self.lib, self.lib.opfg_step(self.handle, C.byref(self.batch), self._stream()))
+
+    def symbolic(self):
+        n, nl = self.info["n_nonref"], self.info["n_levels"]
+        perm = np.zeros(n, np.int32)
+        lvl = np.zeros(nl + 1, np.int32)
+        capi.check(self.lib, self.lib.opfg_grid_symbolic(
+            self.handle, perm.ctypes.data_as(C.POINTER(C.c_int32)),
+            lvl.ctypes.data_as(C.POINTER(C.c_int32))))
+        return perm, lvl
+
+    def launch_count(self) -> int:
+        return int(self.lib.opfg_launch_count())
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.opfg_grid_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
