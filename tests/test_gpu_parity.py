@@ -1,0 +1,81 @@
+"""GPU parity tier: the CUDA path (through the C ABI) against the CPU oracle on
+identical seeded inputs.  Tolerances are BASELINE.json's: converged flag exact,
+|V| and angle 1e-6 pu/rad, loading 1e-4 %, reward 1e-6 relative."""
+import numpy as np
+import pytest
+
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(vm=1e-6, va=1e-6, loading=1e-4, reward_rel=1e-6)
+
+
+def _check(worst):
+    assert worst["flag_mismatch"] == 0, worst
+    assert worst["valid_mismatch"] == 0, worst
+    assert worst["iter_mismatch"] == 0, worst
+    for k, tol in TOL.items():
+        assert worst[k] <= tol, (k, worst)
+    assert worst["violation"] <= 1e-6 and worst["obs"] <= 1e-6, worst
+
+
+@pytest.mark.parametrize("name", ["1-MV-semiurb--1-sw", "1-MV-rural--0-sw", "1-HV-urban--0-sw"])
+def test_step_matches_oracle(cuda_lib, name):
+    import torch
+    from opfgym_b200.engine import Engine
+    case = common.make_case(name, tight=(name == "1-MV-rural--0-sw"))
+    eng = Engine(case.program, 256, obs_dtype="float64")
+    common.randomize(case, eng, seed=1)
+    eng.step()
+    torch.cuda.synchronize()
+    assert int(eng.converged.sum()) == 256
+    _check(common.compare_with_oracle(case, eng, envs=range(0, 256, 8)))
+
+
+def test_position_independence(cuda_lib):
+    """results do not depend on the env's slot in the batch."""
+    import torch
+    from opfgym_b200.engine import Engine
+    case = common.make_case("1-MV-semiurb--1-sw")
+    eng = Engine(case.program, 128, obs_dtype="float64")
+    common.randomize(case, eng, seed=2)
+    eng.state[64:] = eng.state[:64].flip(0)
+    eng.actions[64:] = eng.actions[:64].flip(0)
+    eng.step()
+    torch.cuda.synchronize()
+    assert torch.equal(eng.vm[:64], eng.vm[64:].flip(0))
+    assert torch.equal(eng.reward[:64], eng.reward[64:].flip(0))
+    assert torch.equal(eng.obs[:64], eng.obs[64:].flip(0))
+
+
+def test_mismatch_below_tolerance_full_batch(cuda_lib):
+    """Size-independent property at BASELINE batch size: every env flagged
+    converged satisfies ||S - V conj(Ybus V)||inf < tol, recomputed with torch."""
+    import torch
+    from opfgym_b200.engine import Engine
+    from oracle import pf
+    case = common.make_case("1-MV-semiurb--1-sw")
+    B = 32768
+    eng = Engine(case.program, B)
+    rng = np.random.default_rng(3)
+    for t, c in common.SAMPLED:
+        df = case.net[t]
+        if len(df):
+            lo = torch.tensor(df["min_min_" + c].to_numpy() / df.scaling.to_numpy(), device="cuda")
+            hi = torch.tensor(df["max_max_" + c].to_numpy() / df.scaling.to_numpy(), device="cuda")
+            eng.column(t, c).copy_(lo + (hi - lo) * torch.rand(B, len(df), device="cuda", dtype=torch.float64))
+    eng.actions.uniform_(0, 1)
+    eng.step()
+    torch.cuda.synchronize()
+    assert int(eng.converged.sum()) == B
+    ppc = case.program.ppc
+    ybus, _, _ = pf.make_ybus(ppc.base_mva, ppc.bus, ppc.branch)
+    Y = torch.tensor(ybus.toarray(), device="cuda", dtype=torch.complex128)
+    V = torch.polar(eng.vm, eng.va)
+    S = V * torch.conj(V @ Y.T)
+    sb = torch.view_as_complex(eng.sbus)
+    mis = S - sb
+    nonref = torch.tensor(ppc.bus[:, 1] != 3, device="cuda")
+    worst = torch.view_as_real(mis[:, nonref]).abs().max().item()
+    assert worst < 1e-8, worst
