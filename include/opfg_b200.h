@@ -150,7 +150,7 @@ typedef struct {
 /* device buffers of one batch (any pointer may be NULL if the stage that needs it is not run) */
 typedef struct {
     int64_t n_env;
-    const double* actions;   /* [B, n_act]   in  (opfg_assemble)                              */
+    const double* actions;   /* [B, n_act]   in  (opfg_assemble; NULL = keep set-points, Sbus only)   */
     double* state;           /* [B, n_state] in/out                                           */
     double* sbus;            /* [B, nb, 2]   complex bus injections, ppc bus order, p.u.      */
     double* vm;              /* [B, nb]      out, p.u.                                        */
@@ -201,6 +201,8 @@ int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
 int opfg_assemble(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 int opfg_pf_solve(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 int opfg_score(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
+/* observation gather only (OpfEnv._get_obs after reset, opf_env.py:218): obs[b, j] = value(obs_ref[j]) */
+int opfg_observe(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 /* assemble -> pf_solve -> score, back to back on the stream */
 int opfg_step(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 

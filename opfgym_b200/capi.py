@@ -94,6 +94,7 @@ PROTOTYPES = {
     "opfg_assemble": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_pf_solve": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_score": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "opfg_observe": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_launch_count": (C.c_int64, []),
 }

@@ -158,6 +158,16 @@ __global__ void __launch_bounds__(T) k_score(GridDev g, OpfgBatch B) {
     env_score(g, cx, sm, B, env, nullptr);
 }
 
+__global__ void k_observe(GridDev g, OpfgBatch B) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B.n_env * g.n_obs) return;
+    const int64_t env = idx / g.n_obs;
+    const int j = (int)(idx % g.n_obs);
+    const double v = ref_val(g, B.state + env * (int64_t)g.n_state, g.obs_ref[j]);
+    if (B.obs_f32) B.obs_f32[idx] = (float)v;
+    if (B.obs_f64) B.obs_f64[idx] = v;
+}
+
 #define OPFG_DISPATCH_T(T_, ...)                                     \
     switch (T_) {                                                    \
         case 32: { constexpr int TT = 32; __VA_ARGS__; break; }      \
@@ -492,7 +502,7 @@ int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
 int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (!G || !B) return fail("null argument");
     if (!G->has_assembly) return fail("opfg_set_assembly was not called");
-    if (!B->state || !B->sbus || (G->d.n_act > 0 && !B->actions)) return fail("opfg_assemble needs actions, state, sbus");
+    if (!B->state || !B->sbus) return fail("opfg_assemble needs state and sbus (actions == NULL: Sbus scatter only)");
     if (B->n_env <= 0) return 0;
 #ifdef OPFG_HOSTSIM
     (void)stream;
@@ -560,6 +570,29 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("score launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_observe(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
+    if (!G || !B) return fail("null argument");
+    if (!G->has_scoring) return fail("opfg_set_scoring was not called");
+    if (!B->state || (!B->obs_f32 && !B->obs_f64)) return fail("opfg_observe needs state and an obs buffer");
+    if (B->n_env <= 0 || G->d.n_obs == 0) return 0;
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    for (int64_t env = 0; env < B->n_env; ++env)
+        for (int j = 0; j < G->d.n_obs; ++j) {
+            const double v = ref_val(G->d, B->state + env * (int64_t)G->d.n_state, G->d.obs_ref[j]);
+            if (B->obs_f32) B->obs_f32[env * G->d.n_obs + j] = (float)v;
+            if (B->obs_f64) B->obs_f64[env * G->d.n_obs + j] = v;
+        }
+#else
+    const int64_t total = B->n_env * G->d.n_obs;
+    k_observe<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(G->d, *B);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("observe launch: %s", cudaGetErrorString(e));
 #endif
     return 0;
 }

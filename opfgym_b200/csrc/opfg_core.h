@@ -180,7 +180,7 @@ OPFG_HD void ybus_entry(const GridDev& g, const double* br_y, int e, double* out
 template <class C>
 OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, double* S, double* sbus) {
     const int T = cx.nthreads();
-    for (int j = cx.tid; j < g.n_act; j += T) {
+    for (int j = cx.tid; act != nullptr && j < g.n_act; j += T) {
         double a = act[j];
         a = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);               // opf_env.py:429
         const double lo = ref_val(g, S, g.act_lo[j]), hi = ref_val(g, S, g.act_hi[j]);

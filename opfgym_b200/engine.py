@@ -83,7 +83,7 @@ class Engine:
         return self.torch.zeros(shape, dtype=getattr(self.torch, dtype), device=self.device)
 
     def _from_numpy(self, a):
-        return self.torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+        return self.torch.from_numpy(np.array(a, copy=True, order="C")).to(self.device)
 
     def _ptr(self, t):
         return C.c_void_p(t.data_ptr())
@@ -107,14 +107,22 @@ class Engine:
         capi.check(self.lib, self.lib.opfg_philox_uniform(
             seed, first_env, stream_id, out.shape[0], out.shape[1], self._ptr(out), self._stream()))
 
-    def assemble(self):
-        capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(self.batch), self._stream()))
+    def assemble(self, apply_actions: bool = True):
+        """Kernel 1.  ``apply_actions=False`` only re-scatters Sbus from the current cells."""
+        batch = self.batch
+        if not apply_actions:
+            batch = capi.Batch.from_buffer_copy(self.batch)
+            batch.actions = None
+        capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(batch), self._stream()))
 
     def pf_solve(self):
         capi.check(self.lib, self.lib.opfg_pf_solve(self.handle, C.byref(self.batch), self._stream()))
 
     def score(self):
         capi.check(self.lib, self.lib.opfg_score(self.handle, C.byref(self.batch), self._stream()))
+
+    def observe(self):
+        capi.check(self.lib, self.lib.opfg_observe(self.handle, C.byref(self.batch), self._stream()))
 
     def step(self):
         """assemble -> pf_solve -> score on the current stream (3 launches, no sync)."""

@@ -1,0 +1,504 @@
+"""``BatchedOpfEnv``: thousands of instances of one OPF environment stepping in
+lock-step on one GPU, behind the constructor and method surface of the
+reference ``OpfEnv`` (``opfgym/opf_env.py:26-175``) and a gymnasium-style
+vector-env interface (``num_envs``, ``single_*_space``, batched ``reset`` /
+``step``, same-step auto-reset).
+
+What happens where (reference ``step`` call stack):
+
+===========================  ====================================================
+reference (per env, pandas)  here (all envs, device)
+===========================  ====================================================
+``_sampling``                ``opfg_sample_uniform`` / profile gather + the
+                             subclass hook written as tensor ops on column views
+``_apply_actions``           kernel 1 (``opfg_assemble``)
+``pp.runpp``                 kernels 2-4 (``opfg_pf_solve``)
+``calculate_reward``         kernel 5 (``opfg_score``)
+``_get_obs``                 kernel 5 epilogue / ``opfg_observe``
+===========================  ====================================================
+
+Differences from the reference, on purpose: unknown keyword arguments raise
+instead of being swallowed; features that the reference itself
+ships broken (``add_time_obs``, A.6 quirk 1) raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from . import constraints as constraints_mod
+from . import reward as reward_mod
+from .compiler import Compiler
+from .data_split import define_test_train_split
+from .engine import Engine
+from .ppc import PpcBuilder
+from .spaces import Box, batch_space, get_obs_and_state_space
+
+_SPLIT_KWARGS = {"test_share", "random_test_steps", "validation_share", "random_validation_steps"}
+
+
+_BUILD_KWARGS = ("voltage_band", "max_loading", "storage_scaling", "n_profile_steps")
+
+
+def split_build_kwargs(kwargs: dict) -> dict:
+    """Pop the keyword arguments that the reference forwards through ``*args, **kwargs``
+    to ``build_simbench_net`` (opfgym/simbench/build_simbench_net.py:5-7)."""
+    return {k: kwargs.pop(k) for k in _BUILD_KWARGS if k in kwargs and kwargs[k] is not None}
+
+
+class PowerFlowNotAvailable(Exception):
+    pass
+
+
+class BatchedOpfEnv:
+    metadata = {"autoreset_mode": "same_step"}
+
+    def __init__(self, net, action_keys, observation_keys, state_keys=None, profiles=None,
+                 num_envs: int = 1,
+                 evaluate_on: str = "validation", steps_per_episode: int = 1,
+                 bus_wise_obs: bool = False,
+                 reward_function="summation", reward_function_params: dict | None = None,
+                 diff_objective: bool = False, add_res_obs=False, add_time_obs: bool = False,
+                 add_act_obs: bool = False, add_mean_obs: bool = False,
+                 train_data: str = "simbench", test_data: str = "simbench",
+                 sampling_params: dict | None = None, constraint_params: dict | None = None,
+                 custom_constraints: list | None = None, autoscale_actions: bool = True,
+                 diff_action_step_size: float | None = None,
+                 clipped_action_penalty: float = 0.0, initial_action: str = "center",
+                 objective_function=None, power_flow_solver=None,
+                 optimal_power_flow_solver=None, seed: int | None = None,
+                 # --- engine-side arguments (not in the reference) ---
+                 device=None, rank: int = 0, world_size: int = 1, obs_dtype: str = "float32",
+                 dynamic_columns=(), pwl_price_columns=None, tolerance_mva: float = 1e-8,
+                 max_iteration: int = 10, engine_cls=Engine, engine_kwargs: dict | None = None,
+                 copy_outputs: bool = True, **kwargs):
+        unknown = set(kwargs) - _SPLIT_KWARGS
+        if unknown:
+            raise TypeError(f"unknown keyword arguments: {sorted(unknown)}")
+        for flag, name in ((bus_wise_obs, "bus_wise_obs"), (diff_objective, "diff_objective"),
+                           (diff_action_step_size, "diff_action_step_size")):
+            if flag:
+                raise NotImplementedError(f"{name} is listed under SURVEY.md §8(f) 'next'")
+        if add_time_obs:
+            raise NotImplementedError("add_time_obs raises TypeError in the reference itself "
+                                      "(opf_env.py:545-546 vs time_observation.py:4)")
+        if objective_function is not None or power_flow_solver is not None:
+            raise NotImplementedError(
+                "Python callables cannot run inside the batched kernels; costs are taken from "
+                "net.poly_cost / net.pwl_cost and the power flow is the CUDA engine. Use "
+                "opfgym_b200.adapter.power_flow_solver to plug the engine into a single-env OpfEnv.")
+        if steps_per_episode != 1:
+            raise NotImplementedError("multi-step episodes: SURVEY.md §8(f) rank 3")
+
+        self.net = net
+        self.copy_outputs = copy_outputs   # False: returned tensors alias engine buffers
+        self.num_envs = int(num_envs)
+        self.profiles = profiles
+        self.obs_keys = list(observation_keys)
+        self.state_keys = list(state_keys) if state_keys is not None else copy.copy(self.obs_keys)
+        self.act_keys = list(action_keys)
+        if not profiles:
+            assert "simbench" not in test_data and "simbench" not in train_data
+        self.evaluate_on = evaluate_on
+        self.train_data, self.test_data = train_data, test_data
+        self.sampling_params = sampling_params or {}
+        self.add_act_obs = add_act_obs
+        if add_act_obs:
+            self.obs_keys.extend(self.act_keys)
+        if add_res_obs is True:
+            add_res_obs = ("voltage_magnitude", "voltage_angle", "line_loading",
+                           "trafo_loading", "ext_grid_power")
+        if add_res_obs:   # opf_env.py:99-118
+            buses = set(net.load.bus) | set(net.sgen.bus) | set(net.gen.bus) | set(net.storage.bus)
+            buses = np.sort(list(buses))
+            extra = {"voltage_magnitude": [("res_bus", "vm_pu", buses)],
+                     "voltage_angle": [("res_bus", "va_degree", buses)],
+                     "line_loading": [("res_line", "loading_percent", net.line.index)],
+                     "trafo_loading": [("res_trafo", "loading_percent", net.trafo.index)],
+                     "ext_grid_power": [("res_ext_grid", "p_mw", net.ext_grid.index),
+                                        ("res_ext_grid", "q_mvar", net.ext_grid.index)]}
+            for name in ("voltage_magnitude", "voltage_angle", "line_loading", "trafo_loading",
+                         "ext_grid_power"):
+                if name in add_res_obs:
+                    self.obs_keys.extend(extra[name])
+        self.add_mean_obs = add_mean_obs
+        self.observation_space_single = get_obs_and_state_space(
+            net, self.obs_keys, False, add_mean_obs, seed=seed)
+        self.state_space = get_obs_and_state_space(net, self.state_keys, seed=seed)
+        n_actions = sum(len(idxs) for _, _, idxs in self.act_keys)
+        self.single_action_space = Box(0, 1, shape=(n_actions,), seed=seed)
+        self.single_observation_space = self.observation_space_single
+        self.action_space = batch_space(self.single_action_space, self.num_envs)
+        self.observation_space = batch_space(self.single_observation_space, self.num_envs)
+
+        self.autoscale_actions = autoscale_actions
+        self.clipped_action_penalty = clipped_action_penalty
+        self.initial_action = initial_action
+        self.steps_per_episode = steps_per_episode
+        self.pf_for_obs = any("res_" in unit_type for unit_type, _, _ in self.obs_keys)
+        self.test_steps, self.validation_steps, self.train_steps = define_test_train_split(**kwargs)
+
+        if custom_constraints is None:
+            self.constraints = constraints_mod.create_default_constraints(net, constraint_params or {})
+        else:
+            self.constraints = custom_constraints
+
+        # ---- compile + device buffers ------------------------------------------------
+        self.rank, self.world_size = int(rank), int(world_size)
+        self._builder = PpcBuilder(net)
+        compiler = Compiler(net, self._builder)
+        placeholder = reward_mod.Summation()
+        dynamic = list(dynamic_columns) + list(self._dynamic_columns())
+        self._compile_args = dict(act_keys=self.act_keys, obs_keys=self.obs_keys,
+                                  state_keys=self.state_keys, constraints=self.constraints,
+                                  extra_dynamic=dynamic, autoscale_actions=autoscale_actions,
+                                  pwl_price_columns=pwl_price_columns)
+        self._engine_args = dict(device=device, tolerance_mva=tolerance_mva,
+                                 max_iteration=max_iteration, obs_dtype=obs_dtype,
+                                 **(engine_kwargs or {}))
+        self._engine_cls = engine_cls
+        self.program = compiler.compile(reward_function=placeholder, **self._compile_args)
+        self.engine = engine_cls(self.program, self.num_envs, **self._engine_args)
+        self.xp = self.engine.torch
+        self.device = self.engine.device
+        self.seed = 0 if seed is None else int(seed)
+        self._episode = 0
+        self._stream_in_episode = 0
+        self._sample_cache = {}
+        self._static_cache = {}
+        self.test = False
+        self.power_flow_available = False
+
+        # ---- reward function (may sample the engine for its scaling parameters) --------
+        reward_function_params = reward_function_params or {}
+        if isinstance(reward_function, str):
+            reward_cls = reward_mod.load_reward_class(reward_function)
+            self.reward_function = reward_cls(env=self, **reward_function_params)
+        elif isinstance(reward_function, reward_mod.RewardFunction):
+            self.reward_function = reward_function
+        else:
+            raise TypeError("reward_function must be a name or an opfgym_b200.reward.RewardFunction")
+        if repr(self.reward_function.device_params()) != repr(placeholder.device_params()):
+            self._rebuild_engine()
+
+    # subclasses list the per-environment columns their `_sampling` hook writes
+    def _dynamic_columns(self):
+        return ()
+
+    def _rebuild_engine(self):
+        state = self.engine.state
+        compiler = Compiler(self.net, self._builder)
+        self.program = compiler.compile(reward_function=self.reward_function, **self._compile_args)
+        self.engine.close()
+        self.engine = self._engine_cls(self.program, self.num_envs, **self._engine_args)
+        self.engine.state.copy_(state)
+        self._sample_cache.clear()
+
+    # ------------------------------------------------------------------ column access
+    def col(self, table: str, column: str):
+        """[num_envs, n_rows] view of a per-environment column."""
+        return self.engine.column(table, column)
+
+    def static(self, table: str, column: str):
+        key = (table, column)
+        if key not in self._static_cache:
+            v = np.asarray(self.net[table][column].to_numpy(), dtype=float)
+            self._static_cache[key] = self.engine._from_numpy(v)
+        return self._static_cache[key]
+
+    def positions(self, table: str, idxs):
+        return self.net[table].index.get_indexer(np.asarray(idxs))
+
+    # ------------------------------------------------------------------------ sampling
+    def _next_stream(self) -> int:
+        self._stream_in_episode += 1
+        return self._episode * 64 + self._stream_in_episode
+
+    @property
+    def first_env(self) -> int:
+        return self.rank * self.num_envs
+
+    def _sample_from_range(self, unit_type, column, idxs):
+        """``OpfEnv._sample_from_range`` (opf_env.py:266-284) for all environments."""
+        self._sample_keys([(unit_type, column, idxs)])
+
+    def _sample_keys(self, keys):
+        cache_key = tuple((t, c, tuple(np.asarray(i).tolist())) for t, c, i in keys)
+        if cache_key not in self._sample_cache:
+            slots, lo, hi, div = [], [], [], []
+            for unit_type, column, idxs in keys:
+                if "res_" in unit_type or len(idxs) == 0:
+                    continue
+                df = self.net[unit_type]
+                pos = self.positions(unit_type, idxs)
+                lo_c = f"min_min_{column}" if f"min_min_{column}" in df.columns else f"min_{column}"
+                hi_c = f"max_max_{column}" if f"max_max_{column}" in df.columns else f"max_{column}"
+                start = self.program.layout.columns[(unit_type, column)][0]
+                slots.append(start + pos)
+                lo.append(df[lo_c].to_numpy(float)[pos])
+                hi.append(df[hi_c].to_numpy(float)[pos])
+                div.append(df.scaling.to_numpy(float)[pos] if "scaling" in df.columns
+                           else np.ones(len(pos)))
+            if not slots:
+                self._sample_cache[cache_key] = None
+            else:
+                f = self.engine._from_numpy
+                self._sample_cache[cache_key] = (
+                    f(np.concatenate(slots).astype(np.int32)), f(np.concatenate(lo)),
+                    f(np.concatenate(hi)), f(np.concatenate(div)))
+        plan = self._sample_cache[cache_key]
+        if plan is not None:
+            self.engine.sample_uniform(*plan, seed=self.seed, first_env=self.first_env,
+                                       stream_id=self._next_stream())
+
+    def _sample_uniform(self, sample_keys=None, sample_new=True):
+        """opf_env.py:253-264."""
+        assert sample_new, "Currently only implemented for sample_new=True"
+        self._sample_keys(list(sample_keys or self.state_keys))
+
+    def _set_simbench_state(self, step=None, test=False, noise_factor=0.1,
+                            noise_distribution="uniform", interpolate_steps=False, **_):
+        """opf_env.py:317-372: gather one profile row per environment, multiply by
+        uniform noise, clip to the profile range, store unscaled."""
+        if noise_distribution != "uniform" or interpolate_steps:
+            raise NotImplementedError("normal noise / interpolation: SURVEY.md §8(f) rank 3")
+        xp, B = self.xp, self.num_envs
+        if not hasattr(self, "_prof_dev"):
+            self._prof_dev = {}
+            for key, df in self.profiles.items():
+                if df.shape[1] == 0:
+                    continue
+                unit_type, column = key
+                cols = df[self.net[unit_type].index].to_numpy(float)
+                self._prof_dev[key] = (self.engine._from_numpy(cols),
+                                       self.engine._from_numpy(cols.min(axis=0)),
+                                       self.engine._from_numpy(cols.max(axis=0)))
+            n_prof = len(next(iter(self.profiles.values())))
+            self._steps_dev = {name: self.engine._from_numpy(
+                np.asarray(v, dtype=np.int64)[np.asarray(v, dtype=np.int64) < n_prof])
+                               for name, v in (("test", self.test_steps),
+                                               ("validation", self.validation_steps),
+                                               ("train", self.train_steps))}
+        if step is None:
+            pool = self._steps_dev[self.evaluate_on if test else "train"]
+            u = xp.empty((B, 1), dtype=xp.float64, device=self.device)
+            self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
+            step_idx = pool[(u[:, 0] * pool.shape[0]).long().clamp_(max=pool.shape[0] - 1)]
+        else:
+            step_idx = xp.as_tensor(step, device=self.device).long().expand(B)
+        self.current_simbench_step = step_idx
+        for key, (table, pmin, pmax) in self._prof_dev.items():
+            unit_type, column = key
+            if not self.program.layout.has(unit_type, column):
+                continue
+            values = table[step_idx]
+            if noise_factor:
+                u = xp.empty(values.shape, dtype=xp.float64, device=self.device)
+                self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
+                values = values * (u * (2.0 * noise_factor) + (1.0 - noise_factor))
+            self.col(unit_type, column).copy_(xp.minimum(xp.maximum(values, pmin), pmax))
+
+    def _sampling(self, step=None, test=False, sample_new=True, **kwargs):
+        """opf_env.py:222-251 (dispatch on the data distribution)."""
+        self.power_flow_available = False
+        distr = self.test_data if test else self.train_data
+        kwargs.update(self.sampling_params)
+        if distr == "noisy_simbench" or "noise_factor" in kwargs:
+            if sample_new:
+                self._set_simbench_state(step, test, **kwargs)
+        elif distr == "simbench":
+            if sample_new:
+                self._set_simbench_state(step, test, noise_factor=0.0, **kwargs)
+        elif distr == "full_uniform":
+            self._sample_uniform(sample_new=sample_new)
+        else:
+            raise NotImplementedError(f"data distribution {distr!r}: SURVEY.md §8(f) rank 3")
+
+    # --------------------------------------------------------------------- gym interface
+    def reset(self, seed: int | None = None, options: dict | None = None):
+        if seed is not None:
+            self.seed = int(seed)
+            self._episode = 0
+        options = options or {}
+        self.test = options.get("test", False)
+        self._begin_episode(options.get("step", None))
+        return self._obs_out(), {}
+
+    def _begin_episode(self, step=None):
+        self._episode += 1
+        self._stream_in_episode = 0
+        self.current_simbench_step = None
+        self._sampling(step, self.test, True)
+        act = self.engine.actions
+        if self.initial_action == "random":
+            self.engine.philox_uniform(act, self.seed, self.first_env, self._next_stream())
+        else:
+            act.fill_(0.5)
+        self.engine.assemble()
+        if self.pf_for_obs:
+            # the reference re-samples envs whose reset power flow fails (opf_env.py:209-214);
+            # here such envs simply start with a NaN observation and are flagged in `converged`
+            self.engine.pf_solve()
+            self.engine.score()
+            self.power_flow_available = True
+        else:
+            self.engine.observe()
+
+    def _obs_out(self):
+        obs = self.engine.obs
+        if self.add_mean_obs:
+            parts, k = [], 0
+            for _, _, idxs in self.obs_keys:
+                n = len(idxs)
+                if n > 1:
+                    parts.append(obs[:, k:k + n].mean(dim=1, keepdim=True))
+                k += n
+            return self.xp.cat([obs] + parts, dim=1)
+        return obs.clone() if self.copy_outputs else obs
+
+    def step(self, actions):
+        """Apply ``actions[num_envs, n_act]`` (torch or numpy, any float dtype), run the
+        batched power flow, score, auto-reset.  Returns torch tensors on the device:
+        ``(obs, reward, terminated, truncated, info)``; ``info['final_obs']`` holds the
+        observation of the finished episode."""
+        xp = self.xp
+        act = xp.as_tensor(actions, device=self.device)
+        if xp.isnan(act).any():
+            raise AssertionError("NaN in actions")     # opf_env.py:382
+        self.engine.actions.copy_(act.reshape(self.engine.actions.shape))
+        self.engine.step()
+        self.power_flow_available = True
+        e = self.engine
+        reward = e.reward.clone()
+        if self.clipped_action_penalty:
+            reward -= self._mean_correction(act) * self.clipped_action_penalty
+        nc = max(len(self.constraints), 1)
+        info = {"valids": e.valids[:, :nc].bool(), "violations": e.violations[:, :nc].clone(),
+                "unscaled_penalties": e.penalties[:, :nc].clone(), "cost": e.cost.clone(),
+                "converged": e.converged.bool(), "iterations": e.iterations.clone(),
+                "final_obs": self._obs_out().clone()}   # always copied: reset overwrites it
+        terminated = xp.ones(self.num_envs, dtype=xp.bool, device=self.device)
+        truncated = xp.zeros(self.num_envs, dtype=xp.bool, device=self.device)
+        self._begin_episode()
+        return self._obs_out(), reward, terminated, truncated, info
+
+    def _mean_correction(self, act):
+        """opf_env.py:488-491: mean |applied action - requested action|."""
+        return (self.get_current_actions(from_results_table=False) - act).abs().mean(dim=1)
+
+    def close(self):
+        self.engine.close()
+
+    # ----------------------------------------------------------------- OpfEnv-style API
+    def run_power_flow(self, **kwargs):
+        """opf_env.py:646-662; returns the per-environment converged mask."""
+        self.engine.assemble(apply_actions=False)   # re-scatter Sbus from the current cells
+        self.engine.pf_solve()
+        self.engine.score()
+        self.power_flow_available = True
+        return self.engine.converged.bool()
+
+    def ensure_power_flow_available(self):
+        if not self.power_flow_available:
+            raise PowerFlowNotAvailable("Please call `run_power_flow` first!")
+
+    def _apply_actions(self, actions):
+        self.engine.actions.copy_(self.xp.as_tensor(actions, device=self.device))
+        self.engine.assemble()
+        self.power_flow_available = False
+
+    def get_state(self):
+        return self._gather(self.state_keys)
+
+    def _gather(self, keys):
+        parts = []
+        for unit_type, column, idxs in keys:
+            pos = self.xp.as_tensor(self.positions(unit_type.replace("res_", "", 1)
+                                                   if unit_type.startswith("res_") else unit_type,
+                                                   idxs), device=self.device)
+            if self.program.layout.has(unit_type, column):
+                parts.append(self.col(unit_type, column)[:, pos])
+            else:
+                parts.append(self.static(unit_type, column)[pos].expand(self.num_envs, -1))
+        return self.xp.cat(parts, dim=1)
+
+    def get_current_actions(self, from_results_table=True):
+        """opf_env.py:566-588: the [0, 1] actions that the current set-points represent."""
+        out = []
+        for unit_type, column, idxs in self.act_keys:
+            pos = self.xp.as_tensor(self.positions(unit_type, idxs), device=self.device)
+            sp = self.col(unit_type, column)[:, pos]
+            if "scaling" in self.net[unit_type].columns:
+                sp = sp * self.static(unit_type, "scaling")[pos]
+            lo_c, hi_c = (f"min_{column}", f"max_{column}") if self.autoscale_actions else \
+                         (f"min_min_{column}", f"max_max_{column}")
+            lo = self._value(unit_type, lo_c, pos)
+            hi = self._value(unit_type, hi_c, pos)
+            out.append((sp - lo) / (hi - lo))
+        return self.xp.cat(out, dim=1)
+
+    get_actions = get_current_actions
+
+    def _value(self, table, column, pos):
+        if self.program.layout.has(table, column):
+            return self.col(table, column)[:, pos]
+        return self.static(table, column)[pos]
+
+    def is_state_valid(self):
+        self.ensure_power_flow_available()
+        nc = max(len(self.constraints), 1)
+        return self.engine.valids[:, :nc].bool().all(dim=1)
+
+    def get_objective(self):
+        self.ensure_power_flow_available()
+        return self.engine.objective.clone()
+
+    def calculate_violations(self):
+        self.ensure_power_flow_available()
+        nc = max(len(self.constraints), 1)
+        e = self.engine
+        return e.valids[:, :nc].bool(), e.violations[:, :nc], e.penalties[:, :nc]
+
+    def sample_objective_penalty(self, num_samples: int):
+        """Feeds ``reward.estimate_reward_distribution`` (reference reward.py:181-216:
+        reset, random action, power flow -- ``num_samples`` times) from batched launches."""
+        objs, pens = [], []
+        done = 0
+        while done < num_samples:
+            self._episode += 1
+            self._stream_in_episode = 0
+            self._sampling(None, False, True)
+            self.engine.philox_uniform(self.engine.actions, self.seed, self.first_env,
+                                       self._next_stream())
+            self.engine.step()
+            ok = self.engine.converged.bool()
+            objs.append(self.xp.where(ok, self.engine.objective, float("nan")))
+            pens.append(self.xp.where(ok, self.engine.penalty, float("nan")))
+            done += self.num_envs
+        objs = self.xp.cat(objs)[:num_samples].cpu().numpy()
+        pens = self.xp.cat(pens)[:num_samples].cpu().numpy()
+        return objs, pens
+
+    # ------------------------------------------------------------- episode statistics
+    def episode_statistics(self, reduce: bool = True) -> dict:
+        """Running sums accumulated by kernel 5's epilogue; with ``torch.distributed``
+        initialised they are all-reduced over ranks (the path's only collective)."""
+        stats = self.engine.stats.clone()
+        if reduce and self.world_size > 1:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        s = stats.cpu().numpy()
+        n = max(s[0], 1.0)
+        nconv = max(s[1], 1.0)
+        return {"steps": s[0], "converged": s[1], "valid": s[2],
+                "mean_reward": s[3] / nconv,
+                "std_reward": float(np.sqrt(max(s[4] / nconv - (s[3] / nconv) ** 2, 0.0))),
+                "mean_objective": s[5] / nconv, "mean_penalty": s[6] / nconv,
+                "mean_iterations": s[7] / nconv, "converged_share": s[1] / n,
+                "valid_share": s[2] / n,
+                "violated_share": (s[8:8 + len(self.constraints)] / n).tolist()}
+
+    def reset_statistics(self):
+        self.engine.stats.zero_()

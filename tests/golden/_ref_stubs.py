@@ -134,4 +134,4 @@ def install(profile_steps=None):
         sys.modules[name] = mod
 
     if "/root/reference" not in sys.path:
-        sys.path.insert(0, "/root/reference")
+        sys.path.append("/root/reference")

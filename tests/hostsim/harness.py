@@ -59,3 +59,20 @@ class HostSimEngine(Engine):
 
     def _stream(self):
         return C.c_void_p(0)
+
+
+class TorchHostSimEngine(Engine):
+    """Engine plumbing on torch CPU tensors + the host-sim library, so that the
+    env layer (``BatchedOpfEnv`` and its tensor-op hooks) can be unit-tested on
+    the GPU-less builder box.  Tests only."""
+
+    def __init__(self, program, num_envs, device=None, **kw):
+        super().__init__(program, num_envs, lib=load(), **kw)
+
+    def _setup_device(self, device):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cpu")
+
+    def _stream(self):
+        return C.c_void_p(0)

@@ -1,0 +1,194 @@
+"""BatchedOpfEnv host logic on the host-sim build (CPU tier): vector-env API,
+sampling, auto-reset, determinism, sharding invariance, reference-style identities."""
+import numpy as np
+import pytest
+import torch
+
+from opfgym_b200 import envs
+from opfgym_b200 import reward as R
+from opfgym_b200.data_split import define_test_train_split
+from tests.hostsim.harness import TorchHostSimEngine
+
+KW = dict(engine_cls=TorchHostSimEngine, n_profile_steps=672, obs_dtype="float64")
+
+
+def make(cls=envs.VoltageControl, n=6, **kw):
+    args = dict(KW, train_data="full_uniform", test_data="full_uniform", seed=3)
+    args.update(kw)
+    return cls(num_envs=n, **args)
+
+
+def test_vector_env_api_shapes_and_types():
+    env = make()
+    assert env.num_envs == 6
+    assert env.single_observation_space.shape == (442,) and env.single_action_space.shape == (14,)
+    assert env.observation_space.shape == (6, 442) and env.action_space.shape == (6, 14)
+    obs, info = env.reset(seed=1)
+    assert obs.shape == (6, 442) and isinstance(info, dict) and not torch.isnan(obs).any()
+    act = torch.rand(6, 14, dtype=torch.float64)
+    obs2, reward, term, trunc, info = env.step(act)
+    assert obs2.shape == (6, 442) and reward.shape == (6,)
+    assert term.all() and not trunc.any()                       # steps_per_episode == 1
+    for key in ("valids", "violations", "unscaled_penalties", "cost", "converged", "final_obs"):
+        assert key in info
+    assert info["valids"].shape == (6, len(env.constraints))
+    assert not torch.equal(obs2, info["final_obs"])             # same-step auto-reset happened
+    assert not torch.isnan(reward).any()
+    env.step(act.numpy().astype(np.float32))                    # numpy / float32 actions accepted
+    with pytest.raises(AssertionError):
+        env.step(torch.full((6, 14), float("nan"), dtype=torch.float64))
+
+
+def test_sampled_state_within_bounds_and_hook_columns():
+    env = make(envs.QMarket, n=32)
+    env.reset(seed=5)
+    for table, column in (("load", "p_mw"), ("load", "q_mvar"), ("sgen", "p_mw")):
+        df = env.net[table]
+        v = env.col(table, column) * env.static(table, "scaling")
+        assert (v >= env.static(table, "min_min_" + column) - 1e-12).all()
+        assert (v <= env.static(table, "max_max_" + column) + 1e-12).all()
+    price = env.col("poly_cost", "cq2_eur_per_mvar2")
+    assert (price >= 0).all() and (price <= 0.03).all() and price.std() > 0
+    q_max = env.col("sgen", "max_q_mvar")
+    assert torch.allclose(env.col("sgen", "min_q_mvar"), -q_max)
+    assert (env.col("sgen", "q_mvar") == 0).all()               # centre action of a symmetric range
+
+
+def test_seed_determinism_and_sharding_invariance():
+    a, b = make(n=8), make(n=8)
+    oa, _ = a.reset(seed=11)
+    ob, _ = b.reset(seed=11)
+    assert torch.equal(oa, ob)
+    act = torch.rand(8, 14, dtype=torch.float64)
+    ra, rb = a.step(act), b.step(act)
+    assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+    oc, _ = make(n=8).reset(seed=12)
+    assert not torch.equal(oa, oc)
+    # rank 1 of 2 with 4 envs == envs 4..7 of one rank with 8 (RNG keyed by global env id)
+    shard = make(n=4, rank=1, world_size=2)
+    os_, _ = shard.reset(seed=11)
+    assert torch.equal(os_, oa[4:])
+    rs = shard.step(act[4:])
+    assert torch.equal(rs[1], ra[1][4:]) and torch.equal(rs[0], ra[0][4:])
+
+
+def test_action_round_trip_identity():
+    """reference tests/test_opf_env.py:63-72: allclose(random_action, get_current_actions())."""
+    env = make(envs.MaxRenewable, n=16)
+    env.reset(seed=2)
+    act = torch.rand(16, env.single_action_space.shape[0], dtype=torch.float64)
+    env._apply_actions(act)
+    assert torch.allclose(env.get_current_actions(), act, atol=1e-9)
+
+
+def test_power_flow_availability_and_getters():
+    from opfgym_b200.opf_env import PowerFlowNotAvailable
+    env = make(n=4)
+    env.reset(seed=1)
+    with pytest.raises(PowerFlowNotAvailable):
+        env.get_objective()
+    conv = env.run_power_flow()
+    assert conv.all()
+    assert env.get_objective().shape == (4,) and env.is_state_valid().shape == (4,)
+    assert env.get_state().shape == (4, env.state_space.shape[0])
+    valids, viol, pens = env.calculate_violations()
+    assert valids.shape == viol.shape == pens.shape == (4, len(env.constraints))
+
+
+def test_res_observations_run_a_power_flow_in_reset():
+    env = make(envs.VoltageControl, n=4, add_res_obs=True)
+    assert env.pf_for_obs
+    obs, _ = env.reset(seed=4)
+    n_base = 442
+    assert obs.shape[1] > n_base
+    vm = obs[:, n_base:n_base + 5]
+    assert ((vm > 0.8) & (vm < 1.2)).all()
+    # like pandapower, out-of-service lines (the open ring ties) report NaN loading
+    k = n_base + sum(len(i) for t, c, i in env.obs_keys[4:] if (t, c) != ("res_line", "loading_percent")
+                     and env.obs_keys.index((t, c, i)) < [kk[:2] for kk in env.obs_keys].index(("res_line", "loading_percent")))
+    n_line = len(env.net.line)
+    nan_cols = torch.isnan(obs[0, k:k + n_line]).numpy()
+    assert (nan_cols == ~env.net.line.in_service.to_numpy(bool)).all()
+    rest = torch.cat([obs[:, :k], obs[:, k + n_line:]], dim=1)
+    assert not torch.isnan(rest).any()
+
+
+def test_simbench_sampling_modes():
+    env = make(envs.VoltageControl, n=8, train_data="simbench", test_data="simbench",
+               n_profile_steps=4 * 672)     # week 0 = test, week 1 = validation, 2-3 = train
+    env.reset(seed=9)
+    steps = env.current_simbench_step
+    assert steps.shape == (8,) and set(steps.tolist()) <= set(env.train_steps.tolist())
+    prof = torch.as_tensor(env.profiles[("load", "p_mw")].to_numpy().copy())
+    assert torch.allclose(env.col("load", "p_mw"), prof[steps])
+    env.reset(seed=9, options={"test": True})
+    assert set(env.current_simbench_step.tolist()) <= set(env.validation_steps.tolist())
+    env.reset(options={"step": 17})
+    assert (env.current_simbench_step == 17).all()
+    noisy = make(envs.VoltageControl, n=8, train_data="noisy_simbench", test_data="simbench",
+                 n_profile_steps=4 * 672)
+    noisy.reset(seed=9)
+    prof = torch.as_tensor(noisy.profiles[("load", "p_mw")].to_numpy().copy())
+    ratio = noisy.col("load", "p_mw") / prof[noisy.current_simbench_step]
+    assert (ratio >= 0.9 - 1e-9).all() and (ratio <= 1.1 + 1e-9).all() and ratio.std() > 0
+
+
+def test_reward_function_selection_and_scaling_estimate():
+    env = make(n=8, reward_function="replacement",
+               reward_function_params=dict(valid_reward=0.5, penalty_weight=None))
+    assert isinstance(env.reward_function, R.Replacement)
+    env.reset(seed=1)
+    _, reward, _, _, info = env.step(torch.rand(8, 14, dtype=torch.float64))
+    valid = info["valids"].all(dim=1)
+    pen = info["unscaled_penalties"].sum(dim=1)
+    assert torch.allclose(reward[~valid], pen[~valid])           # invalid: objective replaced by 0
+    # reward_scaling without parameters samples the engine (reference reward.py:33-38)
+    env2 = make(n=16, reward_function="summation",
+                reward_function_params=dict(reward_scaling="normalization",
+                                            scaling_params=dict(num_samples=48)))
+    sp = env2.reward_function.scaling_params
+    assert np.isfinite(sp["objective_factor"]) and sp["std_objective"] > 0
+
+
+def test_unknown_kwargs_and_unsupported_modes_raise():
+    with pytest.raises(TypeError):
+        make(penalty_weight=0.3)        # reference silently swallows this (A.6 quirk 12)
+    with pytest.raises(NotImplementedError):
+        make(add_time_obs=True)
+    with pytest.raises(NotImplementedError):
+        make(power_flow_solver=lambda net: None)
+
+
+def test_episode_statistics_accumulate():
+    env = make(n=8)
+    env.reset(seed=1)
+    env.reset_statistics()
+    for _ in range(3):
+        env.step(torch.rand(8, 14, dtype=torch.float64))
+    s = env.episode_statistics()
+    assert s["steps"] == 24 and s["converged"] == 24 and 3.0 <= s["mean_iterations"] <= 6.0
+    assert len(s["violated_share"]) == len(env.constraints)
+
+
+def test_data_split_matches_reference_anchors():
+    test, val, train = define_test_train_split()
+    assert test[0] == 0 and val[0] == 672          # reference tests/test_simbench.py:83-85
+    assert len(set(test) & set(val)) == 0 and len(set(train) & set(test)) == 0
+    assert len(test) + len(val) + len(train) == 24 * 4 * 366
+    t2, v2, tr2 = define_test_train_split(test_share=1.0, validation_share=0.0)
+    assert len(t2) == 35136 and len(v2) == 0 and len(tr2) == 0
+
+
+@pytest.mark.parametrize("cls,n_obs,n_act", [(envs.VoltageControl, 442, 14), (envs.EcoDispatch, 201, 42),
+                                             (envs.QMarket, 305, 10), (envs.LoadShedding, 386, 16),
+                                             (envs.MaxRenewable, 172, 18)])
+def test_benchmark_sizes_and_three_steps(cls, n_obs, n_act):
+    """reference tests/test_benchmarks_integration.py + docs/source/benchmarks.rst:19-27."""
+    env = make(cls, n=3)
+    assert env.single_observation_space.shape == (n_obs,) and env.single_action_space.shape == (n_act,)
+    obs, _ = env.reset(seed=0)
+    for _ in range(3):
+        obs, reward, term, trunc, info = env.step(torch.rand(3, n_act, dtype=torch.float64))
+        assert obs.shape == (3, n_obs) and term.all() and info["converged"].all()
+    assert envs.make(f"{cls.__name__}-v0", num_envs=2, **dict(KW, train_data="full_uniform",
+                                                             test_data="full_uniform")).num_envs == 2
