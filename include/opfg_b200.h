@@ -206,6 +206,11 @@ int opfg_observe(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream
 /* assemble -> pf_solve -> score, back to back on the stream */
 int opfg_step(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 
+/* FP64 FMA throughput probe for the roofline denominator (MEASURED_PEAKS.json has no FP64 figure):
+ * every thread runs 8 independent DFMA chains of `iters` steps; flops = 2*8*iters*n_blocks*256.
+ * out (device, >= 1 double) keeps the result alive. */
+int opfg_fp64_probe(int32_t n_blocks, int32_t iters, double* out, void* cuda_stream);
+
 /* number of kernel launches issued by this library since load (for bench accounting) */
 int64_t opfg_launch_count(void);
 

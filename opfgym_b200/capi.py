@@ -96,6 +96,7 @@ PROTOTYPES = {
     "opfg_score": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_observe": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "opfg_fp64_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "opfg_launch_count": (C.c_int64, []),
 }
 

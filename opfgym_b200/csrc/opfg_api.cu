@@ -168,6 +168,17 @@ __global__ void k_observe(GridDev g, OpfgBatch B) {
     if (B.obs_f64) B.obs_f64[idx] = v;
 }
 
+__global__ void __launch_bounds__(256) k_fp64_probe(int iters, double* out) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
+}
+
 #define OPFG_DISPATCH_T(T_, ...)                                     \
     switch (T_) {                                                    \
         case 32: { constexpr int TT = 32; __VA_ARGS__; break; }      \
@@ -595,6 +606,20 @@ int opfg_observe(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (e != cudaSuccess) return fail("observe launch: %s", cudaGetErrorString(e));
 #endif
     return 0;
+}
+
+int opfg_fp64_probe(int32_t n_blocks, int32_t iters, double* out, void* stream) {
+    if (!out || n_blocks <= 0 || iters <= 0) return fail("bad argument");
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    return fail("opfg_fp64_probe measures the GPU; not available in the host build");
+#else
+    k_fp64_probe<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("fp64 probe launch: %s", cudaGetErrorString(e));
+    return 0;
+#endif
 }
 
 int opfg_step(const OpfgGrid* G, const OpfgBatch* B, void* stream) {

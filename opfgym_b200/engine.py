@@ -125,8 +125,25 @@ class Engine:
         capi.check(self.lib, self.lib.opfg_observe(self.handle, C.byref(self.batch), self._stream()))
 
     def step(self):
-        """assemble -> pf_solve -> score on the current stream (3 launches, no sync)."""
-        capi.check(self.lib, self.lib.opfg_step(self.handle, C.byref(self.batch), self._stream()))
+        """assemble -> pf_solve -> score on the current stream (3 launches, no sync).
+        With ``self.pf_events`` set to a list, CUDA events bracketing the power-flow
+        kernel are appended to it (bench.py's roofline timing)."""
+        if self.pf_events is None:
+            capi.check(self.lib, self.lib.opfg_step(self.handle, C.byref(self.batch), self._stream()))
+            return
+        self.assemble()
+        e0 = self.torch.cuda.Event(enable_timing=True)
+        e1 = self.torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self.pf_solve()
+        e1.record()
+        self.score()
+        self.pf_events.append((e0, e1))
+
+    pf_events = None
+
+    def fp64_probe(self, n_blocks: int, iters: int):
+        capi.check(self.lib, self.lib.opfg_fp64_probe(n_blocks, iters, self._ptr(self.stats), self._stream()))
 
     def symbolic(self):
         n, nl = self.info["n_nonref"], self.info["n_levels"]

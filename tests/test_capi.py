@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_functions():
     text = open(os.path.join(ROOT, "include", "opfg_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return set(re.findall(r"\b(opfg_[a-z_]+)\s*\(", text))
+    return set(re.findall(r"\b(opfg_[a-z0-9_]+)\s*\(", text))
 
 
 def test_prototypes_cover_header():
