@@ -188,6 +188,13 @@ class Compiler:
                 for pos, g in enumerate(ppc.gen_gen):
                     if g >= 0:
                         gen_q_slot[g] = start + pos
+            elif table in ("res_line", "res_trafo") and column == "_flows4":
+                # 4 cells per element: p_from/hv, q_from/hv, p_to/lv, q_to/lv  (adapter only)
+                start = lay.add(table, column, 4 * n_rows)
+                mapping = ppc.line_branch if base == "line" else ppc.trafo_branch
+                for pos, br in enumerate(mapping):
+                    if br >= 0:
+                        flow_slot[br] = start + 4 * pos
             elif table == "res_trafo3w":
                 lay.add(table, column, n_rows)   # no trafo3w model: column stays NaN
             elif table in ("res_load", "res_sgen", "res_storage", "res_gen") and column in ("p_mw", "q_mvar"):
