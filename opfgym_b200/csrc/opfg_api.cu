@@ -7,8 +7,11 @@
 //               g++ -x c++ -DOPFG_HOSTSIM                       -> tests/hostsim only.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -78,6 +81,29 @@ struct OpfgGrid {
     double flops_score = 0;
     bool has_assembly = false, has_scoring = false;
     size_t smem_pf = 0, smem_score = 0;
+    int carveout_pct = -1;   // -1: leave the driver's default L1/shared split
+    int envs_per_cta = 1;
+
+    // schedule / Ybus tables of the power-flow kernel live in ONE contiguous device arena so that a
+    // multi-environment CTA can stage them in shared memory with a single cooperative copy
+    char* tab_base = nullptr;
+    size_t tab_cap = 0, tab_used = 0;
+    void tab_reserve(size_t bytes) {
+        tab_base = (char*)dev_alloc(bytes);
+        if (!tab_base) throw std::runtime_error("device allocation failed");
+        allocs.push_back(tab_base);
+        tab_cap = bytes;
+    }
+    template <class T>
+    T* tab(const std::vector<T>& v) {
+        tab_used = (tab_used + 15) & ~size_t(15);
+        const size_t bytes = v.size() * sizeof(T);
+        if (tab_used + bytes > tab_cap) throw std::runtime_error("table arena overflow");
+        char* p = tab_base + tab_used;
+        dev_put(p, v.data(), bytes);
+        tab_used += bytes;
+        return (T*)p;
+    }
 
     template <class T>
     const T* up(const std::vector<T>& v) {
@@ -137,7 +163,7 @@ __global__ void k_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t str
 }
 template <int T>
 __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
-    Ctx<T> cx{(int)threadIdx.x, nullptr};
+    Ctx<T> cx{(int)threadIdx.x, nullptr, 0};
     const int64_t env = blockIdx.x;
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                  B.sbus + env * (int64_t)g.nb * 2);
@@ -146,15 +172,44 @@ template <int T>
 __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
     const int64_t env = blockIdx.x;
-    Ctx<T> cx{(int)threadIdx.x, sm + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1)};
+    Ctx<T> cx{(int)threadIdx.x, sm + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1), 0};
     env_pf_solve(g, cx, sm, B.sbus + env * (int64_t)g.nb * 2, nullptr, B.vm + env * (int64_t)g.nb,
                  B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
+}
+// Persistent multi-environment CTA: E environments of T threads each share ONE shared-memory copy of
+// the schedule / Ybus tables (their reads are on the critical path of every level); each environment
+// group synchronises on its own named barrier and walks through its share of the batch.
+template <int T>
+__global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
+    extern __shared__ __align__(16) double sm[];
+    {
+        const int4* src = reinterpret_cast<const int4*>(g.tab_base);
+        int4* dst = reinterpret_cast<int4*>(sm);
+        for (int i = threadIdx.x; i < g.tab_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const char* sbase = reinterpret_cast<const char*>(sm);
+#define OPFG_REBASE(field) g.field = reinterpret_cast<decltype(g.field)>(sbase + (reinterpret_cast<const char*>(g.field) - g.tab_base))
+    OPFG_REBASE(bus_of_int); OPFG_REBASE(type_int); OPFG_REBASE(vm0_int); OPFG_REBASE(va0_int);
+    OPFG_REBASE(level_ptr); OPFG_REBASE(fill_ids); OPFG_REBASE(diag_mode);
+    OPFG_REBASE(dp_ptr); OPFG_REBASE(dp_pack); OPFG_REBASE(off_ptr); OPFG_REBASE(off_hdr); OPFG_REBASE(op_pack);
+    OPFG_REBASE(up_ptr); OPFG_REBASE(up_pack); OPFG_REBASE(y_ptr); OPFG_REBASE(y_meta); OPFG_REBASE(y_val);
+    OPFG_REBASE(dc_val); OPFG_REBASE(dc_rhs0);
+#undef OPFG_REBASE
+    const int e_local = threadIdx.x / T;
+    double* mine = sm + g.tab_bytes / 8 + (size_t)e_local * env_doubles;
+    Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1), 1 + e_local};
+    for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
+        env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2, nullptr, B.vm + env * (int64_t)g.nb,
+                     B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
+        cx.sync();
+    }
 }
 template <int T>
 __global__ void __launch_bounds__(T) k_score(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
     const int64_t env = blockIdx.x;
-    Ctx<T> cx{(int)threadIdx.x, sm + score_smem_doubles(g.nb, g.nbr, T) - 2 * (T / 32 + 1)};
+    Ctx<T> cx{(int)threadIdx.x, sm + score_smem_doubles(g.nb, g.nbr, T) - 2 * (T / 32 + 1), 0};
     env_score(g, cx, sm, B, env, nullptr);
 }
 
@@ -269,7 +324,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         int T = desc->threads_per_env;
         Symbolic& s = G->sym;
         analyse(nb, type, active, desc->ordering, T > 0 ? T : 32, s);
-        if (T <= 0) T = s.n_blocks <= 1200 ? 32 : (s.n_blocks <= 4000 ? 64 : 128);
+        if (T <= 0) T = s.n_blocks <= 4000 ? 64 : 128;   // measured: 64 beats 32 on MV and HV grids
         for (size_t c = 0; c < s.yc_branch.size(); ++c)
             if (s.yc_role[c] != 4) s.yc_branch[c] = active_row[s.yc_branch[c]];
 
@@ -285,18 +340,46 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             vm0[i] = vm_bus[bus];
             va0[i] = type[bus] == 3 ? va_ref[bus] : (desc->init_dc ? 0.0 : va_ref[bus]);
         }
-        d.bus_of_int = G->up(s.bus_of_int); d.int_of_bus = G->up(s.int_of_bus);
-        d.type_int = G->up(type_int); d.vm0_int = G->up(vm0); d.va0_int = G->up(va0);
-        d.level_ptr = G->up(s.level_ptr); d.fill_ids = G->up(s.fill_ids);
-        d.dp_ptr = G->up(s.dp_ptr); d.dp_l = G->up(s.dp_l); d.dp_w = G->up(s.dp_w); d.dp_m = G->up(s.dp_m);
-        d.off_ptr = G->up(s.off_ptr); d.off_tgt = G->up(s.off_tgt); d.off_piv = G->up(s.off_piv);
-        d.op_ptr = G->up(s.op_ptr); d.op_l = G->up(s.op_l); d.op_w = G->up(s.op_w);
-        d.up_ptr = G->up(s.up_ptr); d.up_w = G->up(s.up_w); d.up_j = G->up(s.up_j);
-        d.y_ptr = G->up(s.y_ptr); d.y_col = G->up(s.y_col); d.y_blk = G->up(s.y_blk); d.y_diag = G->up(s.y_diag);
+        G->tab_reserve(4096 + 16 * (size_t)nb * 8 + 8 * (s.dp_l.size() + s.off_tgt.size() + 1) +
+                       4 * (s.op_l.size() + s.up_w.size() + s.fill_ids.size()) + 24 * s.y_col.size() +
+                       8 * (size_t)s.n_blocks + 16 * (size_t)s.n_levels + 64 * 32);
+        d.bus_of_int = G->tab(s.bus_of_int); d.int_of_bus = G->up(s.int_of_bus);
+        d.type_int = G->tab(type_int); d.vm0_int = G->tab(vm0); d.va0_int = G->tab(va0);
+        d.level_ptr = G->tab(s.level_ptr); d.fill_ids = G->tab(s.fill_ids);
+        if (s.n_blocks >= 65535 || nb >= 65535) { delete G; return fail("grid too large for 16-bit schedule ids (%d blocks)", s.n_blocks); }
+        {   // pack the schedule into 16-bit ids (halves the L1 footprint of the shared tables)
+            std::vector<U2> dp(s.dp_l.size()), hdr(s.off_tgt.size() + 1);
+            std::vector<uint32_t> op(s.op_l.size()), upk(s.up_w.size());
+            std::vector<U2> ym(s.y_col.size());
+            for (size_t i = 0; i < dp.size(); ++i) dp[i] = U2{(uint32_t)s.dp_l[i] | ((uint32_t)s.dp_w[i] << 16), (uint32_t)s.dp_m[i]};
+            for (size_t i = 0; i < s.off_tgt.size(); ++i)
+                hdr[i] = U2{(uint32_t)s.off_tgt[i] | ((uint32_t)(s.off_piv[i] + 1) << 16), (uint32_t)s.op_ptr[i]};
+            hdr[s.off_tgt.size()] = U2{0u, (uint32_t)s.op_l.size()};
+            for (size_t i = 0; i < op.size(); ++i) op[i] = (uint32_t)s.op_l[i] | ((uint32_t)s.op_w[i] << 16);
+            for (size_t i = 0; i < upk.size(); ++i) upk[i] = (uint32_t)s.up_w[i] | ((uint32_t)s.up_j[i] << 16);
+            for (int r = 0; r < nb; ++r)
+                for (int e = s.y_ptr[r]; e < s.y_ptr[r + 1]; ++e)
+                    ym[e] = U2{(uint32_t)s.y_col[e] | ((uint32_t)(s.y_blk[e] + 1) << 16), (uint32_t)r};
+            d.nnz_y_nonref = s.y_ptr[s.n];
+            // per level: one lane per pivot, or eight lanes per pivot (component-parallel gather)
+            std::vector<unsigned char> mode(s.n_levels, 0);
+            for (int l = 0; l < s.n_levels; ++l) {
+                int items = s.level_ptr[l + 1] - s.level_ptr[l], maxp = 0;
+                for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) maxp = std::max(maxp, s.dp_ptr[k + 1] - s.dp_ptr[k]);
+                const double narrow = std::ceil(items / (double)T) * (45.0 + 30.0 * maxp);
+                const double wide = std::ceil(items * 8 / (double)T) * (75.0 + 12.0 * maxp);
+                mode[l] = wide < narrow ? 1 : 0;
+            }
+            d.diag_mode = G->tab(mode);
+            d.dp_ptr = G->tab(s.dp_ptr); d.dp_pack = G->tab(dp);
+            d.off_ptr = G->tab(s.off_ptr); d.off_hdr = G->tab(hdr); d.op_pack = G->tab(op);
+            d.up_ptr = G->tab(s.up_ptr); d.up_pack = G->tab(upk);
+            d.y_ptr = G->tab(s.y_ptr); d.y_diag = G->up(s.y_diag); d.y_meta = G->tab(ym);
+        }
         d.yc_ptr = G->up(s.yc_ptr); d.yc_branch = G->up(s.yc_branch); d.yc_role = G->up(s.yc_role);
         d.br_param = G->up(br_param); d.bus_ysh = G->up(ysh); d.br_f = G->up(br_f); d.br_t = G->up(br_t);
         d.br_y = (double*)G->up(std::vector<double>(8 * (size_t)nbr, 0.0));
-        double* y_val = (double*)G->up(std::vector<double>(2 * s.y_col.size(), 0.0));
+        double* y_val = G->tab(std::vector<double>(2 * s.y_col.size(), 0.0));
         d.y_val = y_val;
 
         // DC start: scalar factor of B' on the same schedule + constant part of its rhs
@@ -316,9 +399,20 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             if (t < s.n && f >= s.n) dc_rhs0[t] += b * va_ref[br.f];
         }
         for (int k = 0; k < s.n; ++k) dc_rhs0[k] -= ysh[2 * s.bus_of_int[k]];
-        d.dc_val = G->up(dc_val); d.dc_rhs0 = G->up(dc_rhs0);
+        d.dc_val = G->tab(dc_val); d.dc_rhs0 = G->tab(dc_rhs0);
+        d.tab_base = G->tab_base;
+        d.tab_bytes = (int)((G->tab_used + 15) & ~size_t(15));
 
-        G->smem_pf = pf_smem_doubles(s.n_blocks, s.n, nb, T) * sizeof(double);
+        if (const char* cv = getenv("OPFG_CARVEOUT")) G->carveout_pct = atoi(cv);
+        G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T) * sizeof(double) + 31) & ~size_t(31);
+        {   // environments per CTA: stage the tables in shared memory when several environments share them
+            const size_t budget = 227 * 1024;
+            int E = (int)((budget - d.tab_bytes) / G->smem_pf);
+            E = std::min(E, std::min(15, 640 / T));   // named barriers 1..15; k_pf_multi is bounded to 640 threads
+            if (const char* ev = getenv("OPFG_ENVS_PER_CTA")) E = std::min(atoi(ev), std::min(15, 640 / T));
+            if (E < 2 || (size_t)d.tab_bytes * 3 > budget) E = 1;
+            G->envs_per_cta = E;
+        }
         G->smem_score = score_smem_doubles(nb, nbr, T) * sizeof(double);
         if (G->smem_pf > 227 * 1024) { delete G; return fail("grid needs %zu B shared memory per environment (> 227 KB)", G->smem_pf); }
 
@@ -549,7 +643,29 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             cudaFuncSetAttribute(k_pf<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_smem = smem;
         }
-        k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
+        static int carve_set = -1;
+        if (G->carveout_pct >= 0 && carve_set != G->carveout_pct) {
+            // leave part of the unified L1/shared array to L1: the shared schedule tables must stay
+            // L1-resident, otherwise every table read is an L2 round trip on the critical path
+            cudaFuncSetAttribute(k_pf<TT>, cudaFuncAttributePreferredSharedMemoryCarveout, G->carveout_pct);
+            carve_set = G->carveout_pct;
+        }
+        if (G->envs_per_cta > 1) {
+            const int E = G->envs_per_cta;
+            const size_t smem_multi = G->d.tab_bytes + (size_t)E * smem;
+            static size_t attr_multi = 48 * 1024;
+            if (smem_multi > attr_multi) {
+                cudaFuncSetAttribute(k_pf_multi<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                attr_multi = smem_multi;
+            }
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+            const int64_t groups = (B->n_env + E - 1) / E;
+            const unsigned grid = (unsigned)std::min<int64_t>(groups, n_sm);
+            k_pf_multi<TT><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8));
+        } else {
+            k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
+        }
     });
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -607,6 +723,17 @@ int opfg_observe(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
 #endif
     return 0;
 }
+
+#ifdef OPFG_PHASE_TIMING
+/* developer instrumentation: cycles of thread 0 per phase, summed over CTAs (8 slots) */
+extern "C" int opfg_debug_phase_cycles(OpfgGrid* G, unsigned long long* host_out, int reset) {
+    if (!G->d.phase_cycles) G->d.phase_cycles = (unsigned long long*)G->up(std::vector<unsigned long long>(96, 0ull));
+    cudaDeviceSynchronize();
+    if (host_out) cudaMemcpy(host_out, G->d.phase_cycles, 96 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(G->d.phase_cycles, 0, 96 * sizeof(unsigned long long));
+    return 0;
+}
+#endif
 
 int opfg_fp64_probe(int32_t n_blocks, int32_t iters, double* out, void* stream) {
     if (!out || n_blocks <= 0 || iters <= 0) return fail("bad argument");

@@ -22,6 +22,8 @@
 
 namespace opfg {
 
+struct U2 { uint32_t x, y; };
+
 struct GridDev {
     // sizes
     int nb, n, n_levels, n_blocks, n_fill, nnz_y, nbr, ng, n_ref;
@@ -36,12 +38,20 @@ struct GridDev {
     const double* va0_int;             // start angle (rad); ref buses keep it
     // schedule
     const int* level_ptr;
+    const unsigned char* diag_mode;    // [n_levels] 0: one lane per pivot, 1: eight lanes per pivot
     const int* fill_ids;
-    const int *dp_ptr, *dp_l, *dp_w, *dp_m;
-    const int *off_ptr, *off_tgt, *off_piv, *op_ptr, *op_l, *op_w;
-    const int *up_ptr, *up_w, *up_j;
+    // packed 16-bit block / pivot ids (n_blocks, nb < 65536 is checked at grid creation)
+    const int* dp_ptr;                 // [n+1] pair ranges of the diagonal items
+    const U2* dp_pack;                 // {l | w<<16, m}
+    const int* off_ptr;                // [n_levels+1] off-diagonal item ranges
+    const U2* off_hdr;                 // [n_items+1] {tgt | (piv+1)<<16, first pair}; last entry = sentinel
+    const uint32_t* op_pack;           // l | w<<16
+    const int* up_ptr;                 // [n+1]
+    const uint32_t* up_pack;           // w | j<<16
     // Ybus
-    const int *y_ptr, *y_col, *y_blk, *y_diag;
+    const int *y_ptr, *y_diag;
+    const U2* y_meta;                  // {col | (jacobian block + 1)<<16, row}
+    int nnz_y_nonref;                  // entries of the non-slack rows come first
     const double* y_val;               // [nnz_y*2] re,im  (written by the Ybus assembly kernel)
     const int *yc_ptr, *yc_branch, *yc_role;
     const double* br_param;            // [nbr*6] r x b g tap shift_rad  (ppc branch table)
@@ -79,6 +89,9 @@ struct GridDev {
     double valid_reward, invalid_penalty, invalid_obj_share;
     int n_obs;
     const int* obs_ref;
+    const char* tab_base;              // contiguous arena holding the power-flow tables
+    int tab_bytes;
+    unsigned long long* phase_cycles;  // developer instrumentation (OPFG_PHASE_TIMING builds), else unused
 };
 
 // ------------------------------------------------------------------ block context
@@ -87,9 +100,12 @@ template <int T>
 struct Ctx {
     int tid;
     double* red;   // shared scratch, >= T/32 doubles
+    int bar_id;    // 0: the environment owns the CTA; >0: named barrier of this environment's T threads
     __device__ __forceinline__ int nthreads() const { return T; }
     __device__ __forceinline__ void sync() const {
-        if (T == 32) __syncwarp(); else __syncthreads();
+        if (T == 32) __syncwarp();
+        else if (bar_id) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(T) : "memory");
+        else __syncthreads();
     }
     __device__ __forceinline__ double warp_max(double v) const {
 #pragma unroll
@@ -107,26 +123,35 @@ struct Ctx {
         v = warp_max(bad > 0 ? 0.0 : v);
         bad = warp_max(bad);
         if (T > 32) {
-            __syncthreads();
+            sync();
             if ((tid & 31) == 0) { red[tid >> 5] = v; red[(T >> 5) + (tid >> 5)] = bad; }
-            __syncthreads();
+            sync();
             v = red[0]; bad = red[T >> 5];
 #pragma unroll
             for (int w = 1; w < (T >> 5); ++w) { v = fmax(v, red[w]); bad = fmax(bad, red[(T >> 5) + w]); }
-            __syncthreads();
+            sync();
         }
         return bad > 0 ? NAN : v;
+    }
+    __device__ __forceinline__ bool wide_diag(unsigned char mode) const { return mode != 0; }
+    // values of lanes 0..5 of every aligned group of 8 lanes, broadcast to the whole group
+    __device__ __forceinline__ void gather8(double v, double& a, double& b, double& c, double& d,
+                                            double& y0, double& y1) const {
+        const int base = (tid & 31) & ~7;
+        a = __shfl_sync(0xffffffffu, v, base);      b = __shfl_sync(0xffffffffu, v, base + 1);
+        c = __shfl_sync(0xffffffffu, v, base + 2);  d = __shfl_sync(0xffffffffu, v, base + 3);
+        y0 = __shfl_sync(0xffffffffu, v, base + 4); y1 = __shfl_sync(0xffffffffu, v, base + 5);
     }
     __device__ __forceinline__ double block_sum(double v) const {
         v = warp_sum(v);
         if (T > 32) {
-            __syncthreads();
+            sync();
             if ((tid & 31) == 0) red[tid >> 5] = v;
-            __syncthreads();
+            sync();
             v = 0;
 #pragma unroll
             for (int w = 0; w < (T >> 5); ++w) v += red[w];
-            __syncthreads();
+            sync();
         }
         return v;
     }
@@ -136,11 +161,23 @@ template <int T>
 struct Ctx {
     int tid = 0;
     double* red = nullptr;
+    int bar_id = 0;
     int nthreads() const { return 1; }
     void sync() const {}
+    bool wide_diag(unsigned char) const { return false; }   // host walk: always one "lane" per pivot
+    void gather8(double, double&, double&, double&, double&, double&, double&) const {}
     double block_max(double v) const { return v; }
     double block_sum(double v) const { return v; }
 };
+#endif
+
+#if defined(OPFG_PHASE_TIMING) && defined(OPFG_DEVICE_BUILD)
+#define OPFG_TICK(slot) do { if (cx.tid == 0 && g.phase_cycles) { const long long now_ = clock64(); \
+    atomicAdd(g.phase_cycles + (slot), (unsigned long long)(now_ - tick_)); tick_ = now_; } } while (0)
+#define OPFG_TICK_INIT long long tick_ = clock64()
+#else
+#define OPFG_TICK(slot) do {} while (0)
+#define OPFG_TICK_INIT do {} while (0)
 #endif
 
 OPFG_HD double ref_val(const GridDev& g, const double* S, int r) { return r >= 0 ? S[r] : g.consts[-r - 1]; }
@@ -214,123 +251,175 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
 }
 
 // ------------------------------------------------------ kernels 2-4: Newton-Raphson
+// Shared-memory working set of one environment.  2x2 blocks are 32-byte aligned
+// (two 128-bit shared loads per block); V is kept as interleaved (re, im) pairs.
 struct PfSmem {
-    double *lu, *rhs, *vr, *vi, *vm, *va, *psp, *qsp, *red;
+    double *lu, *rhs, *vri, *vm, *va, *ivm, *red;
 };
 
 OPFG_HHD size_t pf_smem_doubles(int n_blocks, int n, int nb, int threads) {
-    return (size_t)4 * n_blocks + 2 * (size_t)n + 6 * (size_t)nb + 2 * (size_t)(threads / 32 + 1);
+    return (size_t)4 * n_blocks + 2 * (size_t)n + 5 * (size_t)nb + 2 * (size_t)(threads / 32 + 1) + 2;
 }
 
 OPFG_HD PfSmem pf_carve(double* base, int n_blocks, int n, int nb) {
     PfSmem s;
     s.lu = base;
     s.rhs = s.lu + 4 * (size_t)n_blocks;
-    s.vr = s.rhs + 2 * (size_t)n;
-    s.vi = s.vr + nb;
-    s.vm = s.vi + nb;
+    s.vri = s.rhs + 2 * (size_t)n;
+    s.vm = s.vri + 2 * (size_t)nb;
     s.va = s.vm + nb;
-    s.psp = s.va + nb;
-    s.qsp = s.psp + nb;
-    s.red = s.qsp + nb;
+    s.ivm = s.va + nb;
+    s.red = s.ivm + nb + (nb & 1);
     return s;
 }
 
-// Fused power mismatch (kernel 2) + Jacobian assembly into the fixed block
-// pattern (kernel 3) for block row i.  Returns the row's contribution to ||F||inf.
+struct D2 { double x, y; };
+#ifdef OPFG_DEVICE_BUILD
+OPFG_HD D2 ld2(const double* p) { const double2 v = *reinterpret_cast<const double2*>(p); return D2{v.x, v.y}; }
+OPFG_HD void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+OPFG_HD D2 ldg2(const double* p) { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); return D2{v.x, v.y}; }
+#else
+OPFG_HD D2 ld2(const double* p) { return D2{p[0], p[1]}; }
+OPFG_HD void st2(double* p, double x, double y) { p[0] = x; p[1] = y; }
+OPFG_HD D2 ldg2(const double* p) { return D2{p[0], p[1]}; }
+#endif
+
+// Row part of the fused power mismatch (kernel 2) + Jacobian (kernel 3): injected
+// current, S_i = V_i conj(I_i), mismatch into rhs, and -- if `jac` -- the diagonal
+// 2x2 block.  Returns the row's contribution to ||F||inf.  The off-diagonal blocks
+// are written entry-parallel by `jacobian_entry` (balanced over the lanes).
 // Formulas: pypower dSbus_dV.py in polar form [ext-mem], SURVEY.md App. B.4.
-OPFG_HD double row_mismatch_jacobian(const GridDev& g, const PfSmem& s, const double* yv, int i) {
-    const double vir = s.vr[i], vii = s.vi[i], vmi = s.vm[i];
+OPFG_HD double row_mismatch(const GridDev& g, const PfSmem& s, const double* yv, const double* sbus,
+                            int i, bool jac) {
+    const D2 sp = ldg2(sbus + 2 * g.bus_of_int[i]);          // P, Q set-point (global, issued early)
+    const D2 vi = ld2(s.vri + 2 * i);
     const bool pq = g.type_int[i] == OPFG_PQ;
-    double ir = 0, ii = 0, diag_ar = 0, diag_ai = 0;
     const int e0 = g.y_ptr[i], e1 = g.y_ptr[i + 1];
+    double ir = 0, ii = 0, dr = 0, di = 0;
     for (int e = e0; e < e1; ++e) {
-        const int j = g.y_col[e];
-        const double gr = yv[2 * e], bi = yv[2 * e + 1];
-        const double vjr = s.vr[j], vji = s.vi[j];
-        const double tr = gr * vjr - bi * vji, ti = gr * vji + bi * vjr;   // Y_ij V_j
+        const int j = (int)(g.y_meta[e].x & 0xffffu);
+        const D2 y = ld2(yv + 2 * e);                         // table: global or staged in shared memory
+        const D2 vj = ld2(s.vri + 2 * j);
+        const double tr = fma(y.x, vj.x, -(y.y * vj.y)), ti = fma(y.x, vj.y, y.y * vj.x);   // Y_ij V_j
         ir += tr; ii += ti;
-        const double ar = vir * tr + vii * ti, ai = vii * tr - vir * ti;   // V_i conj(Y_ij V_j)
-        if (e == e0) { diag_ar = ar; diag_ai = ai; continue; }             // diagonal entry is first
-        const int blk = g.y_blk[e];
-        if (blk < 0) continue;                                             // column is a ref bus
-        const double inv_vmj = 1.0 / s.vm[j];
-        double* b = s.lu + 4 * (size_t)blk;
-        b[0] = ai;                 // dP_i/dtheta_j
-        b[1] = ar * inv_vmj;       // dP_i/dVm_j
-        b[2] = pq ? -ar : 0.0;     // dQ_i/dtheta_j
-        b[3] = pq ? ai * inv_vmj : 0.0;
+        if (e == e0) { dr = tr; di = ti; }                    // the diagonal entry is first
     }
-    const double P = vir * ir + vii * ii, Q = vii * ir - vir * ii;          // S_i = V_i conj(I_i)
-    const double inv_vmi = 1.0 / vmi;
-    double* d = s.lu + 4 * (size_t)i;
-    d[0] = -Q + diag_ai;
-    d[1] = (diag_ar + P) * inv_vmi;
-    d[2] = pq ? P - diag_ar : 0.0;
-    d[3] = pq ? (diag_ai + Q) * inv_vmi : 1.0;
-    const double dp = P - s.psp[i], dq = pq ? Q - s.qsp[i] : 0.0;
-    s.rhs[2 * i] = -dp;
-    s.rhs[2 * i + 1] = -dq;
-    const double a = fabs(dp), c = fabs(dq);
+    const double P = fma(vi.x, ir, vi.y * ii), Q = fma(vi.y, ir, -(vi.x * ii));   // S_i = V_i conj(I_i)
+    if (jac) {
+        const double ar = fma(vi.x, dr, vi.y * di), ai = fma(vi.y, dr, -(vi.x * di));   // V_i conj(Y_ii V_i)
+        const double inv_vmi = s.ivm[i];
+        st2(s.lu + 4 * i, -Q + ai, (ar + P) * inv_vmi);
+        st2(s.lu + 4 * i + 2, pq ? P - ar : 0.0, pq ? (ai + Q) * inv_vmi : 1.0);
+    }
+    const double dp = P - sp.x, dq = pq ? Q - sp.y : 0.0;
+    st2(s.rhs + 2 * i, -dp, -dq);
     if (dp != dp || dq != dq) return NAN;
+    const double a = fabs(dp), c = fabs(dq);
     return a > c ? a : c;
 }
 
+// Off-diagonal Jacobian block fed by Ybus entry e = (i, j), i != j, both non-slack.
+OPFG_HD void jacobian_entry(const GridDev& g, const PfSmem& s, const double* yv, int e) {
+    const U2 m = g.y_meta[e];
+    const int blk = (int)(m.x >> 16) - 1;
+    if (blk < 0 || blk < g.n) return;                         // ref column, or the diagonal entry
+    const int j = (int)(m.x & 0xffffu), i = (int)m.y;
+    const D2 y = ld2(yv + 2 * e);
+    const D2 vj = ld2(s.vri + 2 * j), vi = ld2(s.vri + 2 * i);
+    const double tr = fma(y.x, vj.x, -(y.y * vj.y)), ti = fma(y.x, vj.y, y.y * vj.x);
+    const double ar = fma(vi.x, tr, vi.y * ti), ai = fma(vi.y, tr, -(vi.x * ti));   // V_i conj(Y_ij V_j)
+    const double inv_vmj = s.ivm[j];
+    const bool pq = g.type_int[i] == OPFG_PQ;
+    st2(s.lu + 4 * blk, ai, ar * inv_vmj);                    // dP/dtheta_j, dP/dVm_j
+    st2(s.lu + 4 * blk + 2, pq ? -ar : 0.0, pq ? ai * inv_vmj : 0.0);
+}
+
+// ---- diagonal pivot: D_k -= sum L~(k,m) W(m,k), y_k -= sum L~(k,m) t_m, invert, t_k = D^-1 y_k
+// (a) one lane per pivot
 OPFG_HD void lu_diag_item(const GridDev& g, const PfSmem& s, int k) {
-    double* D = s.lu + 4 * (size_t)k;
-    double a = D[0], b = D[1], c = D[2], d = D[3];
-    double y0 = s.rhs[2 * k], y1 = s.rhs[2 * k + 1];
-    for (int p = g.dp_ptr[k]; p < g.dp_ptr[k + 1]; ++p) {
-        const double* L = s.lu + 4 * (size_t)g.dp_l[p];
-        const double* W = s.lu + 4 * (size_t)g.dp_w[p];
-        const int m = g.dp_m[p];
-        const double l0 = L[0], l1 = L[1], l2 = L[2], l3 = L[3];
-        const double w0 = W[0], w1 = W[1], w2 = W[2], w3 = W[3];
-        const double t0 = s.rhs[2 * m], t1 = s.rhs[2 * m + 1];
-        a -= l0 * w0 + l1 * w2;  b -= l0 * w1 + l1 * w3;
-        c -= l2 * w0 + l3 * w2;  d -= l2 * w1 + l3 * w3;
-        y0 -= l0 * t0 + l1 * t1; y1 -= l2 * t0 + l3 * t1;
+    double* D = s.lu + 4 * k;
+    D2 r0 = ld2(D), r1 = ld2(D + 2), y = ld2(s.rhs + 2 * k);
+    const int pe = g.dp_ptr[k + 1];
+    for (int p = g.dp_ptr[k]; p < pe; ++p) {
+        const U2 id = g.dp_pack[p];
+        const double* L = s.lu + 4 * (id.x & 0xffffu);
+        const double* W = s.lu + 4 * (id.x >> 16);
+        const D2 l0 = ld2(L), l1 = ld2(L + 2), w0 = ld2(W), w1 = ld2(W + 2), t = ld2(s.rhs + 2 * id.y);
+        r0.x = fma(-l0.y, w1.x, fma(-l0.x, w0.x, r0.x));  r0.y = fma(-l0.y, w1.y, fma(-l0.x, w0.y, r0.y));
+        r1.x = fma(-l1.y, w1.x, fma(-l1.x, w0.x, r1.x));  r1.y = fma(-l1.y, w1.y, fma(-l1.x, w0.y, r1.y));
+        y.x = fma(-l0.y, t.y, fma(-l0.x, t.x, y.x));      y.y = fma(-l1.y, t.y, fma(-l1.x, t.x, y.y));
     }
-    const double r = 1.0 / (a * d - b * c);
-    const double ia = d * r, ib = -b * r, ic = -c * r, id = a * r;
-    D[0] = ia; D[1] = ib; D[2] = ic; D[3] = id;
-    s.rhs[2 * k] = ia * y0 + ib * y1;
-    s.rhs[2 * k + 1] = ic * y0 + id * y1;
+    const double r = 1.0 / fma(r0.x, r1.y, -(r0.y * r1.x));
+    const double ia = r1.y * r, ib = -r0.y * r, ic = -r1.x * r, id_ = r0.x * r;
+    st2(D, ia, ib);
+    st2(D + 2, ic, id_);
+    st2(s.rhs + 2 * k, fma(ia, y.x, ib * y.y), fma(ic, y.x, id_ * y.y));
+}
+
+// (b) eight lanes per pivot: lane `sub` < 4 owns element (sub>>1, sub&1) of the block,
+// lanes 4 and 5 own y_0 and y_1 (short, independent gather chains instead of one long one)
+OPFG_HD double lu_diag_component(const GridDev& g, const PfSmem& s, int k, int sub) {
+    const int r = sub < 4 ? (sub >> 1) : (sub - 4);
+    double acc = sub < 4 ? s.lu[4 * k + sub] : s.rhs[2 * k + r];
+    const int pe = g.dp_ptr[k + 1];
+    for (int p = g.dp_ptr[k]; p < pe; ++p) {
+        const U2 id = g.dp_pack[p];
+        const D2 l = ld2(s.lu + 4 * (id.x & 0xffffu) + 2 * r);
+        double wa, wb;
+        if (sub < 4) { const double* W = s.lu + 4 * (id.x >> 16) + (sub & 1); wa = W[0]; wb = W[2]; }
+        else { const D2 t = ld2(s.rhs + 2 * id.y); wa = t.x; wb = t.y; }
+        acc = fma(-l.y, wb, fma(-l.x, wa, acc));
+    }
+    return acc;
+}
+
+OPFG_HD void lu_diag_finish(const PfSmem& s, int k, int sub, double a, double b, double c, double d,
+                            double y0, double y1) {
+    const double r = 1.0 / fma(a, d, -(b * c));
+    const double ia = d * r, ib = -b * r, ic = -c * r, id_ = a * r;
+    if (sub == 0) s.lu[4 * k] = ia;
+    else if (sub == 1) s.lu[4 * k + 1] = ib;
+    else if (sub == 2) s.lu[4 * k + 2] = ic;
+    else if (sub == 3) s.lu[4 * k + 3] = id_;
+    else if (sub == 4) s.rhs[2 * k] = fma(ia, y0, ib * y1);
+    else if (sub == 5) s.rhs[2 * k + 1] = fma(ic, y0, id_ * y1);
 }
 
 OPFG_HD void lu_off_item(const GridDev& g, const PfSmem& s, int item) {
-    double* X = s.lu + 4 * (size_t)g.off_tgt[item];
-    double a = X[0], b = X[1], c = X[2], d = X[3];
-    for (int p = g.op_ptr[item]; p < g.op_ptr[item + 1]; ++p) {
-        const double* L = s.lu + 4 * (size_t)g.op_l[p];
-        const double* W = s.lu + 4 * (size_t)g.op_w[p];
-        const double l0 = L[0], l1 = L[1], l2 = L[2], l3 = L[3];
-        const double w0 = W[0], w1 = W[1], w2 = W[2], w3 = W[3];
-        a -= l0 * w0 + l1 * w2;  b -= l0 * w1 + l1 * w3;
-        c -= l2 * w0 + l3 * w2;  d -= l2 * w1 + l3 * w3;
+    const U2 hdr = g.off_hdr[item];
+    const int pe = (int)g.off_hdr[item + 1].y;
+    double* X = s.lu + 4 * (hdr.x & 0xffffu);
+    D2 r0 = ld2(X), r1 = ld2(X + 2);
+    for (int p = (int)hdr.y; p < pe; ++p) {
+        const uint32_t id = g.op_pack[p];
+        const double* L = s.lu + 4 * (id & 0xffffu);
+        const double* W = s.lu + 4 * (id >> 16);
+        const D2 l0 = ld2(L), l1 = ld2(L + 2), w0 = ld2(W), w1 = ld2(W + 2);
+        r0.x = fma(-l0.y, w1.x, fma(-l0.x, w0.x, r0.x));  r0.y = fma(-l0.y, w1.y, fma(-l0.x, w0.y, r0.y));
+        r1.x = fma(-l1.y, w1.x, fma(-l1.x, w0.x, r1.x));  r1.y = fma(-l1.y, w1.y, fma(-l1.x, w0.y, r1.y));
     }
-    const int piv = g.off_piv[item];
+    const int piv = (int)(hdr.x >> 16) - 1;
     if (piv >= 0) {   // W = D^-1 * U
-        const double* I = s.lu + 4 * (size_t)piv;
-        const double i0 = I[0], i1 = I[1], i2 = I[2], i3 = I[3];
-        const double na = i0 * a + i1 * c, nb_ = i0 * b + i1 * d;
-        const double nc = i2 * a + i3 * c, nd = i2 * b + i3 * d;
-        a = na; b = nb_; c = nc; d = nd;
+        const D2 i0 = ld2(s.lu + 4 * piv), i1 = ld2(s.lu + 4 * piv + 2);
+        const double a = fma(i0.x, r0.x, i0.y * r1.x), b = fma(i0.x, r0.y, i0.y * r1.y);
+        const double c = fma(i1.x, r0.x, i1.y * r1.x), d = fma(i1.x, r0.y, i1.y * r1.y);
+        r0.x = a; r0.y = b; r1.x = c; r1.y = d;
     }
-    X[0] = a; X[1] = b; X[2] = c; X[3] = d;
+    st2(X, r0.x, r0.y);
+    st2(X + 2, r1.x, r1.y);
 }
 
 OPFG_HD void bwd_item(const GridDev& g, const PfSmem& s, int k) {
-    double x0 = s.rhs[2 * k], x1 = s.rhs[2 * k + 1];
-    for (int p = g.up_ptr[k]; p < g.up_ptr[k + 1]; ++p) {
-        const double* W = s.lu + 4 * (size_t)g.up_w[p];
-        const int j = g.up_j[p];
-        const double xj0 = s.rhs[2 * j], xj1 = s.rhs[2 * j + 1];
-        x0 -= W[0] * xj0 + W[1] * xj1;
-        x1 -= W[2] * xj0 + W[3] * xj1;
+    D2 x = ld2(s.rhs + 2 * k);
+    const int pe = g.up_ptr[k + 1];
+    for (int p = g.up_ptr[k]; p < pe; ++p) {
+        const uint32_t id = g.up_pack[p];
+        const double* W = s.lu + 4 * (id & 0xffffu);
+        const D2 w0 = ld2(W), w1 = ld2(W + 2), xj = ld2(s.rhs + 2 * (id >> 16));
+        x.x = fma(-w0.y, xj.y, fma(-w0.x, xj.x, x.x));
+        x.y = fma(-w1.y, xj.y, fma(-w1.x, xj.x, x.y));
     }
-    s.rhs[2 * k] = x0;
-    s.rhs[2 * k + 1] = x1;
+    st2(s.rhs + 2 * k, x.x, x.y);
 }
 
 // One environment: DC start, Newton-Raphson to tolerance, write |V|, angle, flag.
@@ -344,23 +433,18 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
     const int n = g.n, nb = g.nb;
     PfSmem s = pf_carve(smem, g.n_blocks, n, nb);
     const double* yv = yval_env ? yval_env : g.y_val;
-
-    for (int i = cx.tid; i < nb; i += T) {
-        const int bus = g.bus_of_int[i];
-        s.psp[i] = sbus[2 * bus];
-        s.qsp[i] = sbus[2 * bus + 1];
-        s.vm[i] = g.vm0_int[i];
-        s.va[i] = g.va0_int[i];
-    }
-    cx.sync();
+    OPFG_TICK_INIT;
 
     if (g.init_dc) {   // pandapower init='dc': B' theta = P on the shared, pre-factorised B'
-        for (int k = cx.tid; k < n; k += T) s.rhs[k] = s.psp[k] + g.dc_rhs0[k];
+        for (int k = cx.tid; k < n; k += T) s.rhs[k] = sbus[2 * g.bus_of_int[k]] + g.dc_rhs0[k];
         cx.sync();
         for (int l = 0; l < g.n_levels; ++l) {
             for (int k = g.level_ptr[l] + cx.tid; k < g.level_ptr[l + 1]; k += T) {
                 double y = s.rhs[k];
-                for (int p = g.dp_ptr[k]; p < g.dp_ptr[k + 1]; ++p) y -= g.dc_val[g.dp_l[p]] * s.rhs[g.dp_m[p]];
+                for (int p = g.dp_ptr[k]; p < g.dp_ptr[k + 1]; ++p) {
+                    const U2 pr = g.dp_pack[p];
+                    y = fma(-g.dc_val[pr.x & 0xffffu], s.rhs[pr.y], y);
+                }
                 s.rhs[k] = y * g.dc_val[k];
             }
             cx.sync();
@@ -368,63 +452,100 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         for (int l = g.n_levels - 1; l >= 0; --l) {
             for (int k = g.level_ptr[l] + cx.tid; k < g.level_ptr[l + 1]; k += T) {
                 double x = s.rhs[k];
-                for (int p = g.up_ptr[k]; p < g.up_ptr[k + 1]; ++p) x -= g.dc_val[g.up_w[p]] * s.rhs[g.up_j[p]];
+                for (int p = g.up_ptr[k]; p < g.up_ptr[k + 1]; ++p) {
+                    const uint32_t pr = g.up_pack[p];
+                    x = fma(-g.dc_val[pr & 0xffffu], s.rhs[pr >> 16], x);
+                }
                 s.rhs[k] = x;
             }
             cx.sync();
         }
-        for (int k = cx.tid; k < n; k += T) s.va[k] = s.rhs[k];
-        cx.sync();
     }
+    OPFG_TICK(0);   // DC start
     for (int i = cx.tid; i < nb; i += T) {
+        const double vm = g.vm0_int[i];
+        const double va = (g.init_dc && i < n) ? s.rhs[i] : g.va0_int[i];
         double sn, cs;
-        sincos(s.va[i], &sn, &cs);
-        s.vr[i] = s.vm[i] * cs;
-        s.vi[i] = s.vm[i] * sn;
+        sincos(va, &sn, &cs);
+        s.vm[i] = vm; s.va[i] = va; s.ivm[i] = 1.0 / vm;
+        st2(s.vri + 2 * i, vm * cs, vm * sn);
     }
     cx.sync();
+    OPFG_TICK(7);   // initial V
 
     int it = 0;
     int converged = 0;
+    double prev = 1.0;
     while (true) {
-        for (int f = cx.tid; f < g.n_fill; f += T) {
-            double* b = s.lu + 4 * (size_t)g.fill_ids[f];
-            b[0] = 0; b[1] = 0; b[2] = 0; b[3] = 0;
+        // quadratic convergence: after a norm below 1e-4 the next one is almost surely below
+        // tol, so look at the mismatch alone first and build the Jacobian only if needed
+        bool jac = !(prev < 1e-4);
+        double nrm;
+        while (true) {
+            double part = 0;
+            bool bad = false;
+            for (int i = cx.tid; i < n; i += T) {
+                const double r = row_mismatch(g, s, yv, sbus, i, jac);
+                if (r != r) bad = true; else if (r > part) part = r;
+            }
+            if (jac) {
+                for (int e = cx.tid; e < g.nnz_y_nonref; e += T) jacobian_entry(g, s, yv, e);
+                for (int f = cx.tid; f < g.n_fill; f += T) {
+                    double* b = s.lu + 4 * g.fill_ids[f];
+                    st2(b, 0.0, 0.0);
+                    st2(b + 2, 0.0, 0.0);
+                }
+            }
+            nrm = cx.block_max(bad ? NAN : part);
+            cx.sync();
+            OPFG_TICK(jac ? 1 : 2);   // row pass with / without Jacobian
+            if (jac || nrm < g.tol || it >= g.max_iter || nrm != nrm) break;
+            jac = true;
         }
-        double nrm = 0;
-        bool bad = false;
-        for (int i = cx.tid; i < n; i += T) {
-            const double r = row_mismatch_jacobian(g, s, yv, i);
-            if (r != r) bad = true; else if (r > nrm) nrm = r;
-        }
-        nrm = cx.block_max(bad ? NAN : nrm);
-        cx.sync();
+        prev = nrm;
         if (nrm < g.tol) { converged = 1; break; }
         if (it >= g.max_iter || nrm != nrm) break;
         ++it;
-        int item = 0;
         for (int l = 0; l < g.n_levels; ++l) {
-            for (int k = g.level_ptr[l] + cx.tid; k < g.level_ptr[l + 1]; k += T) lu_diag_item(g, s, k);
+            const int lb = g.level_ptr[l], le = g.level_ptr[l + 1];
+            if (cx.wide_diag(g.diag_mode[l])) {
+                const int sub = cx.tid & 7, grp = cx.tid >> 3, ngrp = T >> 3;
+                for (int base = lb; base < le; base += ngrp) {       // uniform trip count per warp
+                    const int k = base + grp;
+                    const bool on = k < le && sub < 6;
+                    const double acc = on ? lu_diag_component(g, s, k, sub) : 0.0;
+                    double a, b, c, d, y0, y1;
+                    cx.gather8(acc, a, b, c, d, y0, y1);
+                    if (on) lu_diag_finish(s, k, sub, a, b, c, d, y0, y1);
+                }
+            } else {
+                for (int k = lb + cx.tid; k < le; k += T) lu_diag_item(g, s, k);
+            }
             cx.sync();
-            for (item = g.off_ptr[l] + cx.tid; item < g.off_ptr[l + 1]; item += T) lu_off_item(g, s, item);
+            OPFG_TICK(16 + l);
+            for (int item = g.off_ptr[l] + cx.tid; item < g.off_ptr[l + 1]; item += T) lu_off_item(g, s, item);
             cx.sync();
+            OPFG_TICK(32 + l);
         }
         for (int l = g.n_levels - 1; l >= 0; --l) {
             for (int k = g.level_ptr[l] + cx.tid; k < g.level_ptr[l + 1]; k += T) bwd_item(g, s, k);
             cx.sync();
+            OPFG_TICK(48 + l);
         }
         for (int k = cx.tid; k < n; k += T) {
-            double va = s.va[k] + s.rhs[2 * k];
-            double vm = s.vm[k] + ((g.type_int[k] == OPFG_PQ) ? s.rhs[2 * k + 1] : 0.0);
+            const D2 dx = ld2(s.rhs + 2 * k);
+            double va = s.va[k] + dx.x;
+            double vm = s.vm[k] + ((g.type_int[k] == OPFG_PQ) ? dx.y : 0.0);
             // V = Vm*exp(j*Va); Vm = |V|; Va = angle(V)  (newtonpf.py)
             if (vm < 0) { vm = -vm; va += M_PI; }
             if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
             double sn, cs;
             sincos(va, &sn, &cs);
-            s.va[k] = va; s.vm[k] = vm;
-            s.vr[k] = vm * cs; s.vi[k] = vm * sn;
+            s.va[k] = va; s.vm[k] = vm; s.ivm[k] = 1.0 / vm;
+            st2(s.vri + 2 * k, vm * cs, vm * sn);
         }
         cx.sync();
+        OPFG_TICK(6);
     }
     for (int i = cx.tid; i < nb; i += T) {
         const int bus = g.bus_of_int[i];
@@ -546,7 +667,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         const int i = g.int_of_bus[bus];
         double ir = 0, ii = 0;
         for (int e = g.y_ptr[i]; e < g.y_ptr[i + 1]; ++e) {
-            const int j = g.bus_of_int[g.y_col[e]];
+            const int j = g.bus_of_int[g.y_meta[e].x & 0xffffu];
             ir += yv[2 * e] * s.vr[j] - yv[2 * e + 1] * s.vi[j];
             ii += yv[2 * e] * s.vi[j] + yv[2 * e + 1] * s.vr[j];
         }
