@@ -152,7 +152,8 @@ typedef struct {
     int64_t n_env;
     const double* actions;   /* [B, n_act]   in  (opfg_assemble; NULL = keep set-points, Sbus only)   */
     double* state;           /* [B, n_state] in/out                                           */
-    double* sbus;            /* [B, nb, 2]   complex bus injections, ppc bus order, p.u.      */
+    double* sbus;            /* [B, nb, 2]   complex bus injections, ppc bus order, p.u.
+                                (opfg_assemble: NULL = write the set-points only)            */
     double* vm;              /* [B, nb]      out, p.u.                                        */
     double* va;              /* [B, nb]      out, radians                                     */
     uint8_t* converged;      /* [B]          out                                              */
@@ -205,6 +206,23 @@ int opfg_score(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 int opfg_observe(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 /* assemble -> pf_solve -> score, back to back on the stream */
 int opfg_step(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
+
+/* ---- per-row column programs -------------------------------------------------------------
+ * The env `_sampling` hooks of the reference (opfgym/envs/voltage_control.py:121-133,
+ * load_shedding.py:131-149, max_renewable.py:101-105 ...) derive per-sample bounds and prices
+ * row by row from sampled columns.  A row program runs, for every environment and every row of
+ * one table, a short list of ops on 16 f64 registers -- one launch per hook. */
+enum { OPFG_OP_LOAD_STATE = 0 /* r[dst] = S[b, a + row] */, OPFG_OP_LOAD_STATIC = 1 /* r[dst] = statics[a + row] */,
+       OPFG_OP_CONST = 2 /* r[dst] = imm */, OPFG_OP_ADD = 3, OPFG_OP_SUB = 4, OPFG_OP_MUL = 5, OPFG_OP_DIV = 6,
+       OPFG_OP_SQRT = 7 /* r[dst] = sqrt(r[a]) */, OPFG_OP_NEG = 8, OPFG_OP_MIN = 9, OPFG_OP_MAX = 10,
+       OPFG_OP_ABS = 11, OPFG_OP_STORE_STATE = 12 /* S[b, a + row] = r[b] */ };
+typedef struct { int32_t op, dst, a, b; double imm; } OpfgRowOp;
+typedef struct OpfgRowProgram OpfgRowProgram;
+int  opfg_row_program_create(int32_t n_rows, int32_t n_ops, const OpfgRowOp* ops /* host */,
+                             int32_t n_static, const double* statics /* host */, OpfgRowProgram** out);
+void opfg_row_program_destroy(OpfgRowProgram* program);
+int  opfg_row_program_run(const OpfgRowProgram* program, int64_t n_env, double* state, int32_t n_state,
+                          void* cuda_stream);
 
 /* FP64 FMA throughput probe for the roofline denominator (MEASURED_PEAKS.json has no FP64 figure):
  * every thread runs 8 independent DFMA chains of `iters` steps; flops = 2*8*iters*n_blocks*256.

@@ -69,6 +69,11 @@ class ScoringDesc(C.Structure):
                 ("n_obs", C.c_int32), ("obs_ref", _ip)]
 
 
+class RowOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32),
+                ("imm", C.c_double)]
+
+
 class Batch(C.Structure):
     _fields_ = [("n_env", C.c_int64)] + [(n, C.c_void_p) for n in
                 ("actions", "state", "sbus", "vm", "va", "converged", "iterations",
@@ -96,6 +101,10 @@ PROTOTYPES = {
     "opfg_score": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_observe": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "opfg_row_program_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(RowOp), C.c_int32,
+                                          _dp, C.POINTER(C.c_void_p)]),
+    "opfg_row_program_destroy": (None, [C.c_void_p]),
+    "opfg_row_program_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "opfg_fp64_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "opfg_launch_count": (C.c_int64, []),
 }

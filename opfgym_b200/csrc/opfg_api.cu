@@ -122,8 +122,50 @@ struct OpfgGrid {
     }
 };
 
+struct OpfgRowProgram {
+    int n_rows = 0, n_ops = 0;
+    OpfgRowOp* ops = nullptr;        // device
+    double* statics = nullptr;       // device
+    std::vector<OpfgRowOp> host_ops;
+    std::vector<double> host_statics;
+    ~OpfgRowProgram() { dev_free(ops); dev_free(statics); }
+};
+
+OPFG_HHD void row_program_exec(const OpfgRowOp* ops, int n_ops, const double* statics, int row, double* S) {
+    double r[16];
+    for (int i = 0; i < n_ops; ++i) {
+        const OpfgRowOp o = ops[i];
+        switch (o.op) {
+            case OPFG_OP_LOAD_STATE: r[o.dst] = S[o.a + row]; break;
+            case OPFG_OP_LOAD_STATIC: r[o.dst] = statics[o.a + row]; break;
+            case OPFG_OP_CONST: r[o.dst] = o.imm; break;
+            case OPFG_OP_ADD: r[o.dst] = r[o.a] + r[o.b]; break;
+            case OPFG_OP_SUB: r[o.dst] = r[o.a] - r[o.b]; break;
+            case OPFG_OP_MUL: r[o.dst] = r[o.a] * r[o.b]; break;
+            case OPFG_OP_DIV: r[o.dst] = r[o.a] / r[o.b]; break;
+            case OPFG_OP_SQRT: r[o.dst] = sqrt(r[o.a]); break;
+            case OPFG_OP_NEG: r[o.dst] = -r[o.a]; break;
+            case OPFG_OP_MIN: r[o.dst] = fmin(r[o.a], r[o.b]); break;
+            case OPFG_OP_MAX: r[o.dst] = fmax(r[o.a], r[o.b]); break;
+            case OPFG_OP_ABS: r[o.dst] = fabs(r[o.a]); break;
+            case OPFG_OP_STORE_STATE: S[o.a + row] = r[o.b]; break;
+            default: break;
+        }
+    }
+}
+
 // ------------------------------------------------------------------- kernels
 #ifndef OPFG_HOSTSIM
+__global__ void k_row_program(const OpfgRowOp* ops, int n_ops, const double* statics, int n_rows, int64_t n_env,
+                              double* state, int n_state) {
+    __shared__ OpfgRowOp sops[96];
+    for (int i = threadIdx.x; i < n_ops; i += blockDim.x) sops[i] = ops[i];
+    __syncthreads();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_env * n_rows) return;
+    const int64_t env = idx / n_rows;
+    row_program_exec(sops, n_ops, statics, (int)(idx % n_rows), state + env * (int64_t)n_state);
+}
 __global__ void k_branch_y(GridDev g) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < g.nbr) branch_admittance(g.br_param + 6 * (size_t)l, g.br_y + 8 * (size_t)l);
@@ -166,7 +208,7 @@ __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
     Ctx<T> cx{(int)threadIdx.x, nullptr, 0};
     const int64_t env = blockIdx.x;
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
-                 B.sbus + env * (int64_t)g.nb * 2);
+                 B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr);
 }
 template <int T>
 __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
@@ -607,14 +649,14 @@ int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
 int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (!G || !B) return fail("null argument");
     if (!G->has_assembly) return fail("opfg_set_assembly was not called");
-    if (!B->state || !B->sbus) return fail("opfg_assemble needs state and sbus (actions == NULL: Sbus scatter only)");
+    if (!B->state || (!B->sbus && !B->actions)) return fail("opfg_assemble needs state and at least one of actions / sbus");
     if (B->n_env <= 0) return 0;
 #ifdef OPFG_HOSTSIM
     (void)stream;
     Ctx<1> cx;
     for (int64_t env = 0; env < B->n_env; ++env)
         env_assemble(G->d, cx, B->actions ? B->actions + env * G->d.n_act : nullptr,
-                     B->state + env * (int64_t)G->d.n_state, B->sbus + env * (int64_t)G->d.nb * 2);
+                     B->state + env * (int64_t)G->d.n_state, B->sbus ? B->sbus + env * (int64_t)G->d.nb * 2 : nullptr);
 #else
     k_assemble<32><<<(unsigned)B->n_env, 32, 0, (cudaStream_t)stream>>>(G->d, *B);
     ++g_launches;
@@ -734,6 +776,51 @@ extern "C" int opfg_debug_phase_cycles(OpfgGrid* G, unsigned long long* host_out
     return 0;
 }
 #endif
+
+int opfg_row_program_create(int32_t n_rows, int32_t n_ops, const OpfgRowOp* ops, int32_t n_static,
+                            const double* statics, OpfgRowProgram** out) {
+    if (!ops || !out || n_rows < 0 || n_ops <= 0 || n_ops > 96) return fail("bad row program (1..96 ops)");
+    for (int i = 0; i < n_ops; ++i) {
+        const OpfgRowOp& o = ops[i];
+        const bool reg_ok = o.dst >= 0 && o.dst < 16;
+        if (o.op < 0 || o.op > OPFG_OP_STORE_STATE) return fail("row program: unknown op %d", o.op);
+        if (o.op != OPFG_OP_STORE_STATE && !reg_ok) return fail("row program: register out of range");
+        if (o.op >= OPFG_OP_ADD && o.op != OPFG_OP_STORE_STATE && (o.a < 0 || o.a >= 16)) return fail("row program: bad operand");
+        if (o.op == OPFG_OP_STORE_STATE && (o.b < 0 || o.b >= 16)) return fail("row program: bad store register");
+        if (o.op == OPFG_OP_LOAD_STATIC && (o.a < 0 || o.a + n_rows > n_static)) return fail("row program: static out of range");
+    }
+    auto* P = new OpfgRowProgram();
+    P->n_rows = n_rows; P->n_ops = n_ops;
+    P->host_ops.assign(ops, ops + n_ops);
+    P->host_statics.assign(statics, statics + n_static);
+    P->ops = (OpfgRowOp*)dev_alloc(sizeof(OpfgRowOp) * n_ops);
+    P->statics = (double*)dev_alloc(sizeof(double) * std::max(n_static, 1));
+    dev_put(P->ops, ops, sizeof(OpfgRowOp) * n_ops);
+    dev_put(P->statics, statics, sizeof(double) * n_static);
+    *out = P;
+    return 0;
+}
+
+void opfg_row_program_destroy(OpfgRowProgram* p) { delete p; }
+
+int opfg_row_program_run(const OpfgRowProgram* P, int64_t n_env, double* state, int32_t n_state, void* stream) {
+    if (!P || !state || n_env < 0) return fail("bad argument");
+    if (n_env == 0 || P->n_rows == 0) return 0;
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    for (int64_t env = 0; env < n_env; ++env)
+        for (int row = 0; row < P->n_rows; ++row)
+            row_program_exec(P->ops, P->n_ops, P->statics, row, state + env * (int64_t)n_state);
+#else
+    const int64_t total = n_env * P->n_rows;
+    k_row_program<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        P->ops, P->n_ops, P->statics, P->n_rows, n_env, state, n_state);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("row program launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
 
 int opfg_fp64_probe(int32_t n_blocks, int32_t iters, double* out, void* stream) {
     if (!out || n_blocks <= 0 || iters <= 0) return fail("bad argument");

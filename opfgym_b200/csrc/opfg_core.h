@@ -233,6 +233,7 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
         else if (kind == 2) sp = rint(sp);                        // :479-481
         S[g.act_slot[j]] = sp;
     }
+    if (sbus == nullptr) return;          // set-points only (reset applies the centre action)
     cx.sync();
 #ifdef OPFG_DEVICE_BUILD
     __threadfence_block();

@@ -56,6 +56,8 @@ class Engine:
         self.violations = self._zeros((B, max(nc, 1)), "float64")
         self.penalties = self._zeros((B, max(nc, 1)), "float64")
         self.obs = self._zeros((B, max(program.n_obs, 1)), obs_dtype)
+        # observation of the episode that just ended (kernel 5) vs. of the freshly reset one
+        self.obs_final = self._zeros((B, max(program.n_obs, 1)), obs_dtype)
         self.stats = self._zeros((capi.N_STATS,), "float64")
         self.n_constraints = nc
         self.batch = capi.Batch(
@@ -69,6 +71,13 @@ class Engine:
             obs_f32=self._ptr(self.obs) if obs_dtype == "float32" else None,
             obs_f64=self._ptr(self.obs) if obs_dtype == "float64" else None,
             stats=self._ptr(self.stats))
+        self.batch_final = capi.Batch.from_buffer_copy(self.batch)
+        if obs_dtype == "float32":
+            self.batch_final.obs_f32 = self._ptr(self.obs_final)
+        else:
+            self.batch_final.obs_f64 = self._ptr(self.obs_final)
+        self.batch_setpoints = capi.Batch.from_buffer_copy(self.batch)
+        self.batch_setpoints.sbus = None
 
     # ------------------------------------------------------- device plumbing (torch)
     def _setup_device(self, device):
@@ -107,12 +116,15 @@ class Engine:
         capi.check(self.lib, self.lib.opfg_philox_uniform(
             seed, first_env, stream_id, out.shape[0], out.shape[1], self._ptr(out), self._stream()))
 
-    def assemble(self, apply_actions: bool = True):
-        """Kernel 1.  ``apply_actions=False`` only re-scatters Sbus from the current cells."""
+    def assemble(self, apply_actions: bool = True, scatter_sbus: bool = True):
+        """Kernel 1.  ``apply_actions=False`` only re-scatters Sbus from the current cells;
+        ``scatter_sbus=False`` only writes the set-points."""
         batch = self.batch
         if not apply_actions:
             batch = capi.Batch.from_buffer_copy(self.batch)
             batch.actions = None
+        elif not scatter_sbus:
+            batch = self.batch_setpoints
         capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(batch), self._stream()))
 
     def pf_solve(self):
@@ -124,12 +136,14 @@ class Engine:
     def observe(self):
         capi.check(self.lib, self.lib.opfg_observe(self.handle, C.byref(self.batch), self._stream()))
 
-    def step(self):
+    def step(self, final_obs: bool = False):
         """assemble -> pf_solve -> score on the current stream (3 launches, no sync).
-        With ``self.pf_events`` set to a list, CUDA events bracketing the power-flow
-        kernel are appended to it (bench.py's roofline timing)."""
+        ``final_obs``: kernel 5 writes its observation to ``obs_final`` (the env layer's
+        auto-reset then fills ``obs`` without a copy).  With ``self.pf_events`` set to a list,
+        CUDA events bracketing the power-flow kernel are appended to it (bench.py's roofline)."""
+        batch = self.batch_final if final_obs else self.batch
         if self.pf_events is None:
-            capi.check(self.lib, self.lib.opfg_step(self.handle, C.byref(self.batch), self._stream()))
+            capi.check(self.lib, self.lib.opfg_step(self.handle, C.byref(batch), self._stream()))
             return
         self.assemble()
         e0 = self.torch.cuda.Event(enable_timing=True)
@@ -137,7 +151,7 @@ class Engine:
         e0.record()
         self.pf_solve()
         e1.record()
-        self.score()
+        capi.check(self.lib, self.lib.opfg_score(self.handle, C.byref(batch), self._stream()))
         self.pf_events.append((e0, e1))
 
     pf_events = None

@@ -72,15 +72,23 @@ class LoadShedding(BatchedOpfEnv):
         super()._sampling(*args, **kwargs)
         self._sample_from_range("poly_cost", "cp1_eur_per_mw", self.net.poly_cost.index)
         self._sample_from_range("pwl_cost", "cp1_eur_per_mw", self.net.pwl_cost.index)
-        if len(self.net.pwl_cost):
-            price = self.col("pwl_cost", "cp1_eur_per_mw")
-            self.col("pwl_cost", "price_charge").copy_(price * self.storage_efficiency)     # segment [-1000, 0]
-            self.col("pwl_cost", "price_discharge").copy_(price / self.storage_efficiency)  # segment [0, 1000]
-        self.col("load", "max_p_mw").copy_(
-            self.col("load", "p_mw") * self.static("load", "scaling") + 1e-9)
-        for unit in ("load", "storage"):
-            if not len(self.net[unit]):
-                continue
-            q = self._value(unit, "q_mvar", slice(None)) * self.static(unit, "scaling")
-            self.col(unit, "max_q_mvar").copy_((q + 1e-9).expand(self.num_envs, -1))
-            self.col(unit, "min_q_mvar").copy_((q - 1e-9).expand(self.num_envs, -1))
+        eta = self.storage_efficiency
+
+        def prices(r):      # pwl points [[-1000, 0, price*eta], [0, 1000, price/eta]]
+            r.store("price_charge", r.col("cp1_eur_per_mw") * eta)
+            r.store("price_discharge", r.col("cp1_eur_per_mw") / eta)
+
+        def load_bounds(r):
+            r.store("max_p_mw", r.col("p_mw") * r.col("scaling") + 1e-9)
+            q = r.col("q_mvar") * r.col("scaling")
+            r.store("max_q_mvar", q + 1e-9)
+            r.store("min_q_mvar", q - 1e-9)
+
+        def storage_bounds(r):
+            q = r.col("q_mvar") * r.col("scaling")
+            r.store("max_q_mvar", q + 1e-9)
+            r.store("min_q_mvar", q - 1e-9)
+
+        self.run_row_program("ls_prices", "pwl_cost", prices)
+        self.run_row_program("ls_load", "load", load_bounds)
+        self.run_row_program("ls_storage", "storage", storage_bounds)

@@ -50,5 +50,5 @@ class MaxRenewable(BatchedOpfEnv):
 
     def _sampling(self, *args, **kwargs):
         super()._sampling(*args, **kwargs)
-        self.col("sgen", "max_p_mw").copy_(
-            self.col("sgen", "p_mw") * self.static("sgen", "scaling") + 1e-6)
+        self.run_row_program("mr_bounds", "sgen", lambda r: r.store(
+            "max_p_mw", r.col("p_mw") * r.col("scaling") + 1e-6))

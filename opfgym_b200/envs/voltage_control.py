@@ -73,12 +73,16 @@ class VoltageControl(BatchedOpfEnv):
             for unit in ("sgen", "ext_grid", "storage"):
                 self._sample_from_range("poly_cost", "cq2_eur_per_mvar2", pc.index[pc.et == unit])
         for unit in ("sgen", "storage"):
-            if not len(self.net[unit]):
-                continue
-            p_scaled = self.col(unit, "p_mw") * self.static(unit, "scaling")
-            self.col(unit, "max_p_mw").copy_(p_scaled + 1e-9)
-            self.col(unit, "min_p_mw").copy_(p_scaled - 1e-9)
-            q_max = (self.static(unit, "max_s_mva") ** 2 - self.col(unit, "max_p_mw") ** 2) ** 0.5
-            self.col(unit, "min_q_mvar").copy_(-q_max)
-            self.col(unit, "max_q_mvar").copy_(q_max)
-            self.col(unit, "q_mvar").zero_()
+            self.run_row_program("vc_bounds", unit, self._bounds_program)
+
+    @staticmethod
+    def _bounds_program(r):
+        # active power is not controllable: pin its bounds to the sampled value; offer the
+        # whole remaining apparent-power capability as reactive range; start from Q = 0
+        p_max = r.col("p_mw") * r.col("scaling") + 1e-9
+        r.store("max_p_mw", p_max)
+        r.store("min_p_mw", r.col("p_mw") * r.col("scaling") - 1e-9)
+        q_max = (r.col("max_s_mva") ** 2 - p_max ** 2) ** 0.5
+        r.store("min_q_mvar", -q_max)
+        r.store("max_q_mvar", q_max)
+        r.store("q_mvar", 0.0)

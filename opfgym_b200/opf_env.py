@@ -72,7 +72,7 @@ class BatchedOpfEnv:
                  device=None, rank: int = 0, world_size: int = 1, obs_dtype: str = "float32",
                  dynamic_columns=(), pwl_price_columns=None, tolerance_mva: float = 1e-8,
                  max_iteration: int = 10, engine_cls=Engine, engine_kwargs: dict | None = None,
-                 copy_outputs: bool = True, **kwargs):
+                 copy_outputs: bool = True, validate_actions: bool = False, **kwargs):
         unknown = set(kwargs) - _SPLIT_KWARGS
         if unknown:
             raise TypeError(f"unknown keyword arguments: {sorted(unknown)}")
@@ -93,6 +93,10 @@ class BatchedOpfEnv:
 
         self.net = net
         self.copy_outputs = copy_outputs   # False: returned tensors alias engine buffers
+        # The reference asserts `not isnan(action)` (opf_env.py:382).  Checking on the host costs a
+        # device sync per step; by default a NaN action simply propagates: that env comes back
+        # non-converged with NaN reward/obs (its neighbours in the batch are unaffected).
+        self.validate_actions = validate_actions
         self.num_envs = int(num_envs)
         self.profiles = profiles
         self.obs_keys = list(observation_keys)
@@ -167,6 +171,8 @@ class BatchedOpfEnv:
         self._stream_in_episode = 0
         self._sample_cache = {}
         self._static_cache = {}
+        self._row_programs = {}
+        self._flags = None
         self.test = False
         self.power_flow_available = False
 
@@ -194,6 +200,7 @@ class BatchedOpfEnv:
         self.engine = self._engine_cls(self.program, self.num_envs, **self._engine_args)
         self.engine.state.copy_(state)
         self._sample_cache.clear()
+        self._row_programs.clear()
 
     # ------------------------------------------------------------------ column access
     def col(self, table: str, column: str):
@@ -209,6 +216,24 @@ class BatchedOpfEnv:
 
     def positions(self, table: str, idxs):
         return self.net[table].index.get_indexer(np.asarray(idxs))
+
+    # ---------------------------------------------------------------- hook programs
+    def run_row_program(self, name: str, table: str, build):
+        """Run the row program ``name`` (compiled on first use from ``build(r)``, which
+        writes the hook's formulas on a ``RowProgram``) for all environments: ONE launch."""
+        from .rowprog import CompiledRowProgram, RowProgram
+        key = (name, table)
+        if key not in self._row_programs:
+            if not len(self.net[table]):
+                self._row_programs[key] = None
+            else:
+                rp = RowProgram(self, table)
+                build(rp)
+                ops, statics = rp.compile()
+                self._row_programs[key] = CompiledRowProgram(self.engine, rp.n_rows, ops, statics)
+        prog = self._row_programs[key]
+        if prog is not None:
+            prog.run()
 
     # ------------------------------------------------------------------------ sampling
     def _next_stream(self) -> int:
@@ -335,7 +360,7 @@ class BatchedOpfEnv:
             self.engine.philox_uniform(act, self.seed, self.first_env, self._next_stream())
         else:
             act.fill_(0.5)
-        self.engine.assemble()
+        self.engine.assemble(scatter_sbus=self.pf_for_obs)
         if self.pf_for_obs:
             # the reference re-samples envs whose reset power flow fails (opf_env.py:209-214);
             # here such envs simply start with a NaN observation and are flagged in `converged`
@@ -345,8 +370,8 @@ class BatchedOpfEnv:
         else:
             self.engine.observe()
 
-    def _obs_out(self):
-        obs = self.engine.obs
+    def _obs_out(self, final: bool = False):
+        obs = self.engine.obs_final if final else self.engine.obs
         if self.add_mean_obs:
             parts, k = [], 0
             for _, _, idxs in self.obs_keys:
@@ -364,22 +389,25 @@ class BatchedOpfEnv:
         observation of the finished episode."""
         xp = self.xp
         act = xp.as_tensor(actions, device=self.device)
-        if xp.isnan(act).any():
+        if self.validate_actions and xp.isnan(act).any():   # host sync; off by default
             raise AssertionError("NaN in actions")     # opf_env.py:382
         self.engine.actions.copy_(act.reshape(self.engine.actions.shape))
-        self.engine.step()
+        self.engine.step(final_obs=True)
         self.power_flow_available = True
         e = self.engine
-        reward = e.reward.clone()
+        keep = (lambda t: t.clone()) if self.copy_outputs else (lambda t: t)
+        reward = keep(e.reward)
         if self.clipped_action_penalty:
-            reward -= self._mean_correction(act) * self.clipped_action_penalty
+            reward = reward - self._mean_correction(act) * self.clipped_action_penalty
         nc = max(len(self.constraints), 1)
-        info = {"valids": e.valids[:, :nc].bool(), "violations": e.violations[:, :nc].clone(),
-                "unscaled_penalties": e.penalties[:, :nc].clone(), "cost": e.cost.clone(),
-                "converged": e.converged.bool(), "iterations": e.iterations.clone(),
-                "final_obs": self._obs_out().clone()}   # always copied: reset overwrites it
-        terminated = xp.ones(self.num_envs, dtype=xp.bool, device=self.device)
-        truncated = xp.zeros(self.num_envs, dtype=xp.bool, device=self.device)
+        info = {"valids": e.valids[:, :nc].bool(), "violations": keep(e.violations[:, :nc]),
+                "unscaled_penalties": keep(e.penalties[:, :nc]), "cost": keep(e.cost),
+                "converged": e.converged.bool(), "iterations": keep(e.iterations),
+                "final_obs": self._obs_out(final=True)}
+        if self._flags is None:
+            self._flags = (xp.ones(self.num_envs, dtype=xp.bool, device=self.device),
+                           xp.zeros(self.num_envs, dtype=xp.bool, device=self.device))
+        terminated, truncated = (keep(self._flags[0]), keep(self._flags[1]))
         self._begin_episode()
         return self._obs_out(), reward, terminated, truncated, info
 

@@ -35,8 +35,17 @@ def test_vector_env_api_shapes_and_types():
     assert not torch.equal(obs2, info["final_obs"])             # same-step auto-reset happened
     assert not torch.isnan(reward).any()
     env.step(act.numpy().astype(np.float32))                    # numpy / float32 actions accepted
-    with pytest.raises(AssertionError):
-        env.step(torch.full((6, 14), float("nan"), dtype=torch.float64))
+    # a NaN action is data, not a crash: that env alone comes back non-converged with NaN reward
+    bad = torch.rand(6, 14, dtype=torch.float64)
+    bad[2, 3] = float("nan")
+    _, reward, term, _, info = env.step(bad)
+    assert info["converged"].tolist() == [True, True, False, True, True, True]
+    assert torch.isnan(reward[2]) and not torch.isnan(reward[[0, 1, 3, 4, 5]]).any()
+    assert (info["violations"][2] == 1).all() and not info["valids"][2].any()   # opf_env.py:395-398
+    strict = make(validate_actions=True)
+    strict.reset(seed=1)
+    with pytest.raises(AssertionError):                           # opf_env.py:382
+        strict.step(torch.full((6, 14), float("nan"), dtype=torch.float64))
 
 
 def test_sampled_state_within_bounds_and_hook_columns():
