@@ -108,6 +108,7 @@ enum { OPFG_REWARD_SUMMATION = 0, OPFG_REWARD_REPLACEMENT = 1, OPFG_REWARD_PARAM
 
 /* result cells, constraints, costs, reward, observation gather (kernel 5) */
 typedef struct {
+    int32_t n_inputs;                /* S[:, n_inputs:] are result cells (written by opfg_score) */
     /* where results go in S (-1 = not materialised) */
     int32_t n_pp_bus;
     const int32_t* pp_bus_lookup;    /* host [n_pp_bus] pandapower bus -> ppc bus (-1 dropped) */

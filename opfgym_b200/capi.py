@@ -47,7 +47,7 @@ class AssemblyDesc(C.Structure):
 
 
 class ScoringDesc(C.Structure):
-    _fields_ = [("n_pp_bus", C.c_int32), ("pp_bus_lookup", _ip),
+    _fields_ = [("n_inputs", C.c_int32), ("n_pp_bus", C.c_int32), ("pp_bus_lookup", _ip),
                 ("res_bus_vm_slot", C.c_int32), ("res_bus_va_slot", C.c_int32),
                 ("branch_loading_slot", _ip), ("branch_flow_slot", _ip),
                 ("rate_f", _dp), ("rate_t", _dp), ("gen_p_slot", _ip), ("gen_q_slot", _ip),

@@ -202,7 +202,8 @@ class Compiler:
             else:
                 raise NotImplementedError(f"result column {table}.{column} is not produced by the engine")
 
-        # ---- initial state row ----------------------------------------------
+        # ---- initial state row (even width: rows are moved as 16-byte words) --------
+        lay.n += lay.n & 1
         init = np.full(lay.n, np.nan)
         for (table, column), (start, n_rows) in lay.columns.items():
             if _is_res(table):
@@ -338,7 +339,7 @@ class Compiler:
 
         rp = reward_function.device_params()
         scoring = dict(
-            n_pp_bus=len(net.bus), pp_bus_lookup=ppc.bus_lookup.astype(_I32),
+            n_inputs=lay.n_inputs, n_pp_bus=len(net.bus), pp_bus_lookup=ppc.bus_lookup.astype(_I32),
             res_bus_vm_slot=res_vm, res_bus_va_slot=res_va,
             branch_loading_slot=loading_slot, branch_flow_slot=flow_slot,
             rate_f=ppc.rate_f.astype(float), rate_t=ppc.rate_t.astype(float),
@@ -415,7 +416,7 @@ def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_l
     s = program.scoring
     r = s["reward"]
     sd = capi.ScoringDesc(
-        n_pp_bus=s["n_pp_bus"], pp_bus_lookup=iptr(s["pp_bus_lookup"]),
+        n_inputs=s["n_inputs"], n_pp_bus=s["n_pp_bus"], pp_bus_lookup=iptr(s["pp_bus_lookup"]),
         res_bus_vm_slot=s["res_bus_vm_slot"], res_bus_va_slot=s["res_bus_va_slot"],
         branch_loading_slot=iptr(s["branch_loading_slot"]), branch_flow_slot=iptr(s["branch_flow_slot"]),
         rate_f=dptr(s["rate_f"]), rate_t=dptr(s["rate_t"]),

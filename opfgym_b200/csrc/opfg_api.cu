@@ -105,6 +105,34 @@ struct OpfgGrid {
         return (T*)p;
     }
 
+    char* tab2_base = nullptr;
+    size_t tab2_cap = 0, tab2_used = 0;
+    template <class T>
+    const T* tab2(const T* src, size_t n, bool from_device = false) {
+        tab2_used = (tab2_used + 15) & ~size_t(15);
+        const size_t bytes = n * sizeof(T);
+        if (tab2_used + bytes > tab2_cap) throw std::runtime_error("scoring table arena overflow");
+        char* p = tab2_base + tab2_used;
+        if (bytes) {
+#ifdef OPFG_HOSTSIM
+            memcpy(p, src, bytes);
+#else
+            cudaMemcpy(p, src, bytes, from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+#endif
+        }
+        tab2_used += bytes;
+        return (const T*)p;
+    }
+    template <class T>
+    const T* tab2(const std::vector<T>& v) { return tab2(v.data(), v.size()); }
+    std::vector<double> consts_host;
+    const double* score_consts = nullptr;
+    const double* score_br_y = nullptr;
+    const int *score_br_f = nullptr, *score_br_t = nullptr;
+    int score_envs_per_cta = 1;
+    int score_threads = 32;
+    size_t score_env_bytes = 0;
+
     template <class T>
     const T* up(const std::vector<T>& v) {
         void* p = dev_alloc(v.size() * sizeof(T));
@@ -252,7 +280,7 @@ __global__ void __launch_bounds__(T) k_score(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
     const int64_t env = blockIdx.x;
     Ctx<T> cx{(int)threadIdx.x, sm + score_smem_doubles(g.nb, g.nbr, T) - 2 * (T / 32 + 1), 0};
-    env_score(g, cx, sm, B, env, nullptr);
+    env_score(g, cx, sm, B, env, nullptr, B.state + env * (int64_t)g.n_state);
 }
 
 __global__ void k_observe(GridDev g, OpfgBatch B) {
@@ -274,6 +302,53 @@ __global__ void __launch_bounds__(256) k_fp64_probe(int iters, double* out) {
     }
     const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
+}
+
+// Kernel 5, persistent multi-environment form: scoring tables AND each environment's state row are
+// staged in shared memory (one coalesced sweep in, results + observation out), so the many small
+// reference-chasing reads of constraints / costs / observation gather never leave the SM.
+template <int T>
+__global__ void __launch_bounds__(1024) k_score_multi(GridDev g, OpfgBatch B, int E, int env_doubles,
+                                                     const double* consts, const double* br_y, const int* br_f,
+                                                     const int* br_t) {
+    extern __shared__ __align__(16) double sm[];
+    {
+        const int4* src = reinterpret_cast<const int4*>(g.tab2_base);
+        int4* dst = reinterpret_cast<int4*>(sm);
+        for (int i = threadIdx.x; i < g.tab2_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const char* sbase = reinterpret_cast<const char*>(sm);
+    g.consts = consts; g.br_y = const_cast<double*>(br_y); g.br_f = br_f; g.br_t = br_t;
+#define OPFG_REBASE2(field) g.field = (decltype(g.field))(sbase + (reinterpret_cast<const char*>(g.field) - g.tab2_base))
+    OPFG_REBASE2(pp_lookup); OPFG_REBASE2(br_loading_slot); OPFG_REBASE2(br_flow_slot); OPFG_REBASE2(rate_f); OPFG_REBASE2(rate_t);
+    OPFG_REBASE2(gen_bus); OPFG_REBASE2(gen_q_share); OPFG_REBASE2(gen_p_slot); OPFG_REBASE2(gen_q_slot);
+    OPFG_REBASE2(con_ptr); OPFG_REBASE2(con_value); OPFG_REBASE2(con_value_scale); OPFG_REBASE2(con_min); OPFG_REBASE2(con_max);
+    OPFG_REBASE2(con_bound_mul); OPFG_REBASE2(con_autoscale); OPFG_REBASE2(con_worst); OPFG_REBASE2(con_pfactor);
+    OPFG_REBASE2(con_ppower); OPFG_REBASE2(con_pcount);
+    OPFG_REBASE2(poly_p); OPFG_REBASE2(poly_q); OPFG_REBASE2(poly_p_mul); OPFG_REBASE2(poly_q_mul); OPFG_REBASE2(poly_coef);
+    OPFG_REBASE2(pwl_v); OPFG_REBASE2(pwl_v_mul); OPFG_REBASE2(pwl_seg); OPFG_REBASE2(obs_ref);
+    OPFG_REBASE2(consts); OPFG_REBASE2(br_y); OPFG_REBASE2(br_f); OPFG_REBASE2(br_t);
+#undef OPFG_REBASE2
+    const int e_local = threadIdx.x / T, tid = threadIdx.x % T;
+    double* mine = sm + g.tab2_bytes / 8 + (size_t)e_local * env_doubles;
+    double* row = mine;                                           // [n_state] staged state row
+    double* scratch = mine + g.n_state + (g.n_state & 1);
+    Ctx<T> cx{tid, scratch + score_smem_doubles(g.nb, g.nbr, T) - 2 * (T / 32 + 1), 1 + e_local};
+    for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
+        double* Sg = B.state + env * (int64_t)g.n_state;
+        if (B.converged[env]) {
+            const double2* src = reinterpret_cast<const double2*>(Sg);
+            double2* dst = reinterpret_cast<double2*>(row);
+            for (int i = tid; i < g.n_state / 2; i += T) dst[i] = src[i];
+        }
+        cx.sync();
+        env_score(g, cx, scratch, B, env, nullptr, row);
+        cx.sync();
+        if (B.converged[env])
+            for (int i = g.n_inputs + tid; i < g.n_state; i += T) Sg[i] = row[i];
+        cx.sync();
+    }
 }
 
 #define OPFG_DISPATCH_T(T_, ...)                                     \
@@ -484,6 +559,7 @@ int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
         GridDev& d = G->d;
         d.n_state = a->n_state; d.n_const = a->n_const; d.n_act = a->n_act; d.n_inj = a->n_inj;
         d.consts = G->up(a->consts, a->n_const);
+        G->consts_host.assign(a->consts, a->consts + a->n_const);
         auto check_ref = [&](const int* r, int n, const char* what) {
             for (int i = 0; i < n; ++i)
                 if (r[i] >= a->n_state || -r[i] - 1 >= a->n_const) throw std::runtime_error(std::string("reference out of range in ") + what);
@@ -524,30 +600,39 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
     try {
         GridDev& d = G->d;
         const int nbr = d.nbr, ng = d.ng;
-        d.n_pp_bus = sc->n_pp_bus;
-        d.pp_lookup = G->up(sc->pp_bus_lookup, sc->n_pp_bus);
-        d.res_vm_slot = sc->res_bus_vm_slot; d.res_va_slot = sc->res_bus_va_slot;
-        d.br_loading_slot = G->up(sc->branch_loading_slot, nbr);
-        d.br_flow_slot = G->up(sc->branch_flow_slot, nbr);
-        d.rate_f = G->up(sc->rate_f, nbr); d.rate_t = G->up(sc->rate_t, nbr);
-        d.gen_bus = G->up(G->gen_bus_host);
-        d.gen_q_share = G->up(G->gen_q_share_host);
-        d.gen_p_slot = G->up(sc->gen_p_slot, ng); d.gen_q_slot = G->up(sc->gen_q_slot, ng);
-        d.n_con = sc->n_constraints;
         const int n_el = sc->n_constraints ? sc->con_ptr[sc->n_constraints] : 0;
-        d.con_ptr = G->up(sc->con_ptr, sc->n_constraints + 1);
-        d.con_value = G->up(sc->con_value, n_el); d.con_value_scale = G->up(sc->con_value_scale, n_el);
-        d.con_min = G->up(sc->con_min, n_el); d.con_max = G->up(sc->con_max, n_el);
-        d.con_bound_mul = G->up(sc->con_bound_mul, n_el);
-        d.con_autoscale = G->up(sc->con_autoscale, d.n_con); d.con_worst = G->up(sc->con_worst_case, d.n_con);
-        d.con_pfactor = G->up(sc->con_penalty_factor, d.n_con); d.con_ppower = G->up(sc->con_penalty_power, d.n_con);
-        d.con_pcount = G->up(sc->con_count_penalty, d.n_con);
+        {
+            const size_t cap = 8192 + 16 * (size_t)sc->n_pp_bus + 96 * (size_t)nbr + 32 * (size_t)ng + 48 * (size_t)n_el +
+                               64 * (size_t)sc->n_constraints + 64 * (size_t)sc->n_poly + 32 * (size_t)sc->n_pwl * (sc->n_pwl_seg + 1) +
+                               8 * (size_t)sc->n_obs + 8 * G->consts_host.size() + 16 * (size_t)d.nb;
+            G->tab2_base = (char*)dev_alloc(cap);
+            if (!G->tab2_base) throw std::runtime_error("device allocation failed");
+            G->allocs.push_back(G->tab2_base);
+            G->tab2_cap = cap; G->tab2_used = 0;
+        }
+        d.n_pp_bus = sc->n_pp_bus;
+        d.pp_lookup = G->tab2(sc->pp_bus_lookup, sc->n_pp_bus);
+        d.res_vm_slot = sc->res_bus_vm_slot; d.res_va_slot = sc->res_bus_va_slot;
+        d.br_loading_slot = G->tab2(sc->branch_loading_slot, nbr);
+        d.br_flow_slot = G->tab2(sc->branch_flow_slot, nbr);
+        d.rate_f = G->tab2(sc->rate_f, nbr); d.rate_t = G->tab2(sc->rate_t, nbr);
+        d.gen_bus = G->tab2(G->gen_bus_host);
+        d.gen_q_share = G->tab2(G->gen_q_share_host);
+        d.gen_p_slot = G->tab2(sc->gen_p_slot, ng); d.gen_q_slot = G->tab2(sc->gen_q_slot, ng);
+        d.n_con = sc->n_constraints;
+        d.con_ptr = G->tab2(sc->con_ptr, sc->n_constraints + 1);
+        d.con_value = G->tab2(sc->con_value, n_el); d.con_value_scale = G->tab2(sc->con_value_scale, n_el);
+        d.con_min = G->tab2(sc->con_min, n_el); d.con_max = G->tab2(sc->con_max, n_el);
+        d.con_bound_mul = G->tab2(sc->con_bound_mul, n_el);
+        d.con_autoscale = G->tab2(sc->con_autoscale, d.n_con); d.con_worst = G->tab2(sc->con_worst_case, d.n_con);
+        d.con_pfactor = G->tab2(sc->con_penalty_factor, d.n_con); d.con_ppower = G->tab2(sc->con_penalty_power, d.n_con);
+        d.con_pcount = G->tab2(sc->con_count_penalty, d.n_con);
         d.n_poly = sc->n_poly; d.n_pwl = sc->n_pwl; d.n_pwl_seg = sc->n_pwl_seg;
-        d.poly_p = G->up(sc->poly_p, d.n_poly); d.poly_q = G->up(sc->poly_q, d.n_poly);
-        d.poly_p_mul = G->up(sc->poly_p_mul, d.n_poly); d.poly_q_mul = G->up(sc->poly_q_mul, d.n_poly);
-        d.poly_coef = G->up(sc->poly_coef, 6 * (size_t)d.n_poly);
-        d.pwl_v = G->up(sc->pwl_v, d.n_pwl); d.pwl_v_mul = G->up(sc->pwl_v_mul, d.n_pwl);
-        d.pwl_seg = G->up(sc->pwl_seg, 3 * (size_t)d.n_pwl * d.n_pwl_seg);
+        d.poly_p = G->tab2(sc->poly_p, d.n_poly); d.poly_q = G->tab2(sc->poly_q, d.n_poly);
+        d.poly_p_mul = G->tab2(sc->poly_p_mul, d.n_poly); d.poly_q_mul = G->tab2(sc->poly_q_mul, d.n_poly);
+        d.poly_coef = G->tab2(sc->poly_coef, 6 * (size_t)d.n_poly);
+        d.pwl_v = G->tab2(sc->pwl_v, d.n_pwl); d.pwl_v_mul = G->tab2(sc->pwl_v_mul, d.n_pwl);
+        d.pwl_seg = G->tab2(sc->pwl_seg, 3 * (size_t)d.n_pwl * d.n_pwl_seg);
         d.reward_kind = sc->reward_kind; d.penalty_weight = sc->penalty_weight;
         d.clip_lo = sc->clip_lo; d.clip_hi = sc->clip_hi;
         d.obj_factor = sc->objective_factor; d.obj_bias = sc->objective_bias;
@@ -555,7 +640,16 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
         d.valid_reward = sc->valid_reward; d.invalid_penalty = sc->invalid_penalty;
         d.invalid_obj_share = sc->invalid_objective_share;
         d.n_obs = sc->n_obs;
-        d.obs_ref = G->up(sc->obs_ref, sc->n_obs);
+        d.obs_ref = G->tab2(sc->obs_ref, sc->n_obs);
+        // copies of the grid tables that the branch-flow part of kernel 5 reads
+        G->score_consts = G->tab2(G->consts_host);
+        G->score_br_y = G->tab2((const double*)d.br_y, 8 * (size_t)nbr, true);
+        G->score_br_f = G->tab2(d.br_f, nbr, true);
+        G->score_br_t = G->tab2(d.br_t, nbr, true);
+        d.tab2_base = G->tab2_base;
+        d.tab2_bytes = (int)((G->tab2_used + 15) & ~size_t(15));
+        d.n_inputs = sc->n_inputs;
+        if (sc->n_inputs < 0 || sc->n_inputs > d.n_state) throw std::runtime_error("n_inputs out of range");
         int cells = 0;
         if (d.res_vm_slot >= 0) cells += d.n_pp_bus;
         if (d.res_va_slot >= 0) cells += d.n_pp_bus;
@@ -563,6 +657,21 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
         for (int gI = 0; gI < ng; ++gI) cells += (sc->gen_p_slot[gI] >= 0) + (sc->gen_q_slot[gI] >= 0);
         G->n_result_cells = cells;
         G->flops_score = 60.0 * nbr + 30.0 * d.nb + 10.0 * n_el + 14.0 * d.n_poly + 20.0 * d.n_pwl * d.n_pwl_seg + 40.0;
+        {   // multi-environment CTAs for kernel 5: tables + the state row staged in shared memory
+            // one warp per environment on small grids: reductions are pure shuffles, no named barriers
+            int T = (d.nb + nbr <= 600) ? 32 : d.threads;
+            if (const char* tv = getenv("OPFG_SCORE_THREADS")) T = atoi(tv);
+            G->score_threads = T;
+            const size_t env_doubles = score_smem_doubles(d.nb, nbr, T) + (size_t)d.n_state + 2;
+            G->score_env_bytes = (env_doubles * 8 + 31) & ~size_t(31);
+            int E = (int)((227 * 1024 - (size_t)d.tab2_bytes) / G->score_env_bytes);
+            const int cap = T == 32 ? 1024 / T : std::min(15, 1024 / T);
+            E = std::min(E, cap);
+            if (const char* ev = getenv("OPFG_SCORE_ENVS_PER_CTA")) E = std::min(atoi(ev), cap);
+            if (!getenv("OPFG_SCORE_ENVS_PER_CTA")) E = 1;   // measured: no faster than one CTA per environment
+            if (E < 2 || (d.n_state & 1) || (size_t)d.tab2_bytes * 3 > 227 * 1024) E = 1;
+            G->score_envs_per_cta = E;
+        }
         G->has_scoring = true;
         return 0;
     } catch (const std::exception& ex) {
@@ -725,16 +834,32 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     (void)stream;
     Ctx<1> cx;
     std::vector<double> sm(score_smem_doubles(G->d.nb, G->d.nbr, 32));
-    for (int64_t env = 0; env < B->n_env; ++env) env_score(G->d, cx, sm.data(), *B, env, nullptr);
+    for (int64_t env = 0; env < B->n_env; ++env)
+        env_score(G->d, cx, sm.data(), *B, env, nullptr, B->state + env * (int64_t)G->d.n_state);
 #else
-    const size_t smem = G->smem_score;
-    OPFG_DISPATCH_T(G->d.threads, {
+    const size_t smem = score_smem_doubles(G->d.nb, G->d.nbr, G->score_threads) * sizeof(double);
+    OPFG_DISPATCH_T(G->score_threads, {
         static size_t attr_smem = 48 * 1024;
         if (smem > attr_smem) {
             cudaFuncSetAttribute(k_score<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_smem = smem;
         }
-        k_score<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
+        if (G->score_envs_per_cta > 1) {
+            const int E = G->score_envs_per_cta;
+            const size_t smem_multi = G->d.tab2_bytes + (size_t)E * G->score_env_bytes;
+            static size_t attr_multi = 48 * 1024;
+            if (smem_multi > attr_multi) {
+                cudaFuncSetAttribute(k_score_multi<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                attr_multi = smem_multi;
+            }
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+            const int64_t groups = (B->n_env + E - 1) / E;
+            k_score_multi<TT><<<(unsigned)std::min<int64_t>(groups, n_sm), TT * E, smem_multi, (cudaStream_t)stream>>>(
+                G->d, *B, E, (int)(G->score_env_bytes / 8), G->score_consts, G->score_br_y, G->score_br_f, G->score_br_t);
+        } else {
+            k_score<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
+        }
     });
     ++g_launches;
     cudaError_t e = cudaGetLastError();

@@ -91,6 +91,9 @@ struct GridDev {
     const int* obs_ref;
     const char* tab_base;              // contiguous arena holding the power-flow tables
     int tab_bytes;
+    const char* tab2_base;             // contiguous arena holding the scoring tables
+    int tab2_bytes;
+    int n_inputs;                      // S[:, n_inputs:] are the result cells written by kernel 5
     unsigned long long* phase_cycles;  // developer instrumentation (OPFG_PHASE_TIMING builds), else unused
 };
 
@@ -255,11 +258,11 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
 // Shared-memory working set of one environment.  2x2 blocks are 32-byte aligned
 // (two 128-bit shared loads per block); V is kept as interleaved (re, im) pairs.
 struct PfSmem {
-    double *lu, *rhs, *vri, *vm, *va, *ivm, *red;
+    double *lu, *rhs, *vri, *ivm, *red;
 };
 
 OPFG_HHD size_t pf_smem_doubles(int n_blocks, int n, int nb, int threads) {
-    return (size_t)4 * n_blocks + 2 * (size_t)n + 5 * (size_t)nb + 2 * (size_t)(threads / 32 + 1) + 2;
+    return (size_t)4 * n_blocks + 2 * (size_t)n + 3 * (size_t)nb + 2 * (size_t)(threads / 32 + 1) + 2;
 }
 
 OPFG_HD PfSmem pf_carve(double* base, int n_blocks, int n, int nb) {
@@ -267,9 +270,7 @@ OPFG_HD PfSmem pf_carve(double* base, int n_blocks, int n, int nb) {
     s.lu = base;
     s.rhs = s.lu + 4 * (size_t)n_blocks;
     s.vri = s.rhs + 2 * (size_t)n;
-    s.vm = s.vri + 2 * (size_t)nb;
-    s.va = s.vm + nb;
-    s.ivm = s.va + nb;
+    s.ivm = s.vri + 2 * (size_t)nb;
     s.red = s.ivm + nb + (nb & 1);
     return s;
 }
@@ -463,12 +464,15 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         }
     }
     OPFG_TICK(0);   // DC start
+    // |V| and angle are touched only by their owner lane, once per iteration: they live in the
+    // output buffers (L2) instead of shared memory, which buys one more resident environment per SM
     for (int i = cx.tid; i < nb; i += T) {
         const double vm = g.vm0_int[i];
         const double va = (g.init_dc && i < n) ? s.rhs[i] : g.va0_int[i];
         double sn, cs;
         sincos(va, &sn, &cs);
-        s.vm[i] = vm; s.va[i] = va; s.ivm[i] = 1.0 / vm;
+        const int bus = g.bus_of_int[i];
+        vm_out[bus] = vm; va_out[bus] = va; s.ivm[i] = 1.0 / vm;
         st2(s.vri + 2 * i, vm * cs, vm * sn);
     }
     cx.sync();
@@ -535,23 +539,19 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         }
         for (int k = cx.tid; k < n; k += T) {
             const D2 dx = ld2(s.rhs + 2 * k);
-            double va = s.va[k] + dx.x;
-            double vm = s.vm[k] + ((g.type_int[k] == OPFG_PQ) ? dx.y : 0.0);
+            const int bus = g.bus_of_int[k];
+            double va = va_out[bus] + dx.x;
+            double vm = vm_out[bus] + ((g.type_int[k] == OPFG_PQ) ? dx.y : 0.0);
             // V = Vm*exp(j*Va); Vm = |V|; Va = angle(V)  (newtonpf.py)
             if (vm < 0) { vm = -vm; va += M_PI; }
             if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
             double sn, cs;
             sincos(va, &sn, &cs);
-            s.va[k] = va; s.vm[k] = vm; s.ivm[k] = 1.0 / vm;
+            va_out[bus] = va; vm_out[bus] = vm; s.ivm[k] = 1.0 / vm;
             st2(s.vri + 2 * k, vm * cs, vm * sn);
         }
         cx.sync();
         OPFG_TICK(6);
-    }
-    for (int i = cx.tid; i < nb; i += T) {
-        const int bus = g.bus_of_int[i];
-        vm_out[bus] = s.vm[i];
-        va_out[bus] = s.va[i];
     }
     if (cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
 }
@@ -587,13 +587,13 @@ OPFG_HD double pwl_cost(const GridDev& g, const double* S, int row, double v) {
 
 template <class C>
 OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBatch& B, int64_t env,
-                       const double* yval_env) {
+                       const double* yval_env, double* S) {
     const int T = cx.nthreads();
     const int nb = g.nb, nbr = g.nbr, nc = g.n_con;
     ScoreSmem s;
     s.vr = smem; s.vi = s.vr + nb; s.vm = s.vi + nb;
     s.sf = s.vm + nb; s.st = s.sf + 2 * (size_t)nbr; s.red = s.st + 2 * (size_t)nbr;
-    double* S = B.state + env * (int64_t)g.n_state;
+    // S: this environment's state row -- in global memory, or a shared-memory copy staged by the caller
     const double* vm = B.vm + env * (int64_t)nb;
     const double* va = B.va + env * (int64_t)nb;
     const double* sbus = B.sbus + env * (int64_t)nb * 2;

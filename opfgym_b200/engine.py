@@ -76,8 +76,27 @@ class Engine:
             self.batch_final.obs_f32 = self._ptr(self.obs_final)
         else:
             self.batch_final.obs_f64 = self._ptr(self.obs_final)
+        # reset applies its own (centre / random) action: separate buffer so that a reset prefetched on a
+        # side stream never touches the agent's actions
+        self.actions_reset = self._zeros((B, max(program.n_act, 1)), "float64")
         self.batch_setpoints = capi.Batch.from_buffer_copy(self.batch)
         self.batch_setpoints.sbus = None
+        self.batch_setpoints.actions = self._ptr(self.actions_reset)
+        self._states = [self.state]
+        self.cur = 0
+
+    def enable_double_buffer(self):
+        """Second state matrix: the next episode can be sampled while the current one is solved."""
+        if len(self._states) == 1:
+            self._states.append(self.state.clone())
+
+    def select(self, index: int):
+        """Make state buffer ``index`` the one every launch (and ``column()``) refers to."""
+        self.cur = index
+        self.state = self._states[index]
+        ptr = self._ptr(self.state)
+        for b in (self.batch, self.batch_final, self.batch_setpoints):
+            b.state = ptr
 
     # ------------------------------------------------------- device plumbing (torch)
     def _setup_device(self, device):

@@ -79,9 +79,10 @@ class VoltageControl(BatchedOpfEnv):
     def _bounds_program(r):
         # active power is not controllable: pin its bounds to the sampled value; offer the
         # whole remaining apparent-power capability as reactive range; start from Q = 0
-        p_max = r.col("p_mw") * r.col("scaling") + 1e-9
+        p_scaled = r.col("p_mw") * r.col("scaling")
+        p_max = p_scaled + 1e-9
         r.store("max_p_mw", p_max)
-        r.store("min_p_mw", r.col("p_mw") * r.col("scaling") - 1e-9)
+        r.store("min_p_mw", p_scaled - 1e-9)
         q_max = (r.col("max_s_mva") ** 2 - p_max ** 2) ** 0.5
         r.store("min_q_mvar", -q_max)
         r.store("max_q_mvar", q_max)

@@ -72,7 +72,8 @@ class BatchedOpfEnv:
                  device=None, rank: int = 0, world_size: int = 1, obs_dtype: str = "float32",
                  dynamic_columns=(), pwl_price_columns=None, tolerance_mva: float = 1e-8,
                  max_iteration: int = 10, engine_cls=Engine, engine_kwargs: dict | None = None,
-                 copy_outputs: bool = True, validate_actions: bool = False, **kwargs):
+                 copy_outputs: bool = True, validate_actions: bool = False,
+                 prefetch_reset: bool = True, **kwargs):
         unknown = set(kwargs) - _SPLIT_KWARGS
         if unknown:
             raise TypeError(f"unknown keyword arguments: {sorted(unknown)}")
@@ -173,6 +174,16 @@ class BatchedOpfEnv:
         self._static_cache = {}
         self._row_programs = {}
         self._flags = None
+        # Every step ends every episode, and the next episode's state depends only on the RNG: sample
+        # it (sampler, hook programs, centre action, reset observation) on a side stream into a second
+        # state buffer while the main stream solves the current episode.
+        self._prefetch = bool(prefetch_reset) and getattr(self.device, "type", "cpu") == "cuda" \
+            and not self.pf_for_obs
+        if self._prefetch:
+            self.engine.enable_double_buffer()
+            self._side = self.xp.cuda.Stream(device=self.device)
+            self._main_done = self.xp.cuda.Event()
+            self._side_done = self.xp.cuda.Event()
         self.test = False
         self.power_flow_available = False
 
@@ -199,6 +210,8 @@ class BatchedOpfEnv:
         self.engine.close()
         self.engine = self._engine_cls(self.program, self.num_envs, **self._engine_args)
         self.engine.state.copy_(state)
+        if getattr(self, "_prefetch", False):
+            self.engine.enable_double_buffer()
         self._sample_cache.clear()
         self._row_programs.clear()
 
@@ -355,11 +368,13 @@ class BatchedOpfEnv:
         self._stream_in_episode = 0
         self.current_simbench_step = None
         self._sampling(step, self.test, True)
-        act = self.engine.actions
         if self.initial_action == "random":
-            self.engine.philox_uniform(act, self.seed, self.first_env, self._next_stream())
+            self.engine.philox_uniform(self.engine.actions_reset, self.seed, self.first_env,
+                                       self._next_stream())
         else:
-            act.fill_(0.5)
+            self.engine.actions_reset.fill_(0.5)
+        if self.pf_for_obs:
+            self.engine.actions.copy_(self.engine.actions_reset)
         self.engine.assemble(scatter_sbus=self.pf_for_obs)
         if self.pf_for_obs:
             # the reference re-samples envs whose reset power flow fails (opf_env.py:209-214);
@@ -391,10 +406,19 @@ class BatchedOpfEnv:
         act = xp.as_tensor(actions, device=self.device)
         if self.validate_actions and xp.isnan(act).any():   # host sync; off by default
             raise AssertionError("NaN in actions")     # opf_env.py:382
+        e = self.engine
+        if self._prefetch:
+            main = xp.cuda.current_stream(self.device)
+            self._main_done.record(main)
+            e.select(1 - e.cur)                       # launches below target the NEXT episode's buffer
+            with xp.cuda.stream(self._side):
+                self._side.wait_event(self._main_done)
+                self._begin_episode()
+                self._side_done.record(self._side)
+            e.select(1 - e.cur)
         self.engine.actions.copy_(act.reshape(self.engine.actions.shape))
         self.engine.step(final_obs=True)
         self.power_flow_available = True
-        e = self.engine
         keep = (lambda t: t.clone()) if self.copy_outputs else (lambda t: t)
         reward = keep(e.reward)
         if self.clipped_action_penalty:
@@ -408,7 +432,11 @@ class BatchedOpfEnv:
             self._flags = (xp.ones(self.num_envs, dtype=xp.bool, device=self.device),
                            xp.zeros(self.num_envs, dtype=xp.bool, device=self.device))
         terminated, truncated = (keep(self._flags[0]), keep(self._flags[1]))
-        self._begin_episode()
+        if self._prefetch:
+            xp.cuda.current_stream(self.device).wait_event(self._side_done)
+            e.select(1 - e.cur)                       # the prefetched episode becomes the current one
+        else:
+            self._begin_episode()
         return self._obs_out(), reward, terminated, truncated, info
 
     def _mean_correction(self, act):
