@@ -102,6 +102,7 @@ class Compiler:
         self.ppc = self.builder.build(net)
         self.layout = StateLayout()
         self.consts = ConstTable()
+        self.referenced: set[tuple[str, str]] = set()   # columns some compiled table actually reads
 
     # ---------------------------------------------------------------- references
     def declare_dynamic(self, table: str, column: str):
@@ -112,6 +113,7 @@ class Compiler:
         self.layout.add(table, column, len(self.net[table]))
 
     def value_ref(self, table: str, column: str, pos: int) -> int:
+        self.referenced.add((table, column))
         if self.layout.has(table, column):
             return self.layout.columns[(table, column)][0] + int(pos)
         if _is_res(table):
@@ -128,7 +130,14 @@ class Compiler:
     def compile(self, act_keys, obs_keys, state_keys, constraints: list[Constraint],
                 reward_function: RewardFunction, extra_dynamic=(),
                 autoscale_actions: bool = True, pwl_price_columns=None,
-                extra_results=()) -> EnvProgram:
+                extra_results=(), prune_unused: bool = False) -> EnvProgram:
+        if prune_unused and extra_dynamic:
+            # dry run: find out which hook-written columns any kernel table actually reads
+            # (e.g. max_p_mw / min_p_mw exist in the reference only for the pandapower OPF)
+            probe = Compiler(self.net, self.builder)
+            probe.compile(act_keys, obs_keys, state_keys, constraints, reward_function, extra_dynamic,
+                          autoscale_actions, pwl_price_columns, extra_results, prune_unused=False)
+            extra_dynamic = [tc for tc in extra_dynamic if tuple(tc) in probe.referenced]
         net, lay, ppc = self.net, self.layout, self.ppc
         for table, column, _ in list(state_keys) + list(act_keys):
             if not _is_res(table):

@@ -242,8 +242,10 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
     __threadfence_block();
 #endif
     const double inv_base = 1.0 / g.base_mva;
+#pragma unroll 2
     for (int bus = cx.tid; bus < g.nb; bus += T) {
         double p = 0, q = 0;
+#pragma unroll 4
         for (int e = g.inj_ptr[bus]; e < g.inj_ptr[bus + 1]; ++e) {
             const double c = ref_val(g, S, g.inj_coef[e]);
             p += c * ref_val(g, S, g.inj_p[e]);

@@ -73,7 +73,7 @@ class BatchedOpfEnv:
                  dynamic_columns=(), pwl_price_columns=None, tolerance_mva: float = 1e-8,
                  max_iteration: int = 10, engine_cls=Engine, engine_kwargs: dict | None = None,
                  copy_outputs: bool = True, validate_actions: bool = False,
-                 prefetch_reset: bool = True, **kwargs):
+                 prefetch_reset: bool = True, keep_all_columns: bool = False, **kwargs):
         unknown = set(kwargs) - _SPLIT_KWARGS
         if unknown:
             raise TypeError(f"unknown keyword arguments: {sorted(unknown)}")
@@ -158,12 +158,16 @@ class BatchedOpfEnv:
         self._compile_args = dict(act_keys=self.act_keys, obs_keys=self.obs_keys,
                                   state_keys=self.state_keys, constraints=self.constraints,
                                   extra_dynamic=dynamic, autoscale_actions=autoscale_actions,
-                                  pwl_price_columns=pwl_price_columns)
+                                  pwl_price_columns=pwl_price_columns,
+                                  # hook-written columns that no kernel reads (they only feed the
+                                  # reference's pandapower-OPF baseline) are not materialised
+                                  prune_unused=not keep_all_columns)
         self._engine_args = dict(device=device, tolerance_mva=tolerance_mva,
                                  max_iteration=max_iteration, obs_dtype=obs_dtype,
                                  **(engine_kwargs or {}))
         self._engine_cls = engine_cls
         self.program = compiler.compile(reward_function=placeholder, **self._compile_args)
+        self.pruned_columns = {tuple(tc) for tc in dynamic if not self.program.layout.has(*tc)}
         self.engine = engine_cls(self.program, self.num_envs, **self._engine_args)
         self.xp = self.engine.torch
         self.device = self.engine.device
@@ -243,7 +247,8 @@ class BatchedOpfEnv:
                 rp = RowProgram(self, table)
                 build(rp)
                 ops, statics = rp.compile()
-                self._row_programs[key] = CompiledRowProgram(self.engine, rp.n_rows, ops, statics)
+                self._row_programs[key] = CompiledRowProgram(self.engine, rp.n_rows, ops, statics) \
+                    if ops else None       # every store was to a pruned (unread) column
         prog = self._row_programs[key]
         if prog is not None:
             prog.run()

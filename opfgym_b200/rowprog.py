@@ -84,6 +84,8 @@ class RowProgram:
     def store(self, column: str, value):
         lay = self.env.program.layout
         if not lay.has(self.table, column):
+            if (self.table, column) in self.env.pruned_columns:
+                return                     # nothing reads this column: not materialised
             raise KeyError(f"{self.table}.{column} is not a per-environment column")
         self._cols.pop(column, None)   # later reads see the stored value
         self.stores.append((lay.columns[(self.table, column)][0], Expr.wrap(value)))
