@@ -242,7 +242,7 @@ template <int T>
 __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
     const int64_t env = blockIdx.x;
-    Ctx<T> cx{(int)threadIdx.x, sm + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1), 0};
+    Ctx<T> cx{(int)threadIdx.x, sm + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 0};
     env_pf_solve(g, cx, sm, B.sbus + env * (int64_t)g.nb * 2, nullptr, B.vm + env * (int64_t)g.nb,
                  B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
 }
@@ -265,10 +265,11 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     OPFG_REBASE(dp_ptr); OPFG_REBASE(dp_pack); OPFG_REBASE(off_ptr); OPFG_REBASE(off_hdr); OPFG_REBASE(op_pack);
     OPFG_REBASE(up_ptr); OPFG_REBASE(up_pack); OPFG_REBASE(y_ptr); OPFG_REBASE(y_meta); OPFG_REBASE(y_val);
     OPFG_REBASE(dc_val); OPFG_REBASE(dc_rhs0);
+    OPFG_REBASE(qlim_bus); OPFG_REBASE(qlim_min); OPFG_REBASE(qlim_max);
 #undef OPFG_REBASE
     const int e_local = threadIdx.x / T;
     double* mine = sm + g.tab_bytes / 8 + (size_t)e_local * env_doubles;
-    Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1), 1 + e_local};
+    Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 1 + e_local};
     for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
         env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2, nullptr, B.vm + env * (int64_t)g.nb,
                      B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
@@ -517,11 +518,30 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         }
         for (int k = 0; k < s.n; ++k) dc_rhs0[k] -= ysh[2 * s.bus_of_int[k]];
         d.dc_val = G->tab(dc_val); d.dc_rhs0 = G->tab(dc_rhs0);
+        {   // enforce_q_lims tables: one entry per PV bus with an active limit
+            std::vector<int> qb;
+            std::vector<double> qmn, qmx;
+            if (desc->enforce_q_lims && desc->gen_cols > OPFG_QMIN) {
+                std::vector<double> mn(nb, 0.0), mx(nb, 0.0);
+                std::vector<int> cnt(nb, 0);
+                for (int gI = 0; gI < ng; ++gI) {
+                    const double* row = desc->gen + (size_t)gI * desc->gen_cols;
+                    const int bus = (int)row[OPFG_GEN_BUS];
+                    if (row[OPFG_GEN_STATUS] <= 0 || type[bus] != 2) continue;
+                    if (row[OPFG_QMAX] == 0.0 && row[OPFG_QMIN] == 0.0) continue;   // pandapower's both-zero rule
+                    mn[bus] += row[OPFG_QMIN] / base; mx[bus] += row[OPFG_QMAX] / base; cnt[bus]++;
+                }
+                for (int b = 0; b < nb; ++b)
+                    if (cnt[b]) { qb.push_back(s.int_of_bus[b]); qmn.push_back(mn[b]); qmx.push_back(mx[b]); }
+            }
+            d.n_qlim = (int)qb.size();
+            d.qlim_bus = G->tab(qb); d.qlim_min = G->tab(qmn); d.qlim_max = G->tab(qmx);
+        }
         d.tab_base = G->tab_base;
         d.tab_bytes = (int)((G->tab_used + 15) & ~size_t(15));
 
         if (const char* cv = getenv("OPFG_CARVEOUT")) G->carveout_pct = atoi(cv);
-        G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T) * sizeof(double) + 31) & ~size_t(31);
+        G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
             const size_t budget = 227 * 1024;
             int E = (int)((budget - d.tab_bytes) / G->smem_pf);
@@ -782,7 +802,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
 #ifdef OPFG_HOSTSIM
     (void)stream;
     Ctx<1> cx;
-    std::vector<double> sm(pf_smem_doubles(G->d.n_blocks, G->d.n, G->d.nb, 32));
+    std::vector<double> sm(pf_smem_doubles(G->d.n_blocks, G->d.n, G->d.nb, 32, G->d.n_qlim));
     for (int64_t env = 0; env < B->n_env; ++env)
         env_pf_solve(G->d, cx, sm.data(), B->sbus + env * (int64_t)G->d.nb * 2, nullptr, B->vm + env * (int64_t)G->d.nb,
                      B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);

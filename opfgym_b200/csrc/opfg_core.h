@@ -59,6 +59,11 @@ struct GridDev {
     const double* bus_ysh;             // [nb*2] (GS + jBS)/base by ppc bus
     const int* br_f;                   // [nbr] ppc from bus
     const int* br_t;
+    // enforce_q_lims: PV buses whose generators have active reactive limits (both-zero limits are
+    // skipped like pandapower does); limits are per bus, in p.u. of base_mva
+    int n_qlim;
+    const int* qlim_bus;               // [n_qlim] internal bus index
+    const double *qlim_min, *qlim_max; // [n_qlim]
     // DC start
     const double* dc_val;              // [n_blocks] scalar factor on the same schedule
     const double* dc_rhs0;             // [n]
@@ -261,10 +266,14 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
 // (two 128-bit shared loads per block); V is kept as interleaved (re, im) pairs.
 struct PfSmem {
     double *lu, *rhs, *vri, *ivm, *red;
+    double* qadd;                 // [n] reactive power fixed at a limit (enforce_q_lims), else null
+    unsigned char* type;          // [nb] per-environment bus types (enforce_q_lims), else null
+    const unsigned char* bus_type;   // what the kernels read: `type` or the shared table
 };
 
-OPFG_HHD size_t pf_smem_doubles(int n_blocks, int n, int nb, int threads) {
-    return (size_t)4 * n_blocks + 2 * (size_t)n + 3 * (size_t)nb + 2 * (size_t)(threads / 32 + 1) + 2;
+OPFG_HHD size_t pf_smem_doubles(int n_blocks, int n, int nb, int threads, int n_qlim = 0) {
+    return (size_t)4 * n_blocks + 2 * (size_t)n + 3 * (size_t)nb + 2 * (size_t)(threads / 32 + 1) + 2 +
+           (n_qlim > 0 ? (size_t)n + (size_t)(nb + 7) / 8 + 1 : 0);
 }
 
 OPFG_HD PfSmem pf_carve(double* base, int n_blocks, int n, int nb) {
@@ -274,6 +283,7 @@ OPFG_HD PfSmem pf_carve(double* base, int n_blocks, int n, int nb) {
     s.vri = s.rhs + 2 * (size_t)n;
     s.ivm = s.vri + 2 * (size_t)nb;
     s.red = s.ivm + nb + (nb & 1);
+    s.qadd = nullptr; s.type = nullptr; s.bus_type = nullptr;
     return s;
 }
 
@@ -295,9 +305,10 @@ OPFG_HD D2 ldg2(const double* p) { return D2{p[0], p[1]}; }
 // Formulas: pypower dSbus_dV.py in polar form [ext-mem], SURVEY.md App. B.4.
 OPFG_HD double row_mismatch(const GridDev& g, const PfSmem& s, const double* yv, const double* sbus,
                             int i, bool jac) {
-    const D2 sp = ldg2(sbus + 2 * g.bus_of_int[i]);          // P, Q set-point (global, issued early)
+    D2 sp = ldg2(sbus + 2 * g.bus_of_int[i]);                // P, Q set-point (global, issued early)
     const D2 vi = ld2(s.vri + 2 * i);
-    const bool pq = g.type_int[i] == OPFG_PQ;
+    const bool pq = s.bus_type[i] == OPFG_PQ;
+    if (s.qadd) sp.y += s.qadd[i];
     const int e0 = g.y_ptr[i], e1 = g.y_ptr[i + 1];
     double ir = 0, ii = 0, dr = 0, di = 0;
     for (int e = e0; e < e1; ++e) {
@@ -333,7 +344,7 @@ OPFG_HD void jacobian_entry(const GridDev& g, const PfSmem& s, const double* yv,
     const double tr = fma(y.x, vj.x, -(y.y * vj.y)), ti = fma(y.x, vj.y, y.y * vj.x);
     const double ar = fma(vi.x, tr, vi.y * ti), ai = fma(vi.y, tr, -(vi.x * ti));   // V_i conj(Y_ij V_j)
     const double inv_vmj = s.ivm[j];
-    const bool pq = g.type_int[i] == OPFG_PQ;
+    const bool pq = s.bus_type[i] == OPFG_PQ;
     st2(s.lu + 4 * blk, ai, ar * inv_vmj);                    // dP/dtheta_j, dP/dVm_j
     st2(s.lu + 4 * blk + 2, pq ? -ar : 0.0, pq ? ai * inv_vmj : 0.0);
 }
@@ -438,6 +449,15 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
     PfSmem s = pf_carve(smem, g.n_blocks, n, nb);
     const double* yv = yval_env ? yval_env : g.y_val;
     OPFG_TICK_INIT;
+    s.bus_type = g.type_int;
+    if (g.n_qlim > 0) {   // enforce_q_lims: this environment may turn PV buses into PQ buses
+        s.qadd = s.red + 2 * (T / 32 + 1) + 2;
+        s.type = reinterpret_cast<unsigned char*>(s.qadd + n);
+        for (int i = cx.tid; i < nb; i += T) s.type[i] = g.type_int[i];
+        for (int k = cx.tid; k < n; k += T) s.qadd[k] = 0.0;
+        s.bus_type = s.type;
+        cx.sync();
+    }
 
     if (g.init_dc) {   // pandapower init='dc': B' theta = P on the shared, pre-factorised B'
         for (int k = cx.tid; k < n; k += T) s.rhs[k] = sbus[2 * g.bus_of_int[k]] + g.dc_rhs0[k];
@@ -483,6 +503,7 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
     int it = 0;
     int converged = 0;
     double prev = 1.0;
+  restart_after_q_limits:
     while (true) {
         // quadratic convergence: after a norm below 1e-4 the next one is almost surely below
         // tol, so look at the mismatch alone first and build the Jacobian only if needed
@@ -543,7 +564,7 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
             const D2 dx = ld2(s.rhs + 2 * k);
             const int bus = g.bus_of_int[k];
             double va = va_out[bus] + dx.x;
-            double vm = vm_out[bus] + ((g.type_int[k] == OPFG_PQ) ? dx.y : 0.0);
+            double vm = vm_out[bus] + ((s.bus_type[k] == OPFG_PQ) ? dx.y : 0.0);
             // V = Vm*exp(j*Va); Vm = |V|; Va = angle(V)  (newtonpf.py)
             if (vm < 0) { vm = -vm; va += M_PI; }
             if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
@@ -554,6 +575,30 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         }
         cx.sync();
         OPFG_TICK(6);
+    }
+    if (converged && g.n_qlim > 0) {
+        // pandapower `_run_ac_pf_with_qlims_enforced` [ext-mem]: a voltage-controlled bus whose reactive
+        // output left [QMIN, QMAX] is fixed at the limit and becomes a PQ bus; solve again from the
+        // current voltages until no limit is violated.
+        double changed = 0;
+        for (int q = cx.tid; q < g.n_qlim; q += T) {
+            const int i = g.qlim_bus[q];
+            if (s.type[i] != OPFG_PV) continue;
+            const D2 vi = ld2(s.vri + 2 * i);
+            double ir = 0, ii = 0;
+            for (int e = g.y_ptr[i]; e < g.y_ptr[i + 1]; ++e) {
+                const D2 y = ld2(yv + 2 * e);
+                const D2 vj = ld2(s.vri + 2 * (g.y_meta[e].x & 0xffffu));
+                ir += fma(y.x, vj.x, -(y.y * vj.y));
+                ii += fma(y.x, vj.y, y.y * vj.x);
+            }
+            const double qg = fma(vi.y, ir, -(vi.x * ii)) - sbus[2 * g.bus_of_int[i] + 1];   // generator Q, p.u.
+            if (qg > g.qlim_max[q]) { s.qadd[i] = g.qlim_max[q]; s.type[i] = OPFG_PQ; changed = 1; }
+            else if (qg < g.qlim_min[q]) { s.qadd[i] = g.qlim_min[q]; s.type[i] = OPFG_PQ; changed = 1; }
+        }
+        changed = cx.block_max(changed);
+        cx.sync();
+        if (changed > 0) { converged = 0; it = 0; prev = 1.0; goto restart_after_q_limits; }
     }
     if (cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
 }

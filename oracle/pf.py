@@ -183,7 +183,7 @@ def run_pf(ppc: Ppc, tolerance_mva=1e-8, max_iteration=10, enforce_q_lims=True,
         ref, pv, pq = bus_types(bus, gen)
         sbus = make_sbus(base, bus, gen)
         v, ok, it = newtonpf(ybus, sbus, v0, ref, pv, pq, tol, max_iteration)
-        total_it += it
+        total_it = it          # pandapower keeps the iteration count of the last inner run
         # pfsoln: generator reactive power and slack active power
         sinj = v * np.conj(ybus @ v) * base + (bus[:, PD] + 1j * bus[:, QD])
         on = gen[:, GEN_STATUS] > 0
