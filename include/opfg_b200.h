@@ -148,6 +148,21 @@ typedef struct {
     const opfg_ref* obs_ref;         /* host [n_obs]                                   */
 } OpfgScoringDesc;
 
+/* per-environment branch parameters (tap_pos / in_service actions, N-1 contingencies): the listed
+ * branches get their admittances -- and Ybus its values -- recomputed per environment by
+ * opfg_assemble (kernel 1), in the fixed sparsity pattern of the nominal topology.
+ * Replaces pandapower's per-call `_calc_branch_values_from_trafo_df` / `_calc_line_parameter` +
+ * makeYbus for those branches (reached from opfgym/opf_env.py:476-483, 703). */
+typedef struct {
+    int32_t n_dyn;
+    const int32_t* branch;          /* host [n_dyn] ppc branch row                                        */
+    const opfg_ref* tap_pos;        /* host [n_dyn] tap position cell (ref to a NaN constant: tap fixed)   */
+    const double* tap_neutral;      /* host [n_dyn]                                                        */
+    const double* tap_step_percent; /* host [n_dyn]                                                        */
+    const double* ratio_neutral;    /* host [n_dyn] off-nominal ratio at the neutral tap (HV-side changer) */
+    const opfg_ref* in_service;     /* host [n_dyn] 0/1 cell (ref to constant 1: always in service)        */
+} OpfgDynBranchDesc;
+
 /* device buffers of one batch (any pointer may be NULL if the stage that needs it is not run) */
 typedef struct {
     int64_t n_env;
@@ -169,6 +184,8 @@ typedef struct {
     float*  obs_f32;         /* [B, n_obs] out (either or both)                               */
     double* obs_f64;         /* [B, n_obs] out                                                */
     double* stats;           /* [OPFG_N_STATS] accumulated with atomics; caller zeroes        */
+    double* yval;            /* [B, nnz_y, 2] per-env Ybus values, only with dynamic branches  */
+    double* bry;             /* [B, n_dyn, 8] per-env admittances of the dynamic branches      */
 } OpfgBatch;
 
 enum { OPFG_STAT_N = 0, OPFG_STAT_CONVERGED = 1, OPFG_STAT_VALID = 2, OPFG_STAT_SUM_REWARD = 3,
@@ -183,6 +200,7 @@ int  opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out);
 void opfg_grid_destroy(OpfgGrid* grid);
 int  opfg_set_assembly(OpfgGrid* grid, const OpfgAssemblyDesc* desc);
 int  opfg_set_scoring(OpfgGrid* grid, const OpfgScoringDesc* desc);
+int  opfg_set_dynamic_branches(OpfgGrid* grid, const OpfgDynBranchDesc* desc);   /* after opfg_set_assembly */
 int  opfg_grid_info(const OpfgGrid* grid, OpfgGridInfo* out);
 /* host copies of the symbolic analysis, for inspection/tests: perm[n_nonref] = ppc bus of pivot k,
  * level_ptr[n_levels+1]; either pointer may be NULL */

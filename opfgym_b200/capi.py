@@ -69,6 +69,11 @@ class ScoringDesc(C.Structure):
                 ("n_obs", C.c_int32), ("obs_ref", _ip)]
 
 
+class DynBranchDesc(C.Structure):
+    _fields_ = [("n_dyn", C.c_int32), ("branch", _ip), ("tap_pos", _ip), ("tap_neutral", _dp),
+                ("tap_step_percent", _dp), ("ratio_neutral", _dp), ("in_service", _ip)]
+
+
 class RowOp(C.Structure):
     _fields_ = [("op", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32),
                 ("imm", C.c_double)]
@@ -78,7 +83,7 @@ class Batch(C.Structure):
     _fields_ = [("n_env", C.c_int64)] + [(n, C.c_void_p) for n in
                 ("actions", "state", "sbus", "vm", "va", "converged", "iterations",
                  "reward", "objective", "penalty", "cost", "valids", "violations",
-                 "penalties", "obs_f32", "obs_f64", "stats")]
+                 "penalties", "obs_f32", "obs_f64", "stats", "yval", "bry")]
 
 
 # every symbol include/opfg_b200.h declares: name -> (restype, argtypes)
@@ -89,6 +94,7 @@ PROTOTYPES = {
     "opfg_grid_destroy": (None, [C.c_void_p]),
     "opfg_set_assembly": (C.c_int, [C.c_void_p, C.POINTER(AssemblyDesc)]),
     "opfg_set_scoring": (C.c_int, [C.c_void_p, C.POINTER(ScoringDesc)]),
+    "opfg_set_dynamic_branches": (C.c_int, [C.c_void_p, C.POINTER(DynBranchDesc)]),
     "opfg_grid_info": (C.c_int, [C.c_void_p, C.POINTER(GridInfo)]),
     "opfg_grid_symbolic": (C.c_int, [C.c_void_p, _ip, _ip]),
     "opfg_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64,

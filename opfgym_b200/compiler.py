@@ -81,6 +81,7 @@ class EnvProgram:
     act_high_refs: np.ndarray
     sample_plan: dict = field(default_factory=dict)
     index_pos: dict = field(default_factory=dict)
+    dyn_branches: dict | None = None     # OpfgDynBranchDesc arrays, if any branch cell is per-environment
 
 
 def _positions(net, table: str, idxs) -> np.ndarray:
@@ -346,6 +347,35 @@ class Compiler:
                 else:
                     obs_ref.append(self.value_ref(table, column, p))
 
+        # ---- per-environment branch parameters (tap_pos / in_service cells) ------------
+        dyn = None
+        dyn_rows = []
+        one, nan = self.consts.ref(1.0), self.consts.ref(np.nan)
+        if lay.has("line", "in_service"):
+            for pos, br in enumerate(ppc.line_branch):
+                if br >= 0:
+                    dyn_rows.append((int(br), nan, 0.0, 0.0, 1.0, self.value_ref("line", "in_service", pos)))
+        if lay.has("trafo", "tap_pos") or lay.has("trafo", "in_service"):
+            tr = net.trafo
+            for pos, br in enumerate(ppc.trafo_branch):
+                if br < 0:
+                    continue
+                k = int(np.nonzero(self.builder.trafo_pos == pos)[0][0])
+                tap = nan
+                if lay.has("trafo", "tap_pos"):
+                    if not self.builder.trafo_tap_on_hv[k]:
+                        raise NotImplementedError("per-environment tap_pos needs an HV-side tap changer")
+                    tap = self.value_ref("trafo", "tap_pos", pos)
+                svc = self.value_ref("trafo", "in_service", pos) if lay.has("trafo", "in_service") else one
+                dyn_rows.append((int(br), tap, float(tr.tap_neutral.iloc[pos]),
+                                 float(tr.tap_step_percent.iloc[pos]),
+                                 float(self.builder.trafo_ratio_neutral[k]), svc))
+        if dyn_rows:
+            cols = list(zip(*dyn_rows))
+            dyn = dict(branch=np.asarray(cols[0], _I32), tap_pos=np.asarray(cols[1], _I32),
+                       tap_neutral=np.asarray(cols[2], float), tap_step_percent=np.asarray(cols[3], float),
+                       ratio_neutral=np.asarray(cols[4], float), in_service=np.asarray(cols[5], _I32))
+
         rp = reward_function.device_params()
         scoring = dict(
             n_inputs=lay.n_inputs, n_pp_bus=len(net.bus), pp_bus_lookup=ppc.bus_lookup.astype(_I32),
@@ -369,7 +399,8 @@ class Compiler:
         return EnvProgram(ppc=ppc, layout=lay, consts=np.asarray(self.consts.values, float),
                           initial_state=init, assembly=assembly, scoring=scoring,
                           n_act=n_act, n_obs=len(obs_ref), constraints=list(constraints),
-                          act_low_refs=np.asarray(a_lo, _I32), act_high_refs=np.asarray(a_hi, _I32))
+                          act_low_refs=np.asarray(a_lo, _I32), act_high_refs=np.asarray(a_hi, _I32),
+                          dyn_branches=dyn)
 
     def _result_ref(self, res_table: str, column: str, pos: int) -> tuple[int, float]:
         """Reference (and multiplier) that yields ``net[res_table][column]`` of row ``pos``."""
@@ -445,4 +476,10 @@ def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_l
         penalty_bias=r["penalty_bias"], valid_reward=r["valid_reward"],
         invalid_penalty=r["invalid_penalty"], invalid_objective_share=r["invalid_objective_share"],
         n_obs=s["n_obs"], obs_ref=iptr(s["obs_ref"]))
-    return gd, ad, sd, keep
+    dd = None
+    if program.dyn_branches is not None:
+        d = program.dyn_branches
+        dd = capi.DynBranchDesc(n_dyn=len(d["branch"]), branch=iptr(d["branch"]), tap_pos=iptr(d["tap_pos"]),
+                                tap_neutral=dptr(d["tap_neutral"]), tap_step_percent=dptr(d["tap_step_percent"]),
+                                ratio_neutral=dptr(d["ratio_neutral"]), in_service=iptr(d["in_service"]))
+    return gd, ad, sd, dd, keep

@@ -236,14 +236,17 @@ __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
     Ctx<T> cx{(int)threadIdx.x, nullptr, 0};
     const int64_t env = blockIdx.x;
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
-                 B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr);
+                 B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
+                 B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr);
 }
 template <int T>
 __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
     const int64_t env = blockIdx.x;
     Ctx<T> cx{(int)threadIdx.x, sm + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 0};
-    env_pf_solve(g, cx, sm, B.sbus + env * (int64_t)g.nb * 2, nullptr, B.vm + env * (int64_t)g.nb,
+    env_pf_solve(g, cx, sm, B.sbus + env * (int64_t)g.nb * 2,
+                 (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr, B.vm + env * (int64_t)g.nb,
                  B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
 }
 // Persistent multi-environment CTA: E environments of T threads each share ONE shared-memory copy of
@@ -271,7 +274,8 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     double* mine = sm + g.tab_bytes / 8 + (size_t)e_local * env_doubles;
     Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 1 + e_local};
     for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
-        env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2, nullptr, B.vm + env * (int64_t)g.nb,
+        env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
+                     (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr, B.vm + env * (int64_t)g.nb,
                      B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
         cx.sync();
     }
@@ -281,7 +285,8 @@ __global__ void __launch_bounds__(T) k_score(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
     const int64_t env = blockIdx.x;
     Ctx<T> cx{(int)threadIdx.x, sm + score_smem_doubles(g.nb, g.nbr, T) - 2 * (T / 32 + 1), 0};
-    env_score(g, cx, sm, B, env, nullptr, B.state + env * (int64_t)g.n_state);
+    env_score(g, cx, sm, B, env, (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+              B.state + env * (int64_t)g.n_state);
 }
 
 __global__ void k_observe(GridDev g, OpfgBatch B) {
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(1024) k_score_multi(GridDev g, OpfgBatch B, in
             for (int i = tid; i < g.n_state / 2; i += T) dst[i] = src[i];
         }
         cx.sync();
-        env_score(g, cx, scratch, B, env, nullptr, row);
+        env_score(g, cx, scratch, B, env, (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr, row);
         cx.sync();
         if (B.converged[env])
             for (int i = g.n_inputs + tid; i < g.n_state; i += T) Sg[i] = row[i];
@@ -614,6 +619,34 @@ int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
     }
 }
 
+int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
+    if (!G || !dd) return fail("null argument");
+    if (!G->has_assembly) return fail("call opfg_set_assembly first (it defines the state layout)");
+    try {
+        GridDev& d = G->d;
+        std::vector<int> of(d.nbr, -1);
+        for (int i = 0; i < dd->n_dyn; ++i) {
+            const int br = dd->branch[i];
+            if (br < 0 || br >= d.nbr) throw std::runtime_error("dynamic branch out of range");
+            if (of[br] >= 0) throw std::runtime_error("branch listed twice");
+            of[br] = i;
+            for (const int* r : {dd->tap_pos + i, dd->in_service + i})
+                if (*r >= d.n_state || -*r - 1 >= d.n_const) throw std::runtime_error("reference out of range");
+        }
+        d.n_dyn = dd->n_dyn;
+        d.dyn_branch = G->up(dd->branch, dd->n_dyn);
+        d.dyn_of_branch = G->up(of);
+        d.dyn_tap_ref = G->up(dd->tap_pos, dd->n_dyn);
+        d.dyn_svc_ref = G->up(dd->in_service, dd->n_dyn);
+        d.dyn_neutral = G->up(dd->tap_neutral, dd->n_dyn);
+        d.dyn_step = G->up(dd->tap_step_percent, dd->n_dyn);
+        d.dyn_ratio0 = G->up(dd->ratio_neutral, dd->n_dyn);
+        return 0;
+    } catch (const std::exception& ex) {
+        return fail("opfg_set_dynamic_branches: %s", ex.what());
+    }
+}
+
 int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
     if (!G || !sc) return fail("null argument");
     if (!G->has_assembly) return fail("call opfg_set_assembly first (it defines the state layout)");
@@ -779,13 +812,16 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (!G || !B) return fail("null argument");
     if (!G->has_assembly) return fail("opfg_set_assembly was not called");
     if (!B->state || (!B->sbus && !B->actions)) return fail("opfg_assemble needs state and at least one of actions / sbus");
+    if (G->d.n_dyn > 0 && B->sbus && (!B->yval || !B->bry)) return fail("grid has dynamic branches: batch needs yval and bry");
     if (B->n_env <= 0) return 0;
 #ifdef OPFG_HOSTSIM
     (void)stream;
     Ctx<1> cx;
     for (int64_t env = 0; env < B->n_env; ++env)
         env_assemble(G->d, cx, B->actions ? B->actions + env * G->d.n_act : nullptr,
-                     B->state + env * (int64_t)G->d.n_state, B->sbus ? B->sbus + env * (int64_t)G->d.nb * 2 : nullptr);
+                     B->state + env * (int64_t)G->d.n_state, B->sbus ? B->sbus + env * (int64_t)G->d.nb * 2 : nullptr,
+                     B->yval ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr,
+                     B->bry ? B->bry + env * (int64_t)G->d.n_dyn * 8 : nullptr);
 #else
     k_assemble<32><<<(unsigned)B->n_env, 32, 0, (cudaStream_t)stream>>>(G->d, *B);
     ++g_launches;
@@ -804,7 +840,8 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     Ctx<1> cx;
     std::vector<double> sm(pf_smem_doubles(G->d.n_blocks, G->d.n, G->d.nb, 32, G->d.n_qlim));
     for (int64_t env = 0; env < B->n_env; ++env)
-        env_pf_solve(G->d, cx, sm.data(), B->sbus + env * (int64_t)G->d.nb * 2, nullptr, B->vm + env * (int64_t)G->d.nb,
+        env_pf_solve(G->d, cx, sm.data(), B->sbus + env * (int64_t)G->d.nb * 2,
+                     (G->d.n_dyn > 0 && B->yval) ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr, B->vm + env * (int64_t)G->d.nb,
                      B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);
 #else
     const size_t smem = G->smem_pf;
@@ -855,7 +892,9 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     Ctx<1> cx;
     std::vector<double> sm(score_smem_doubles(G->d.nb, G->d.nbr, 32));
     for (int64_t env = 0; env < B->n_env; ++env)
-        env_score(G->d, cx, sm.data(), *B, env, nullptr, B->state + env * (int64_t)G->d.n_state);
+        env_score(G->d, cx, sm.data(), *B, env,
+                  (G->d.n_dyn > 0 && B->yval) ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr,
+                  B->state + env * (int64_t)G->d.n_state);
 #else
     const size_t smem = score_smem_doubles(G->d.nb, G->d.nbr, G->score_threads) * sizeof(double);
     OPFG_DISPATCH_T(G->score_threads, {

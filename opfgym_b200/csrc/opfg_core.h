@@ -64,6 +64,13 @@ struct GridDev {
     int n_qlim;
     const int* qlim_bus;               // [n_qlim] internal bus index
     const double *qlim_min, *qlim_max; // [n_qlim]
+    // per-environment branch parameters (tap / in-service cells): kernel 1 rebuilds their
+    // admittances and the Ybus values per environment
+    int n_dyn;
+    const int* dyn_branch;             // [n_dyn] ppc branch row
+    const int* dyn_of_branch;          // [nbr] index into the dynamic list or -1
+    const int *dyn_tap_ref, *dyn_svc_ref;
+    const double *dyn_neutral, *dyn_step, *dyn_ratio0;
     // DC start
     const double* dc_val;              // [n_blocks] scalar factor on the same schedule
     const double* dc_rhs0;             // [n]
@@ -211,19 +218,23 @@ OPFG_HD void branch_admittance(const double* p, double* y) {
 }
 
 // one Ybus CSR entry = ordered sum of its branch / shunt contributions
-OPFG_HD void ybus_entry(const GridDev& g, const double* br_y, int e, double* out) {
+OPFG_HD void ybus_entry(const GridDev& g, const double* br_y, int e, double* out,
+                        const double* bry_env = nullptr) {
     double re = 0, im = 0;
     for (int c = g.yc_ptr[e]; c < g.yc_ptr[e + 1]; ++c) {
         const int role = g.yc_role[c], idx = g.yc_branch[c];
-        if (role == 4) { re += g.bus_ysh[2 * idx]; im += g.bus_ysh[2 * idx + 1]; }
-        else { re += br_y[8 * idx + 2 * role]; im += br_y[8 * idx + 2 * role + 1]; }
+        if (role == 4) { re += g.bus_ysh[2 * idx]; im += g.bus_ysh[2 * idx + 1]; continue; }
+        const double* y = br_y + 8 * idx;
+        if (bry_env) { const int d = g.dyn_of_branch[idx]; if (d >= 0) y = bry_env + 8 * d; }
+        re += y[2 * role]; im += y[2 * role + 1];
     }
     out[0] = re; out[1] = im;
 }
 
 // --------------------------------------- kernel 1b: actions -> set-points -> Sbus
 template <class C>
-OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, double* S, double* sbus) {
+OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, double* S, double* sbus,
+                          double* yval_env = nullptr, double* bry_env = nullptr) {
     const int T = cx.nthreads();
     for (int j = cx.tid; act != nullptr && j < g.n_act; j += T) {
         double a = act[j];
@@ -246,6 +257,24 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
 #ifdef OPFG_DEVICE_BUILD
     __threadfence_block();
 #endif
+    if (g.n_dyn > 0 && yval_env && bry_env) {
+        // kernel 1a per environment: admittances of the branches with tap / in-service cells
+        // (pandapower build_branch.py tap handling + pypower makeYbus.py [ext-mem]), then Ybus values
+        for (int d = cx.tid; d < g.n_dyn; d += T) {
+            double p[6];
+            const double* src = g.br_param + 6 * (size_t)g.dyn_branch[d];
+            for (int k = 0; k < 6; ++k) p[k] = src[k];
+            const double pos = ref_val(g, S, g.dyn_tap_ref[d]);
+            if (pos == pos) p[4] = g.dyn_ratio0[d] * (1.0 + (pos - g.dyn_neutral[d]) * g.dyn_step[d] / 100.0);
+            if (ref_val(g, S, g.dyn_svc_ref[d]) == 0.0) { p[0] = 1e300; p[1] = 0; p[2] = 0; p[3] = 0; }
+            branch_admittance(p, bry_env + 8 * (size_t)d);
+        }
+        cx.sync();
+#ifdef OPFG_DEVICE_BUILD
+        __threadfence_block();
+#endif
+        for (int e = cx.tid; e < g.nnz_y; e += T) ybus_entry(g, g.br_y, e, yval_env + 2 * (size_t)e, bry_env);
+    }
     const double inv_base = 1.0 / g.base_mva;
 #pragma unroll 2
     for (int bus = cx.tid; bus < g.nb; bus += T) {
@@ -682,8 +711,14 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     }
     cx.sync();
     // branch flows and loading (pfsoln + results_branch.py [ext-mem])
+    const double* bry_env = (g.n_dyn > 0 && B.bry) ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr;
     for (int l = cx.tid; l < nbr; l += T) {
         const double* y = g.br_y + 8 * (size_t)l;
+        bool in_service = true;
+        if (bry_env) {
+            const int d = g.dyn_of_branch[l];
+            if (d >= 0) { y = bry_env + 8 * (size_t)d; in_service = ref_val(g, S, g.dyn_svc_ref[d]) != 0.0; }
+        }
         const int f = g.br_f[l], t = g.br_t[l];
         const double vfr = s.vr[f], vfi = s.vi[f], vtr = s.vr[t], vti = s.vi[t];
         const double ifr = y[0] * vfr - y[1] * vfi + y[2] * vtr - y[3] * vti;
@@ -696,7 +731,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         const double lf = sqrt(pf * pf + qf * qf) * g.rate_f[l] / s.vm[f];
         const double lt = sqrt(pt * pt + qt * qt) * g.rate_t[l] / s.vm[t];
         const int slot = g.br_loading_slot[l];
-        if (slot >= 0) S[slot] = 100.0 * (lf > lt ? lf : lt);
+        if (slot >= 0) S[slot] = in_service ? 100.0 * (lf > lt ? lf : lt) : NAN;   // pandapower: NaN when out of service
         const int fs = g.br_flow_slot[l];
         if (fs >= 0) { S[fs] = pf; S[fs + 1] = qf; S[fs + 2] = pt; S[fs + 3] = qt; }
     }

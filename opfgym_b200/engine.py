@@ -24,7 +24,7 @@ class Engine:
         self.num_envs = int(num_envs)
         self.lib = lib if lib is not None else capi.load()
         self._setup_device(device)
-        gd, ad, sd, keep = fill_descs(
+        gd, ad, sd, dd, keep = fill_descs(
             capi, program, tol_pu=tolerance_mva / program.ppc.base_mva,
             max_iter=max_iteration, init_dc=(init == "dc"), enforce_q_lims=enforce_q_lims,
             threads_per_env=threads_per_env, ordering=ordering)
@@ -32,6 +32,8 @@ class Engine:
         capi.check(self.lib, self.lib.opfg_grid_create(C.byref(gd), C.byref(handle)))
         self.handle = handle
         capi.check(self.lib, self.lib.opfg_set_assembly(handle, C.byref(ad)))
+        if dd is not None:
+            capi.check(self.lib, self.lib.opfg_set_dynamic_branches(handle, C.byref(dd)))
         capi.check(self.lib, self.lib.opfg_set_scoring(handle, C.byref(sd)))
         del keep
         info = capi.GridInfo()
@@ -60,6 +62,10 @@ class Engine:
         self.obs_final = self._zeros((B, max(program.n_obs, 1)), obs_dtype)
         self.stats = self._zeros((capi.N_STATS,), "float64")
         self.n_constraints = nc
+        self.yval = self.bry = None
+        if dd is not None:     # per-environment Ybus values / branch admittances (kernel 1 output)
+            self.yval = self._zeros((B, self.info["nnz_y"], 2), "float64")
+            self.bry = self._zeros((B, dd.n_dyn, 8), "float64")
         self.batch = capi.Batch(
             n_env=B, actions=self._ptr(self.actions), state=self._ptr(self.state),
             sbus=self._ptr(self.sbus), vm=self._ptr(self.vm), va=self._ptr(self.va),
@@ -70,7 +76,9 @@ class Engine:
             penalties=self._ptr(self.penalties),
             obs_f32=self._ptr(self.obs) if obs_dtype == "float32" else None,
             obs_f64=self._ptr(self.obs) if obs_dtype == "float64" else None,
-            stats=self._ptr(self.stats))
+            stats=self._ptr(self.stats),
+            yval=self._ptr(self.yval) if self.yval is not None else None,
+            bry=self._ptr(self.bry) if self.bry is not None else None)
         self.batch_final = capi.Batch.from_buffer_copy(self.batch)
         if obs_dtype == "float32":
             self.batch_final.obs_f32 = self._ptr(self.obs_final)

@@ -151,7 +151,9 @@ class BatchedOpfEnv:
 
         # ---- compile + device buffers ------------------------------------------------
         self.rank, self.world_size = int(rank), int(world_size)
-        self._builder = PpcBuilder(net)
+        dyn_service = {t for t, c, _ in self.act_keys if c == "in_service" and t in ("line", "trafo")}
+        dyn_service |= {t for t, c in dynamic_columns if c == "in_service" and t in ("line", "trafo")}
+        self._builder = PpcBuilder(net, dynamic_service=tuple(sorted(dyn_service)))
         compiler = Compiler(net, self._builder)
         placeholder = reward_mod.Summation()
         dynamic = list(dynamic_columns) + list(self._dynamic_columns())

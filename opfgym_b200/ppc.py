@@ -98,9 +98,13 @@ class PpcBuilder:
     """
 
     def __init__(self, net, calculate_voltage_angles: bool = True,
-                 trafo_model: str = "t"):
+                 trafo_model: str = "t", dynamic_service=()):
+        """``dynamic_service``: tables ('line', 'trafo') whose ``in_service`` flag is a
+        per-environment cell: their elements stay in the topology (status is applied per
+        environment by kernel 1), so that e.g. normally-open ties can be switched on."""
         self.calculate_voltage_angles = calculate_voltage_angles
         self.trafo_model = trafo_model
+        self.dynamic_service = tuple(dynamic_service)
         self._analyse(net)
 
     # ------------------------------------------------------------------ topology
@@ -128,6 +132,8 @@ class PpcBuilder:
         lf = np.array([pos_of[int(b)] for b in net.line.from_bus.to_numpy()], dtype=np.int64)
         lt = np.array([pos_of[int(b)] for b in net.line.to_bus.to_numpy()], dtype=np.int64)
         l_in = net.line.in_service.to_numpy(bool).copy() if nl else np.zeros(0, bool)
+        if "line" in self.dynamic_service:
+            l_in[:] = True
         open_f = np.zeros(nl, bool)
         open_t = np.zeros(nl, bool)
         if len(sw):
@@ -147,6 +153,8 @@ class PpcBuilder:
         th = np.array([pos_of[int(b)] for b in net.trafo.hv_bus.to_numpy()], dtype=np.int64)
         tl = np.array([pos_of[int(b)] for b in net.trafo.lv_bus.to_numpy()], dtype=np.int64)
         t_in = net.trafo.in_service.to_numpy(bool).copy() if nt else np.zeros(0, bool)
+        if "trafo" in self.dynamic_service:
+            t_in[:] = True
         if len(sw):
             ts = sw[(sw.et == "t") & ~sw.closed.astype(bool)]
             tpos = {int(t): i for i, t in enumerate(trafo_index)}
@@ -273,6 +281,9 @@ class PpcBuilder:
             vnh = np.where(on_hv, vnh * (1.0 + steps), vnh)
             vnl = np.where(on_lv, vnl * (1.0 + steps), vnl)
             ratio = (vnh / vnl) / (vn_hv_bus / vn_lv_bus)
+            self.trafo_ratio_neutral = (tr.vn_hv_kv.to_numpy(float) / tr.vn_lv_kv.to_numpy(float)) / \
+                (vn_hv_bus / vn_lv_bus)
+            self.trafo_tap_on_hv = on_hv
             shift = tr.shift_degree.to_numpy(float) if self.calculate_voltage_angles else np.zeros(nt)
             par = tr.parallel.to_numpy(float)
             sn_t = tr.sn_mva.to_numpy(float)
