@@ -137,6 +137,35 @@ class RewardFunction:
     def adjust_objective(self, objective: float, valid: bool) -> float:
         return objective
 
+    # ---- tensor form of the same arithmetic (N-1 recombination on the device) ----
+    def batched(self, objective, penalty, valid):
+        """``__call__`` on torch tensors [B] (objective, penalty float; valid bool)."""
+        import torch
+        p = self.device_params()
+        obj, pen = objective, penalty
+        if p["kind"] == REPLACEMENT:
+            obj = torch.where(valid, obj + p["valid_reward"], torch.zeros_like(obj))
+        elif p["kind"] == PARAMETERIZED:
+            pen = torch.where(valid, pen + p["valid_reward"], pen - p["invalid_penalty"])
+            obj = torch.where(valid, obj, obj * p["invalid_objective_share"])
+        elif p["kind"] == ONLY_OBJECTIVE:
+            pen = torch.zeros_like(pen)
+        obj = obj * p["objective_factor"] + p["objective_bias"]
+        pen = pen * p["penalty_factor"] + p["penalty_bias"]
+        w = p["penalty_weight"]
+        r = obj + pen if math.isnan(w) else obj * (1 - w) + pen * w
+        if not math.isnan(p["clip_lo"]):
+            r = r.clamp(p["clip_lo"], p["clip_hi"])
+        return r
+
+    def batched_cost(self, penalty, valid):
+        import torch
+        p = self.device_params()
+        c = (penalty * p["penalty_factor"]).abs()
+        if p["kind"] == PARAMETERIZED:
+            c = c + p["invalid_penalty"]
+        return torch.where(valid, torch.zeros_like(c), c)
+
     # ---- flat parameter record consumed by the scoring kernel --------------
     def device_params(self) -> dict:
         sp = self.scaling_params
