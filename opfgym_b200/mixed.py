@@ -1,0 +1,76 @@
+"""Several batched envs of different grids stepped as one batch (BASELINE config 4:
+"MaxRenewable + QMarket mixed batch").  Each member keeps its own compiled grid; the
+members' launches go to separate CUDA streams so that their kernels overlap on the
+device, and the outputs are concatenated along the env axis (observations are padded to
+the widest member).  Episode statistics add up across members."""
+from __future__ import annotations
+
+
+class MixedBatchEnv:
+    def __init__(self, envs):
+        self.envs = list(envs)
+        self.num_envs = sum(e.num_envs for e in self.envs)
+        self.xp = self.envs[0].xp
+        self.device = self.envs[0].device
+        self.splits = [e.num_envs for e in self.envs]
+        self.n_obs = max(e.single_observation_space.shape[0] for e in self.envs)
+        self.n_act = max(e.single_action_space.shape[0] for e in self.envs)
+        cuda = getattr(self.device, "type", "cpu") == "cuda"
+        self._streams = [self.xp.cuda.Stream(device=self.device) for _ in self.envs] if cuda else None
+
+    def _each(self, fn):
+        """Run ``fn(i, env)`` for every member, each on its own stream; join on the caller's stream."""
+        if self._streams is None:
+            return [fn(i, e) for i, e in enumerate(self.envs)]
+        xp = self.xp
+        cur = xp.cuda.current_stream(self.device)
+        start = xp.cuda.Event()
+        start.record(cur)
+        outs = []
+        for i, (e, s) in enumerate(zip(self.envs, self._streams)):
+            with xp.cuda.stream(s):
+                s.wait_event(start)
+                outs.append(fn(i, e))
+                done = xp.cuda.Event()
+                done.record(s)
+            cur.wait_event(done)
+        return outs
+
+    def _pad(self, obs):
+        xp = self.xp
+        out = []
+        for o in obs:
+            if o.shape[1] < self.n_obs:
+                pad = xp.full((o.shape[0], self.n_obs - o.shape[1]), float("nan"), dtype=o.dtype, device=o.device)
+                o = xp.cat([o, pad], dim=1)
+            out.append(o)
+        return xp.cat(out, dim=0)
+
+    def reset(self, seed=None, options=None):
+        outs = self._each(lambda i, e: e.reset(seed=seed, options=options))
+        return self._pad([o[0] for o in outs]), {}
+
+    def step(self, actions):
+        """``actions[num_envs, n_act]``: member i reads its rows and its first n_act_i columns."""
+        xp = self.xp
+        act = xp.as_tensor(actions, device=self.device)
+        parts = act.split(self.splits, dim=0)
+        outs = self._each(lambda i, e: e.step(parts[i][:, :e.single_action_space.shape[0]]))
+        obs = self._pad([o[0] for o in outs])
+        reward, term, trunc = (xp.cat([o[k] for o in outs]) for k in (1, 2, 3))
+        info = {"member": outs, "converged": xp.cat([o[4]["converged"] for o in outs]),
+                "cost": xp.cat([o[4]["cost"] for o in outs])}
+        return obs, reward, term, trunc, info
+
+    def episode_statistics(self, reduce=True):
+        stats = [e.episode_statistics(reduce=reduce) for e in self.envs]
+        steps = sum(s["steps"] for s in stats)
+        return {"steps": steps, "converged": sum(s["converged"] for s in stats),
+                "valid": sum(s["valid"] for s in stats),
+                "mean_reward": sum(s["mean_reward"] * s["converged"] for s in stats) /
+                max(sum(s["converged"] for s in stats), 1.0),
+                "members": stats}
+
+    def close(self):
+        for e in self.envs:
+            e.close()

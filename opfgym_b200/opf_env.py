@@ -89,8 +89,8 @@ class BatchedOpfEnv:
                 "Python callables cannot run inside the batched kernels; costs are taken from "
                 "net.poly_cost / net.pwl_cost and the power flow is the CUDA engine. Use "
                 "opfgym_b200.adapter.power_flow_solver to plug the engine into a single-env OpfEnv.")
-        if steps_per_episode != 1:
-            raise NotImplementedError("multi-step episodes: SURVEY.md §8(f) rank 3")
+        if steps_per_episode != 1 and not getattr(self, "_multi_step_ok", False):
+            raise NotImplementedError("multi-step episodes: use opfgym_b200.multi_stage.MultiStageBatchedOpfEnv")
 
         self.net = net
         self.copy_outputs = copy_outputs   # False: returned tensors alias engine buffers
@@ -331,7 +331,8 @@ class BatchedOpfEnv:
             self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
             step_idx = pool[(u[:, 0] * pool.shape[0]).long().clamp_(max=pool.shape[0] - 1)]
         else:
-            step_idx = xp.as_tensor(step, device=self.device).long().expand(B)
+            step_idx = xp.as_tensor(step, device=self.device).long()
+            step_idx = step_idx.expand(B) if step_idx.dim() == 0 else step_idx
         self.current_simbench_step = step_idx
         for key, (table, pmin, pmax) in self._prof_dev.items():
             unit_type, column = key

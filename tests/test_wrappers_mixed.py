@@ -1,0 +1,49 @@
+"""StochasticObservation wrapper (reference wrappers/stochastic_obs.py) and the mixed
+MaxRenewable + QMarket batch (BASELINE config 4) on the host-sim build."""
+import numpy as np
+import torch
+
+from opfgym_b200 import envs
+from opfgym_b200.mixed import MixedBatchEnv
+from opfgym_b200.wrappers import StochasticObservation
+from tests.hostsim.harness import TorchHostSimEngine
+
+KW = dict(engine_cls=TorchHostSimEngine, n_profile_steps=672, obs_dtype="float64",
+          train_data="full_uniform", test_data="full_uniform", seed=3)
+
+
+def test_stochastic_observation_noise_and_clipping():
+    base = envs.QMarket(num_envs=16, **KW)
+    clean, _ = base.reset(seed=4)
+    env = StochasticObservation(envs.QMarket(num_envs=16, **KW), noise_relative_range=0.1)
+    noisy, _ = env.reset(seed=4)
+    lo = torch.as_tensor(np.asarray(env.single_observation_space.low, float))
+    hi = torch.as_tensor(np.asarray(env.single_observation_space.high, float))
+    assert noisy.shape == clean.shape and not torch.equal(noisy, clean)
+    assert (noisy >= lo - 1e-12).all() and (noisy <= hi + 1e-12).all()       # clipped to the space
+    assert ((noisy - clean).abs() <= 0.1 * (hi - lo) + 1e-9).all()
+    wide = StochasticObservation(envs.QMarket(num_envs=16, **KW), noise_relative_range=0.1,
+                                 maintain_original_range=False)
+    assert (np.asarray(wide.single_observation_space.high) >
+            np.asarray(base.single_observation_space.high) - 1e-12).all()
+    obs, reward, term, trunc, info = env.step(torch.rand(16, 10, dtype=torch.float64))
+    assert obs.shape == (16, 305) and term.all()
+    assert env.num_envs == 16 and env.single_action_space.shape == (10,)      # attribute pass-through
+
+
+def test_mixed_batch_equals_members_stepped_alone():
+    def members():
+        return [envs.MaxRenewable(num_envs=6, **KW), envs.QMarket(num_envs=10, **KW)]
+    mixed = MixedBatchEnv(members())
+    alone = members()
+    assert mixed.num_envs == 16 and mixed.n_obs == 305 and mixed.n_act == 18
+    obs, _ = mixed.reset(seed=9)
+    ref = [e.reset(seed=9)[0] for e in alone]
+    assert torch.equal(obs[:6, :172], ref[0]) and torch.isnan(obs[:6, 172:]).all()
+    assert torch.equal(obs[6:], ref[1])
+    act = torch.rand(16, 18, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    obs, reward, term, trunc, info = mixed.step(act)
+    r0 = alone[0].step(act[:6, :18])
+    r1 = alone[1].step(act[6:, :10])
+    assert torch.equal(reward, torch.cat([r0[1], r1[1]])) and term.all() and info["converged"].all()
+    assert mixed.episode_statistics()["steps"] == 16
