@@ -302,6 +302,36 @@ class BatchedOpfEnv:
         assert sample_new, "Currently only implemented for sample_new=True"
         self._sample_keys(list(sample_keys or self.state_keys))
 
+    def _sample_normal(self, relative_std=None, truncated=False, sample_new=True, **_):
+        """opf_env.py:286-315: N(mean, std*diff) around the profile mean, clipped to the data range.
+        (As in the reference, `relative_std` ends up multiplied by the range twice, A.6 quirk 9.)"""
+        assert sample_new, "Currently only implemented for sample_new=True"
+        if truncated:
+            raise NotImplementedError("truncated normal (scipy.stats.truncnorm) is not on the device")
+        xp = self.xp
+        if "_normal" not in self._sample_cache:
+            plan = []
+            for unit_type, column, idxs in self.state_keys:
+                if "res_" in unit_type or "poly_cost" in unit_type or len(idxs) == 0:
+                    continue
+                df = self.net[unit_type]
+                pos = self.positions(unit_type, idxs)
+                scal = df.scaling.to_numpy(float)[pos]
+                hi = df[f"max_max_{column}"].to_numpy(float)[pos] / scal
+                lo = df[f"min_min_{column}"].to_numpy(float)[pos] / scal
+                std = relative_std * (hi - lo) if relative_std else df[f"std_dev_{column}"].to_numpy(float)[pos]
+                start = self.program.layout.columns[(unit_type, column)][0]
+                f = self.engine._from_numpy
+                plan.append((xp.as_tensor(start + pos, device=self.device), f(df[f"mean_{column}"].to_numpy(float)[pos]),
+                             f(std * (hi - lo)), f(lo), f(hi)))
+            self._sample_cache["_normal"] = plan
+        for cols, mean, sigma, lo, hi in self._sample_cache["_normal"]:
+            n = cols.shape[0]
+            u = xp.empty((self.num_envs, 2 * n), dtype=xp.float64, device=self.device)
+            self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
+            z = xp.sqrt(-2.0 * xp.log1p(-u[:, :n])) * xp.cos(2.0 * np.pi * u[:, n:])    # Box-Muller
+            self.engine.state[:, cols] = xp.minimum(xp.maximum(mean + sigma * z, lo), hi)
+
     def _set_simbench_state(self, step=None, test=False, noise_factor=0.1,
                             noise_distribution="uniform", interpolate_steps=False, **_):
         """opf_env.py:317-372: gather one profile row per environment, multiply by
@@ -358,8 +388,29 @@ class BatchedOpfEnv:
                 self._set_simbench_state(step, test, noise_factor=0.0, **kwargs)
         elif distr == "full_uniform":
             self._sample_uniform(sample_new=sample_new)
+        elif distr == "normal_around_mean":
+            self._sample_normal(sample_new=sample_new, **kwargs)
+        elif distr == "mixed":
+            # opf_env.py:242-251 draws ONE data source per episode; here every environment draws its
+            # own: all three samplers run and each env keeps the columns of the source it drew
+            probs = kwargs.pop("data_probabilities", (0.5, 0.75, 1.0))
+            xp = self.xp
+            r = xp.empty((self.num_envs, 1), dtype=xp.float64, device=self.device)
+            self.engine.philox_uniform(r, self.seed, self.first_env, self._next_stream())
+            n_in = self.program.layout.n_inputs
+            state = self.engine.state
+            self._set_simbench_state(step, test, **{k: v for k, v in kwargs.items()
+                                                    if k in ("noise_factor", "noise_distribution")})
+            from_simbench = state[:, :n_in].clone()
+            self._sample_uniform(sample_new=sample_new)
+            from_uniform = state[:, :n_in].clone()
+            self._sample_normal(sample_new=sample_new, **{k: v for k, v in kwargs.items()
+                                                          if k in ("relative_std", "truncated")})
+            pick = xp.where(r < probs[0], from_simbench, xp.where(r < probs[1], from_uniform, state[:, :n_in]))
+            state[:, :n_in] = pick
+            self.sample_source = (r[:, 0] >= probs[0]).long() + (r[:, 0] >= probs[1]).long()
         else:
-            raise NotImplementedError(f"data distribution {distr!r}: SURVEY.md §8(f) rank 3")
+            raise NotImplementedError(f"unknown data distribution {distr!r}")
 
     # --------------------------------------------------------------------- gym interface
     def reset(self, seed: int | None = None, options: dict | None = None):

@@ -201,3 +201,34 @@ def test_benchmark_sizes_and_three_steps(cls, n_obs, n_act):
         assert obs.shape == (3, n_obs) and term.all() and info["converged"].all()
     assert envs.make(f"{cls.__name__}-v0", num_envs=2, **dict(KW, train_data="full_uniform",
                                                              test_data="full_uniform")).num_envs == 2
+
+
+def test_normal_and_mixed_sampling():
+    """opf_env.py:240-251, 286-315."""
+    env = make(n=2048, train_data="normal_around_mean", n_profile_steps=4 * 672,
+               sampling_params={"relative_std": 0.3})
+    env.reset(seed=3)
+    df = env.net.load
+    p = env.col("load", "p_mw")
+    lo = torch.as_tensor((df.min_min_p_mw / df.scaling).to_numpy().copy())
+    hi = torch.as_tensor((df.max_max_p_mw / df.scaling).to_numpy().copy())
+    assert (p >= lo - 1e-12).all() and (p <= hi + 1e-12).all()
+    inside = (p > lo + 1e-9) & (p < hi - 1e-9)
+    col = 5
+    want_sigma = 0.3 * float(hi[col] - lo[col]) ** 2              # quirk 9: range applied twice
+    sample = p[:, col][inside[:, col]]
+    assert abs(float(sample.std()) - want_sigma) < 0.35 * want_sigma or inside[:, col].float().mean() < 0.9
+    mixed = make(n=4096, train_data="mixed", n_profile_steps=4 * 672)
+    mixed.reset(seed=4)
+    share = torch.bincount(mixed.sample_source, minlength=3).double() / 4096
+    assert torch.allclose(share, torch.tensor([0.5, 0.25, 0.25], dtype=torch.float64), atol=0.03)
+    prof = torch.as_tensor(mixed.profiles[("load", "p_mw")].to_numpy().copy())
+    sb = mixed.sample_source == 0
+    noise = mixed.col("load", "p_mw")[sb] / prof[mixed.current_simbench_step[sb]]
+    assert (noise >= 0.9 - 1e-9).all() and (noise <= 1.1 + 1e-9).all()   # default noise_factor 0.1
+    # a storage sampled exactly at its rated power makes the reference's VoltageControl hook take
+    # sqrt(max_s^2 - (p + 1e-9)^2) of a negative number (envs/voltage_control.py:128-131): NaN Q
+    # bounds there, and here -- such envs come back non-converged, all others solve
+    nan_bounds = torch.isnan(mixed.col("storage", "max_q_mvar")).any(dim=1)
+    obs, reward, term, _, info = mixed.step(torch.rand(4096, 14, dtype=torch.float64))
+    assert info["converged"][~nan_bounds].all() and info["converged"].float().mean() > 0.7
