@@ -447,7 +447,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         int T = desc->threads_per_env;
         Symbolic& s = G->sym;
         analyse(nb, type, active, desc->ordering, T > 0 ? T : 32, s);
-        if (T <= 0) T = s.n_blocks <= 4000 ? 64 : 128;   // measured: 64 beats 32 on MV and HV grids
+        if (T <= 0) T = s.n_blocks <= 1000 ? 64 : 128;   // measured: 64 on the MV grids (~450 blocks), 128 on HV (~1900)
         for (size_t c = 0; c < s.yc_branch.size(); ++c)
             if (s.yc_role[c] != 4) s.yc_branch[c] = active_row[s.yc_branch[c]];
 
