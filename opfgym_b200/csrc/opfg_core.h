@@ -293,8 +293,11 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
 // ------------------------------------------------------ kernels 2-4: Newton-Raphson
 // Shared-memory working set of one environment.  2x2 blocks are 32-byte aligned
 // (two 128-bit shared loads per block); V is kept as interleaved (re, im) pairs.
+// The 2x2 blocks are stored as two planes of 16-byte rows (row 0 of every block, then row 1 of
+// every block): neighbouring lanes working on neighbouring blocks then touch contiguous 128-byte
+// spans instead of a 32-byte stride, which halves the shared-memory bank conflicts (profile r01d).
 struct PfSmem {
-    double *lu, *rhs, *vri, *ivm, *red;
+    double *lu, *lu1, *rhs, *vri, *ivm, *red;
     double* qadd;                 // [n] reactive power fixed at a limit (enforce_q_lims), else null
     unsigned char* type;          // [nb] per-environment bus types (enforce_q_lims), else null
     const unsigned char* bus_type;   // what the kernels read: `type` or the shared table
@@ -308,6 +311,7 @@ OPFG_HHD size_t pf_smem_doubles(int n_blocks, int n, int nb, int threads, int n_
 OPFG_HD PfSmem pf_carve(double* base, int n_blocks, int n, int nb) {
     PfSmem s;
     s.lu = base;
+    s.lu1 = base + 2 * (size_t)n_blocks;
     s.rhs = s.lu + 4 * (size_t)n_blocks;
     s.vri = s.rhs + 2 * (size_t)n;
     s.ivm = s.vri + 2 * (size_t)nb;
@@ -352,8 +356,8 @@ OPFG_HD double row_mismatch(const GridDev& g, const PfSmem& s, const double* yv,
     if (jac) {
         const double ar = fma(vi.x, dr, vi.y * di), ai = fma(vi.y, dr, -(vi.x * di));   // V_i conj(Y_ii V_i)
         const double inv_vmi = s.ivm[i];
-        st2(s.lu + 4 * i, -Q + ai, (ar + P) * inv_vmi);
-        st2(s.lu + 4 * i + 2, pq ? P - ar : 0.0, pq ? (ai + Q) * inv_vmi : 1.0);
+        st2(s.lu + 2 * i, -Q + ai, (ar + P) * inv_vmi);
+        st2(s.lu1 + 2 * i, pq ? P - ar : 0.0, pq ? (ai + Q) * inv_vmi : 1.0);
     }
     const double dp = P - sp.x, dq = pq ? Q - sp.y : 0.0;
     st2(s.rhs + 2 * i, -dp, -dq);
@@ -374,29 +378,28 @@ OPFG_HD void jacobian_entry(const GridDev& g, const PfSmem& s, const double* yv,
     const double ar = fma(vi.x, tr, vi.y * ti), ai = fma(vi.y, tr, -(vi.x * ti));   // V_i conj(Y_ij V_j)
     const double inv_vmj = s.ivm[j];
     const bool pq = s.bus_type[i] == OPFG_PQ;
-    st2(s.lu + 4 * blk, ai, ar * inv_vmj);                    // dP/dtheta_j, dP/dVm_j
-    st2(s.lu + 4 * blk + 2, pq ? -ar : 0.0, pq ? ai * inv_vmj : 0.0);
+    st2(s.lu + 2 * blk, ai, ar * inv_vmj);                    // dP/dtheta_j, dP/dVm_j
+    st2(s.lu1 + 2 * blk, pq ? -ar : 0.0, pq ? ai * inv_vmj : 0.0);
 }
 
 // ---- diagonal pivot: D_k -= sum L~(k,m) W(m,k), y_k -= sum L~(k,m) t_m, invert, t_k = D^-1 y_k
 // (a) one lane per pivot
 OPFG_HD void lu_diag_item(const GridDev& g, const PfSmem& s, int k) {
-    double* D = s.lu + 4 * k;
-    D2 r0 = ld2(D), r1 = ld2(D + 2), y = ld2(s.rhs + 2 * k);
+    D2 r0 = ld2(s.lu + 2 * k), r1 = ld2(s.lu1 + 2 * k), y = ld2(s.rhs + 2 * k);
     const int pe = g.dp_ptr[k + 1];
     for (int p = g.dp_ptr[k]; p < pe; ++p) {
         const U2 id = g.dp_pack[p];
-        const double* L = s.lu + 4 * (id.x & 0xffffu);
-        const double* W = s.lu + 4 * (id.x >> 16);
-        const D2 l0 = ld2(L), l1 = ld2(L + 2), w0 = ld2(W), w1 = ld2(W + 2), t = ld2(s.rhs + 2 * id.y);
+        const int li = 2 * (int)(id.x & 0xffffu), wi = 2 * (int)(id.x >> 16);
+        const D2 l0 = ld2(s.lu + li), l1 = ld2(s.lu1 + li), w0 = ld2(s.lu + wi), w1 = ld2(s.lu1 + wi),
+                 t = ld2(s.rhs + 2 * id.y);
         r0.x = fma(-l0.y, w1.x, fma(-l0.x, w0.x, r0.x));  r0.y = fma(-l0.y, w1.y, fma(-l0.x, w0.y, r0.y));
         r1.x = fma(-l1.y, w1.x, fma(-l1.x, w0.x, r1.x));  r1.y = fma(-l1.y, w1.y, fma(-l1.x, w0.y, r1.y));
         y.x = fma(-l0.y, t.y, fma(-l0.x, t.x, y.x));      y.y = fma(-l1.y, t.y, fma(-l1.x, t.x, y.y));
     }
     const double r = 1.0 / fma(r0.x, r1.y, -(r0.y * r1.x));
     const double ia = r1.y * r, ib = -r0.y * r, ic = -r1.x * r, id_ = r0.x * r;
-    st2(D, ia, ib);
-    st2(D + 2, ic, id_);
+    st2(s.lu + 2 * k, ia, ib);
+    st2(s.lu1 + 2 * k, ic, id_);
     st2(s.rhs + 2 * k, fma(ia, y.x, ib * y.y), fma(ic, y.x, id_ * y.y));
 }
 
@@ -404,13 +407,13 @@ OPFG_HD void lu_diag_item(const GridDev& g, const PfSmem& s, int k) {
 // lanes 4 and 5 own y_0 and y_1 (short, independent gather chains instead of one long one)
 OPFG_HD double lu_diag_component(const GridDev& g, const PfSmem& s, int k, int sub) {
     const int r = sub < 4 ? (sub >> 1) : (sub - 4);
-    double acc = sub < 4 ? s.lu[4 * k + sub] : s.rhs[2 * k + r];
+    double acc = sub < 4 ? (r ? s.lu1 : s.lu)[2 * k + (sub & 1)] : s.rhs[2 * k + r];
     const int pe = g.dp_ptr[k + 1];
     for (int p = g.dp_ptr[k]; p < pe; ++p) {
         const U2 id = g.dp_pack[p];
-        const D2 l = ld2(s.lu + 4 * (id.x & 0xffffu) + 2 * r);
+        const D2 l = ld2((r ? s.lu1 : s.lu) + 2 * (id.x & 0xffffu));
         double wa, wb;
-        if (sub < 4) { const double* W = s.lu + 4 * (id.x >> 16) + (sub & 1); wa = W[0]; wb = W[2]; }
+        if (sub < 4) { const int wi = 2 * (int)(id.x >> 16) + (sub & 1); wa = s.lu[wi]; wb = s.lu1[wi]; }
         else { const D2 t = ld2(s.rhs + 2 * id.y); wa = t.x; wb = t.y; }
         acc = fma(-l.y, wb, fma(-l.x, wa, acc));
     }
@@ -421,10 +424,10 @@ OPFG_HD void lu_diag_finish(const PfSmem& s, int k, int sub, double a, double b,
                             double y0, double y1) {
     const double r = 1.0 / fma(a, d, -(b * c));
     const double ia = d * r, ib = -b * r, ic = -c * r, id_ = a * r;
-    if (sub == 0) s.lu[4 * k] = ia;
-    else if (sub == 1) s.lu[4 * k + 1] = ib;
-    else if (sub == 2) s.lu[4 * k + 2] = ic;
-    else if (sub == 3) s.lu[4 * k + 3] = id_;
+    if (sub == 0) s.lu[2 * k] = ia;
+    else if (sub == 1) s.lu[2 * k + 1] = ib;
+    else if (sub == 2) s.lu1[2 * k] = ic;
+    else if (sub == 3) s.lu1[2 * k + 1] = id_;
     else if (sub == 4) s.rhs[2 * k] = fma(ia, y0, ib * y1);
     else if (sub == 5) s.rhs[2 * k + 1] = fma(ic, y0, id_ * y1);
 }
@@ -432,25 +435,24 @@ OPFG_HD void lu_diag_finish(const PfSmem& s, int k, int sub, double a, double b,
 OPFG_HD void lu_off_item(const GridDev& g, const PfSmem& s, int item) {
     const U2 hdr = g.off_hdr[item];
     const int pe = (int)g.off_hdr[item + 1].y;
-    double* X = s.lu + 4 * (hdr.x & 0xffffu);
-    D2 r0 = ld2(X), r1 = ld2(X + 2);
+    const int xi = 2 * (int)(hdr.x & 0xffffu);
+    D2 r0 = ld2(s.lu + xi), r1 = ld2(s.lu1 + xi);
     for (int p = (int)hdr.y; p < pe; ++p) {
         const uint32_t id = g.op_pack[p];
-        const double* L = s.lu + 4 * (id & 0xffffu);
-        const double* W = s.lu + 4 * (id >> 16);
-        const D2 l0 = ld2(L), l1 = ld2(L + 2), w0 = ld2(W), w1 = ld2(W + 2);
+        const int li = 2 * (int)(id & 0xffffu), wi = 2 * (int)(id >> 16);
+        const D2 l0 = ld2(s.lu + li), l1 = ld2(s.lu1 + li), w0 = ld2(s.lu + wi), w1 = ld2(s.lu1 + wi);
         r0.x = fma(-l0.y, w1.x, fma(-l0.x, w0.x, r0.x));  r0.y = fma(-l0.y, w1.y, fma(-l0.x, w0.y, r0.y));
         r1.x = fma(-l1.y, w1.x, fma(-l1.x, w0.x, r1.x));  r1.y = fma(-l1.y, w1.y, fma(-l1.x, w0.y, r1.y));
     }
     const int piv = (int)(hdr.x >> 16) - 1;
     if (piv >= 0) {   // W = D^-1 * U
-        const D2 i0 = ld2(s.lu + 4 * piv), i1 = ld2(s.lu + 4 * piv + 2);
+        const D2 i0 = ld2(s.lu + 2 * piv), i1 = ld2(s.lu1 + 2 * piv);
         const double a = fma(i0.x, r0.x, i0.y * r1.x), b = fma(i0.x, r0.y, i0.y * r1.y);
         const double c = fma(i1.x, r0.x, i1.y * r1.x), d = fma(i1.x, r0.y, i1.y * r1.y);
         r0.x = a; r0.y = b; r1.x = c; r1.y = d;
     }
-    st2(X, r0.x, r0.y);
-    st2(X + 2, r1.x, r1.y);
+    st2(s.lu + xi, r0.x, r0.y);
+    st2(s.lu1 + xi, r1.x, r1.y);
 }
 
 OPFG_HD void bwd_item(const GridDev& g, const PfSmem& s, int k) {
@@ -458,8 +460,8 @@ OPFG_HD void bwd_item(const GridDev& g, const PfSmem& s, int k) {
     const int pe = g.up_ptr[k + 1];
     for (int p = g.up_ptr[k]; p < pe; ++p) {
         const uint32_t id = g.up_pack[p];
-        const double* W = s.lu + 4 * (id & 0xffffu);
-        const D2 w0 = ld2(W), w1 = ld2(W + 2), xj = ld2(s.rhs + 2 * (id >> 16));
+        const int wi = 2 * (int)(id & 0xffffu);
+        const D2 w0 = ld2(s.lu + wi), w1 = ld2(s.lu1 + wi), xj = ld2(s.rhs + 2 * (id >> 16));
         x.x = fma(-w0.y, xj.y, fma(-w0.x, xj.x, x.x));
         x.y = fma(-w1.y, xj.y, fma(-w1.x, xj.x, x.y));
     }
@@ -548,9 +550,9 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
             if (jac) {
                 for (int e = cx.tid; e < g.nnz_y_nonref; e += T) jacobian_entry(g, s, yv, e);
                 for (int f = cx.tid; f < g.n_fill; f += T) {
-                    double* b = s.lu + 4 * g.fill_ids[f];
-                    st2(b, 0.0, 0.0);
-                    st2(b + 2, 0.0, 0.0);
+                    const int fi = 2 * g.fill_ids[f];
+                    st2(s.lu + fi, 0.0, 0.0);
+                    st2(s.lu1 + fi, 0.0, 0.0);
                 }
             }
             nrm = cx.block_max(bad ? NAN : part);
@@ -702,6 +704,11 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         return;
     }
 
+#ifdef OPFG_DEVICE_BUILD
+    // the row is read piecemeal through references below: pull it towards the SM now
+    for (int off = cx.tid * 128; off < g.n_state * 8; off += T * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S) + off));
+#endif
     for (int i = cx.tid; i < nb; i += T) {
         double sn, cs;
         sincos(va[i], &sn, &cs);
