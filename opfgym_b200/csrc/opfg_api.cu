@@ -258,11 +258,13 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     {
         const int4* src = reinterpret_cast<const int4*>(g.tab_base);
         int4* dst = reinterpret_cast<int4*>(sm);
-        for (int i = threadIdx.x; i < g.tab_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        for (int i = threadIdx.x; i < g.tab_staged_bytes / 16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
     const char* sbase = reinterpret_cast<const char*>(sm);
-#define OPFG_REBASE(field) g.field = reinterpret_cast<decltype(g.field)>(sbase + (reinterpret_cast<const char*>(g.field) - g.tab_base))
+#define OPFG_REBASE(field)                                                                        \
+    if (reinterpret_cast<const char*>(g.field) - g.tab_base < g.tab_staged_bytes)                  \
+        g.field = reinterpret_cast<decltype(g.field)>(sbase + (reinterpret_cast<const char*>(g.field) - g.tab_base))
     OPFG_REBASE(bus_of_int); OPFG_REBASE(type_int); OPFG_REBASE(vm0_int); OPFG_REBASE(va0_int);
     OPFG_REBASE(level_ptr); OPFG_REBASE(fill_ids); OPFG_REBASE(diag_mode);
     OPFG_REBASE(dp_ptr); OPFG_REBASE(dp_pack); OPFG_REBASE(off_ptr); OPFG_REBASE(off_hdr); OPFG_REBASE(op_pack);
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     OPFG_REBASE(qlim_bus); OPFG_REBASE(qlim_min); OPFG_REBASE(qlim_max);
 #undef OPFG_REBASE
     const int e_local = threadIdx.x / T;
-    double* mine = sm + g.tab_bytes / 8 + (size_t)e_local * env_doubles;
+    double* mine = sm + g.tab_staged_bytes / 8 + (size_t)e_local * env_doubles;
     Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 1 + e_local};
     for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
         env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
@@ -497,6 +499,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             d.dp_ptr = G->tab(s.dp_ptr); d.dp_pack = G->tab(dp);
             d.off_ptr = G->tab(s.off_ptr); d.off_hdr = G->tab(hdr); d.op_pack = G->tab(op);
             d.up_ptr = G->tab(s.up_ptr); d.up_pack = G->tab(upk);
+            d.tab_hot_bytes = (int)((G->tab_used + 15) & ~size_t(15));   // LU schedule ends here
             d.y_ptr = G->tab(s.y_ptr); d.y_diag = G->up(s.y_diag); d.y_meta = G->tab(ym);
         }
         d.yc_ptr = G->up(s.yc_ptr); d.yc_branch = G->up(s.yc_branch); d.yc_role = G->up(s.yc_role);
@@ -549,10 +552,16 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
             const size_t budget = 227 * 1024;
-            int E = (int)((budget - d.tab_bytes) / G->smem_pf);
-            E = std::min(E, std::min(15, 640 / T));   // named barriers 1..15; k_pf_multi is bounded to 640 threads
-            if (const char* ev = getenv("OPFG_ENVS_PER_CTA")) E = std::min(atoi(ev), std::min(15, 640 / T));
-            if (E < 2 || (size_t)d.tab_bytes * 3 > budget) E = 1;
+            const int cap = std::min(15, 640 / T);    // named barriers 1..15; k_pf_multi is bounded to 640 threads
+            d.tab_staged_bytes = d.tab_bytes;
+            int E = std::min((int)((budget - d.tab_bytes) / G->smem_pf), cap);
+            if (E < 2 || (size_t)d.tab_bytes * 3 > budget) {
+                // large grid: stage only the LU schedule; the Ybus / DC tables stay in global memory
+                d.tab_staged_bytes = d.tab_hot_bytes;
+                E = (size_t)d.tab_hot_bytes < budget ? std::min((int)((budget - d.tab_hot_bytes) / G->smem_pf), cap) : 1;
+            }
+            if (const char* ev = getenv("OPFG_ENVS_PER_CTA")) E = std::min(atoi(ev), cap);
+            if (E < 2) E = 1;
             G->envs_per_cta = E;
         }
         G->smem_score = score_smem_doubles(nb, nbr, T) * sizeof(double);
@@ -860,7 +869,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         }
         if (G->envs_per_cta > 1) {
             const int E = G->envs_per_cta;
-            const size_t smem_multi = G->d.tab_bytes + (size_t)E * smem;
+            const size_t smem_multi = G->d.tab_staged_bytes + (size_t)E * smem;
             static size_t attr_multi = 48 * 1024;
             if (smem_multi > attr_multi) {
                 cudaFuncSetAttribute(k_pf_multi<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);

@@ -103,6 +103,8 @@ struct GridDev {
     const int* obs_ref;
     const char* tab_base;              // contiguous arena holding the power-flow tables
     int tab_bytes;
+    int tab_hot_bytes;                 // prefix holding the LU schedule (the Ybus / DC tables follow)
+    int tab_staged_bytes;              // how much of the arena the multi-environment kernel stages
     const char* tab2_base;             // contiguous arena holding the scoring tables
     int tab2_bytes;
     int n_inputs;                      // S[:, n_inputs:] are the result cells written by kernel 5
