@@ -240,6 +240,25 @@ __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
                  B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
                  B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr);
 }
+// One warp per environment, W environments per CTA (lifts the 32-CTAs-per-SM limit on resident envs).
+__global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) {
+    const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= B.n_env) return;
+    Ctx<32> cx{(int)(threadIdx.x & 31), nullptr, 0};
+    env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
+                 B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
+                 B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr);
+}
+__global__ void __launch_bounds__(128) k_score_warps(GridDev g, OpfgBatch B, int env_doubles) {
+    extern __shared__ __align__(16) double sm[];
+    const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= B.n_env) return;
+    double* mine = sm + (size_t)(threadIdx.x >> 5) * env_doubles;
+    Ctx<32> cx{(int)(threadIdx.x & 31), mine + score_smem_doubles(g.nb, g.nbr, 32) - 4, 0};
+    env_score(g, cx, mine, B, env, (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+              B.state + env * (int64_t)g.n_state);
+}
 template <int T>
 __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
@@ -832,7 +851,10 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                      B->yval ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr,
                      B->bry ? B->bry + env * (int64_t)G->d.n_dyn * 8 : nullptr);
 #else
-    k_assemble<32><<<(unsigned)B->n_env, 32, 0, (cudaStream_t)stream>>>(G->d, *B);
+    {
+        static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
+        k_assemble_warps<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, 0, (cudaStream_t)stream>>>(G->d, *B);
+    }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("assemble launch: %s", cudaGetErrorString(e));
@@ -925,6 +947,16 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             const int64_t groups = (B->n_env + E - 1) / E;
             k_score_multi<TT><<<(unsigned)std::min<int64_t>(groups, n_sm), TT * E, smem_multi, (cudaStream_t)stream>>>(
                 G->d, *B, E, (int)(G->score_env_bytes / 8), G->score_consts, G->score_br_y, G->score_br_f, G->score_br_t);
+        } else if (TT == 32) {
+            static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
+            const size_t per_env = (smem + 15) & ~size_t(15);
+            static size_t attr_w = 48 * 1024;
+            if (per_env * warps > attr_w) {
+                cudaFuncSetAttribute(k_score_warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_env * warps));
+                attr_w = per_env * warps;
+            }
+            k_score_warps<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, per_env * warps, (cudaStream_t)stream>>>(
+                G->d, *B, (int)(per_env / 8));
         } else {
             k_score<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
         }

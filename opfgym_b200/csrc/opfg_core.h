@@ -638,11 +638,12 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
 
 // ------------------------------------------------------------- kernel 5: scoring
 struct ScoreSmem {
-    double *vr, *vi, *vm, *sf, *st, *red;
+    double *vr, *vi, *vm, *red;
 };
 
 OPFG_HHD size_t score_smem_doubles(int nb, int nbr, int threads) {
-    return 3 * (size_t)nb + 4 * (size_t)nbr + 2 * (size_t)(threads / 32 + 1);
+    (void)nbr;
+    return 3 * (size_t)nb + (nb & 1) + 2 * (size_t)(threads / 32 + 1);
 }
 
 OPFG_HD double pwl_cost(const GridDev& g, const double* S, int row, double v) {
@@ -672,7 +673,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     const int nb = g.nb, nbr = g.nbr, nc = g.n_con;
     ScoreSmem s;
     s.vr = smem; s.vi = s.vr + nb; s.vm = s.vi + nb;
-    s.sf = s.vm + nb; s.st = s.sf + 2 * (size_t)nbr; s.red = s.st + 2 * (size_t)nbr;
+    s.red = s.vm + nb + (nb & 1);
     // S: this environment's state row -- in global memory, or a shared-memory copy staged by the caller
     const double* vm = B.vm + env * (int64_t)nb;
     const double* va = B.va + env * (int64_t)nb;
@@ -736,7 +737,6 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         const double iti = y[4] * vfi + y[5] * vfr + y[6] * vti + y[7] * vtr;
         const double pf = (vfr * ifr + vfi * ifi) * base, qf = (vfi * ifr - vfr * ifi) * base;
         const double pt = (vtr * itr + vti * iti) * base, qt = (vti * itr - vtr * iti) * base;
-        s.sf[2 * l] = pf; s.sf[2 * l + 1] = qf; s.st[2 * l] = pt; s.st[2 * l + 1] = qt;
         const double lf = sqrt(pf * pf + qf * qf) * g.rate_f[l] / s.vm[f];
         const double lt = sqrt(pt * pt + qt * qt) * g.rate_t[l] / s.vm[t];
         const int slot = g.br_loading_slot[l];
@@ -787,7 +787,9 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         cnt = cx.block_sum(cnt);
         viol = worst ? cx.block_max(viol) : cx.block_sum(viol);
         viol *= g.con_autoscale[c];
-        const double pen = -(pow(viol, g.con_ppower[c]) * g.con_pfactor[c] + cnt * g.con_pcount[c]);
+        const double pp = g.con_ppower[c];
+        const double vp = pp == 1.0 ? viol : (pp == 2.0 ? viol * viol : pow(viol, pp));   // pow() is ~100 instructions
+        const double pen = -(vp * g.con_pfactor[c] + cnt * g.con_pcount[c]);
         pen_sum += pen;
         if (cnt > 0) all_valid = false;
         if (cx.tid == 0) {

@@ -22,23 +22,28 @@ def timeit(fn, n=20, w=5):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-name = sys.argv[1] if len(sys.argv) > 1 else "1-MV-semiurb--1-sw"
-B = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
-threads = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [32, 64, 128]
-orders = [int(x) for x in sys.argv[4].split(',')] if len(sys.argv) > 4 else [0]
-case = common.make_case(name)
-for o in orders:
-  for t in threads:
-    v = dict(ordering=o, threads_per_env=t)
-    try:
-        eng = Engine(case.program, B, **v)
-    except Exception as e:
-        print(v, 'ERR', e); continue
-    fill(case, eng, B)
-    eng.assemble()
-    ms = timeit(eng.pf_solve)
-    i = eng.info
-    ms2 = timeit(eng.score)
-    print(f"{name} {v} levels={i['n_levels']} blocks={i['n_blocks']} smem={i['smem_bytes_pf']} "
-          f"pf={ms:.3f} ms -> {B/ms*1e3:.3e} env/s  iters={eng.iterations.float().mean().item():.2f}  score={ms2:.3f} ms", flush=True)
-    eng.close(); del eng
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "1-MV-semiurb--1-sw"
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
+    threads = [int(x) for x in sys.argv[3].split(',')] if len(sys.argv) > 3 else [32, 64, 128]
+    orders = [int(x) for x in sys.argv[4].split(',')] if len(sys.argv) > 4 else [0]
+    case = common.make_case(name)
+    for o in orders:
+      for t in threads:
+        v = dict(ordering=o, threads_per_env=t)
+        try:
+            eng = Engine(case.program, B, **v)
+        except Exception as e:
+            print(v, 'ERR', e); continue
+        fill(case, eng, B)
+        eng.assemble()
+        ms = timeit(eng.pf_solve)
+        i = eng.info
+        ms2 = timeit(eng.score)
+        print(f"{name} {v} levels={i['n_levels']} blocks={i['n_blocks']} smem={i['smem_bytes_pf']} "
+              f"pf={ms:.3f} ms -> {B/ms*1e3:.3e} env/s  iters={eng.iterations.float().mean().item():.2f}  score={ms2:.3f} ms", flush=True)
+        eng.close(); del eng
+
+
+if __name__ == "__main__":
+    main()
