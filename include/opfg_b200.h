@@ -95,6 +95,8 @@ typedef struct {
     const int32_t* act_kind;         /* host [n_act] 0 continuous, 1 bool round, 2 integer round */
     const opfg_ref* act_clamp_lo;    /* host [n_act] or NULL: clamp after mapping (non-autoscale mode) */
     const opfg_ref* act_clamp_hi;
+    double act_diff_step;            /* > 0: incremental set-points (diff_action_step_size, opf_env.py:451-458):
+                                        sp = (2a-1)*step*(hi-lo) + previous*div                             */
     /* injections: Sbus[bus] += coef * (P + jQ) / base_mva, in list order per bus */
     int32_t n_inj;
     const int32_t* inj_bus;          /* host [n_inj] ppc bus                           */
@@ -145,7 +147,10 @@ typedef struct {
     double valid_reward, invalid_penalty, invalid_objective_share;
     /* observation gather */
     int32_t n_obs;
-    const opfg_ref* obs_ref;         /* host [n_obs]                                   */
+    const opfg_ref* obs_ref;         /* host [n_obs], or [obs_ptr[n_obs]] with obs_ptr  */
+    const int32_t* obs_ptr;          /* host [n_obs+1] or NULL: observation j is the SUM of
+                                        obs_ref[obs_ptr[j] .. obs_ptr[j+1]) (bus_wise_obs,
+                                        opf_env.py:535-536, 806-810)                    */
 } OpfgScoringDesc;
 
 /* per-environment branch parameters (tap_pos / in_service actions, N-1 contingencies): the listed
@@ -186,6 +191,10 @@ typedef struct {
     double* stats;           /* [OPFG_N_STATS] accumulated with atomics; caller zeroes        */
     double* yval;            /* [B, nnz_y, 2] per-env Ybus values, only with dynamic branches  */
     double* bry;             /* [B, n_dyn, 8] per-env admittances of the dynamic branches      */
+    const double* objective_offset; /* [B] or NULL: subtracted from the objective (diff_objective,
+                                       opf_env.py:497-498: -costs - initial_obj)                    */
+    int32_t absolute_actions;       /* != 0: kernel 1 ignores act_diff_step (reset applies the initial
+                                       action as an absolute set-point, opf_env.py:207)             */
 } OpfgBatch;
 
 enum { OPFG_STAT_N = 0, OPFG_STAT_CONVERGED = 1, OPFG_STAT_VALID = 2, OPFG_STAT_SUM_REWARD = 3,

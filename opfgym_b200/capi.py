@@ -41,7 +41,7 @@ class AssemblyDesc(C.Structure):
     _fields_ = [("n_state", C.c_int32), ("n_const", C.c_int32), ("consts", _dp),
                 ("n_act", C.c_int32), ("act_slot", _ip), ("act_lo", _ip), ("act_hi", _ip),
                 ("act_div", _ip), ("act_kind", _ip), ("act_clamp_lo", _ip),
-                ("act_clamp_hi", _ip),
+                ("act_clamp_hi", _ip), ("act_diff_step", C.c_double),
                 ("n_inj", C.c_int32), ("inj_bus", _ip), ("inj_p", _ip), ("inj_q", _ip),
                 ("inj_coef", _ip)]
 
@@ -66,7 +66,7 @@ class ScoringDesc(C.Structure):
                 ("penalty_factor", C.c_double), ("penalty_bias", C.c_double),
                 ("valid_reward", C.c_double), ("invalid_penalty", C.c_double),
                 ("invalid_objective_share", C.c_double),
-                ("n_obs", C.c_int32), ("obs_ref", _ip)]
+                ("n_obs", C.c_int32), ("obs_ref", _ip), ("obs_ptr", _ip)]
 
 
 class DynBranchDesc(C.Structure):
@@ -83,7 +83,8 @@ class Batch(C.Structure):
     _fields_ = [("n_env", C.c_int64)] + [(n, C.c_void_p) for n in
                 ("actions", "state", "sbus", "vm", "va", "converged", "iterations",
                  "reward", "objective", "penalty", "cost", "valids", "violations",
-                 "penalties", "obs_f32", "obs_f64", "stats", "yval", "bry")]
+                 "penalties", "obs_f32", "obs_f64", "stats", "yval", "bry", "objective_offset")] + [
+                ("absolute_actions", C.c_int32)]
 
 
 # every symbol include/opfg_b200.h declares: name -> (restype, argtypes)

@@ -82,6 +82,7 @@ class EnvProgram:
     sample_plan: dict = field(default_factory=dict)
     index_pos: dict = field(default_factory=dict)
     dyn_branches: dict | None = None     # OpfgDynBranchDesc arrays, if any branch cell is per-environment
+    obs_segments: list | None = None     # observation entries per obs key (after bus-wise grouping)
 
 
 def _positions(net, table: str, idxs) -> np.ndarray:
@@ -131,13 +132,15 @@ class Compiler:
     def compile(self, act_keys, obs_keys, state_keys, constraints: list[Constraint],
                 reward_function: RewardFunction, extra_dynamic=(),
                 autoscale_actions: bool = True, pwl_price_columns=None,
-                extra_results=(), prune_unused: bool = False) -> EnvProgram:
+                extra_results=(), prune_unused: bool = False,
+                diff_action_step_size: float | None = None, bus_wise_obs: bool = False) -> EnvProgram:
         if prune_unused and extra_dynamic:
             # dry run: find out which hook-written columns any kernel table actually reads
             # (e.g. max_p_mw / min_p_mw exist in the reference only for the pandapower OPF)
             probe = Compiler(self.net, self.builder)
             probe.compile(act_keys, obs_keys, state_keys, constraints, reward_function, extra_dynamic,
-                          autoscale_actions, pwl_price_columns, extra_results, prune_unused=False)
+                          autoscale_actions, pwl_price_columns, extra_results, prune_unused=False,
+                          diff_action_step_size=diff_action_step_size, bus_wise_obs=bus_wise_obs)
             extra_dynamic = [tc for tc in extra_dynamic if tuple(tc) in probe.referenced]
         net, lay, ppc = self.net, self.layout, self.ppc
         for table, column, _ in list(state_keys) + list(act_keys):
@@ -273,6 +276,7 @@ class Compiler:
             act_kind=np.asarray(a_kind, _I32),
             act_clamp_lo=np.asarray(a_clo, _I32) if a_clo else None,
             act_clamp_hi=np.asarray(a_chi, _I32) if a_chi else None,
+            act_diff_step=float(diff_action_step_size or 0.0),
             inj_bus=np.asarray(inj_bus, _I32), inj_p=np.asarray(inj_p, _I32),
             inj_q=np.asarray(inj_q, _I32), inj_coef=np.asarray(inj_c, _I32))
 
@@ -335,10 +339,22 @@ class Compiler:
                     pwl_seg.append(self.consts.ref(price))
 
         # ---- observation gather (opf_env.py:532-549) --------------------------
-        obs_ref = []
+        obs_ref, obs_ptr, obs_segments = [], [0], []
         for table, column, idxs in obs_keys:
             base = table[len(RES_PREFIX):] if _is_res(table) else table
+            if bus_wise_obs and table == "load":
+                # loads at the same bus are observed as one sum, groups sorted by bus
+                # (get_bus_aggregated_obs, opf_env.py:806-810 -- note its .iloc[idxs])
+                buses = net.load.bus.to_numpy()[np.asarray(idxs, int)]
+                for bus in sorted(set(buses.tolist())):
+                    for p in np.asarray(idxs, int)[buses == bus]:
+                        obs_ref.append(self.value_ref(table, column, int(p)))
+                    obs_ptr.append(len(obs_ref))
+                obs_segments.append(len(set(buses.tolist())))
+                continue
+            obs_segments.append(len(idxs))
             for p in _positions(net, base, idxs):
+                obs_ptr.append(len(obs_ref) + 1)
                 if _is_res(table):
                     r, m = self._result_ref(table, column, p)
                     if m != 1.0:
@@ -394,11 +410,13 @@ class Compiler:
             poly_coef=np.asarray(poly_cf, _I32),
             n_pwl=len(pw), n_pwl_seg=n_seg, pwl_v=np.asarray(pwl_v, _I32),
             pwl_v_mul=np.asarray(pwl_vm, float), pwl_seg=np.asarray(pwl_seg, _I32),
-            reward=rp, n_obs=len(obs_ref), obs_ref=np.asarray(obs_ref, _I32))
+            reward=rp, n_obs=len(obs_ptr) - 1, obs_ref=np.asarray(obs_ref, _I32),
+            obs_ptr=np.asarray(obs_ptr, _I32) if len(obs_ref) != len(obs_ptr) - 1 else None)
 
         return EnvProgram(ppc=ppc, layout=lay, consts=np.asarray(self.consts.values, float),
                           initial_state=init, assembly=assembly, scoring=scoring,
-                          n_act=n_act, n_obs=len(obs_ref), constraints=list(constraints),
+                          n_act=n_act, n_obs=len(obs_ptr) - 1, constraints=list(constraints),
+                          obs_segments=obs_segments,
                           act_low_refs=np.asarray(a_lo, _I32), act_high_refs=np.asarray(a_hi, _I32),
                           dyn_branches=dyn)
 
@@ -450,7 +468,8 @@ def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_l
                            act_slot=iptr(a["act_slot"]), act_lo=iptr(a["act_lo"]),
                            act_hi=iptr(a["act_hi"]), act_div=iptr(a["act_div"]),
                            act_kind=iptr(a["act_kind"]), act_clamp_lo=iptr(a["act_clamp_lo"]),
-                           act_clamp_hi=iptr(a["act_clamp_hi"]), n_inj=len(a["inj_bus"]),
+                           act_clamp_hi=iptr(a["act_clamp_hi"]), act_diff_step=a["act_diff_step"],
+                           n_inj=len(a["inj_bus"]),
                            inj_bus=iptr(a["inj_bus"]), inj_p=iptr(a["inj_p"]),
                            inj_q=iptr(a["inj_q"]), inj_coef=iptr(a["inj_coef"]))
     s = program.scoring
@@ -475,7 +494,7 @@ def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_l
         objective_bias=r["objective_bias"], penalty_factor=r["penalty_factor"],
         penalty_bias=r["penalty_bias"], valid_reward=r["valid_reward"],
         invalid_penalty=r["invalid_penalty"], invalid_objective_share=r["invalid_objective_share"],
-        n_obs=s["n_obs"], obs_ref=iptr(s["obs_ref"]))
+        n_obs=s["n_obs"], obs_ref=iptr(s["obs_ref"]), obs_ptr=iptr(s["obs_ptr"]))
     dd = None
     if program.dyn_branches is not None:
         d = program.dyn_branches

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                  B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
                  B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
-                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr);
+                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0);
 }
 // One warp per environment, W environments per CTA (lifts the 32-CTAs-per-SM limit on resident envs).
 __global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) {
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) 
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                  B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
                  B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
-                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr);
+                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0);
 }
 __global__ void __launch_bounds__(128) k_score_warps(GridDev g, OpfgBatch B, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
@@ -315,7 +315,7 @@ __global__ void k_observe(GridDev g, OpfgBatch B) {
     if (idx >= B.n_env * g.n_obs) return;
     const int64_t env = idx / g.n_obs;
     const int j = (int)(idx % g.n_obs);
-    const double v = ref_val(g, B.state + env * (int64_t)g.n_state, g.obs_ref[j]);
+    const double v = obs_value(g, B.state + env * (int64_t)g.n_state, j);
     if (B.obs_f32) B.obs_f32[idx] = (float)v;
     if (B.obs_f64) B.obs_f64[idx] = v;
 }
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(1024) k_score_multi(GridDev g, OpfgBatch B, in
     OPFG_REBASE2(con_ppower); OPFG_REBASE2(con_pcount);
     OPFG_REBASE2(poly_p); OPFG_REBASE2(poly_q); OPFG_REBASE2(poly_p_mul); OPFG_REBASE2(poly_q_mul); OPFG_REBASE2(poly_coef);
     OPFG_REBASE2(pwl_v); OPFG_REBASE2(pwl_v_mul); OPFG_REBASE2(pwl_seg); OPFG_REBASE2(obs_ref);
+    if (g.obs_ptr) OPFG_REBASE2(obs_ptr);
     OPFG_REBASE2(consts); OPFG_REBASE2(br_y); OPFG_REBASE2(br_f); OPFG_REBASE2(br_t);
 #undef OPFG_REBASE2
     const int e_local = threadIdx.x / T, tid = threadIdx.x % T;
@@ -611,6 +612,7 @@ int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
     try {
         GridDev& d = G->d;
         d.n_state = a->n_state; d.n_const = a->n_const; d.n_act = a->n_act; d.n_inj = a->n_inj;
+        d.act_diff_step = a->act_diff_step;
         d.consts = G->up(a->consts, a->n_const);
         G->consts_host.assign(a->consts, a->consts + a->n_const);
         auto check_ref = [&](const int* r, int n, const char* what) {
@@ -721,7 +723,8 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
         d.valid_reward = sc->valid_reward; d.invalid_penalty = sc->invalid_penalty;
         d.invalid_obj_share = sc->invalid_objective_share;
         d.n_obs = sc->n_obs;
-        d.obs_ref = G->tab2(sc->obs_ref, sc->n_obs);
+        d.obs_ref = G->tab2(sc->obs_ref, sc->obs_ptr ? sc->obs_ptr[sc->n_obs] : sc->n_obs);
+        d.obs_ptr = sc->obs_ptr ? G->tab2(sc->obs_ptr, sc->n_obs + 1) : nullptr;
         // copies of the grid tables that the branch-flow part of kernel 5 reads
         G->score_consts = G->tab2(G->consts_host);
         G->score_br_y = G->tab2((const double*)d.br_y, 8 * (size_t)nbr, true);
@@ -849,7 +852,7 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         env_assemble(G->d, cx, B->actions ? B->actions + env * G->d.n_act : nullptr,
                      B->state + env * (int64_t)G->d.n_state, B->sbus ? B->sbus + env * (int64_t)G->d.nb * 2 : nullptr,
                      B->yval ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr,
-                     B->bry ? B->bry + env * (int64_t)G->d.n_dyn * 8 : nullptr);
+                     B->bry ? B->bry + env * (int64_t)G->d.n_dyn * 8 : nullptr, B->absolute_actions != 0);
 #else
     {
         static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
@@ -977,7 +980,7 @@ int opfg_observe(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     (void)stream;
     for (int64_t env = 0; env < B->n_env; ++env)
         for (int j = 0; j < G->d.n_obs; ++j) {
-            const double v = ref_val(G->d, B->state + env * (int64_t)G->d.n_state, G->d.obs_ref[j]);
+            const double v = obs_value(G->d, B->state + env * (int64_t)G->d.n_state, j);
             if (B->obs_f32) B->obs_f32[env * G->d.n_obs + j] = (float)v;
             if (B->obs_f64) B->obs_f64[env * G->d.n_obs + j] = v;
         }

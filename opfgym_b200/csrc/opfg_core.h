@@ -76,6 +76,7 @@ struct GridDev {
     const double* dc_rhs0;             // [n]
     // ---- assembly (kernel 1) ----
     int n_state, n_const, n_act, n_inj;
+    double act_diff_step;
     const double* consts;
     const int* act_slot;
     const int *act_lo, *act_hi, *act_div, *act_kind, *act_clamp_lo, *act_clamp_hi;
@@ -101,6 +102,7 @@ struct GridDev {
     double valid_reward, invalid_penalty, invalid_obj_share;
     int n_obs;
     const int* obs_ref;
+    const int* obs_ptr;      // nullptr: one ref per observation
     const char* tab_base;              // contiguous arena holding the power-flow tables
     int tab_bytes;
     int tab_hot_bytes;                 // prefix holding the LU schedule (the Ybus / DC tables follow)
@@ -233,16 +235,29 @@ OPFG_HD void ybus_entry(const GridDev& g, const double* br_y, int e, double* out
     out[0] = re; out[1] = im;
 }
 
+// observation j: one cell, or the sum of a group of cells (bus_wise_obs, opf_env.py:806-810)
+OPFG_HD double obs_value(const GridDev& g, const double* S, int j) {
+    if (!g.obs_ptr) return ref_val(g, S, g.obs_ref[j]);
+    double v = 0.0;
+    for (int k = g.obs_ptr[j]; k < g.obs_ptr[j + 1]; ++k) v += ref_val(g, S, g.obs_ref[k]);
+    return v;
+}
+
 // --------------------------------------- kernel 1b: actions -> set-points -> Sbus
 template <class C>
 OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, double* S, double* sbus,
-                          double* yval_env = nullptr, double* bry_env = nullptr) {
+                          double* yval_env = nullptr, double* bry_env = nullptr, bool absolute = false) {
     const int T = cx.nthreads();
     for (int j = cx.tid; act != nullptr && j < g.n_act; j += T) {
         double a = act[j];
         a = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);               // opf_env.py:429
         const double lo = ref_val(g, S, g.act_lo[j]), hi = ref_val(g, S, g.act_hi[j]);
         double sp = a * (hi - lo) + lo;                           // :461
+        if (g.act_diff_step > 0.0 && !absolute) {                 // :451-458 incremental set-points
+            const double prev = S[g.act_slot[j]] * ref_val(g, S, g.act_div[j]);
+            sp = (2.0 * a - 1.0) * g.act_diff_step * (hi - lo) + prev;
+            if (!g.act_clamp_lo) { if (sp > hi) sp = hi; if (sp < lo) sp = lo; }   // :464-470 (min_/max_ = lo/hi)
+        }
         if (g.act_clamp_lo) {                                     // :464-470
             const double cl = ref_val(g, S, g.act_clamp_lo[j]), ch = ref_val(g, S, g.act_clamp_hi[j]);
             if (sp > ch) sp = ch;
@@ -814,7 +829,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     }
     for (int r = cx.tid; r < g.n_pwl; r += T)
         csum += pwl_cost(g, S, r, ref_val(g, S, g.pwl_v[r]) * g.pwl_v_mul[r]);
-    const double objective = -cx.block_sum(csum);
+    const double objective = -cx.block_sum(csum) - (B.objective_offset ? B.objective_offset[env] : 0.0);
     // reward (opfgym/reward.py:61-98 and subclasses)
     if (cx.tid == 0) {
         double obj = objective, pen = pen_sum;
@@ -856,7 +871,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     }
     // observation gather (opf_env.py:532-549)
     for (int j = cx.tid; j < g.n_obs; j += T) {
-        const double v = ref_val(g, S, g.obs_ref[j]);
+        const double v = obs_value(g, S, j);
         if (B.obs_f32) B.obs_f32[env * (int64_t)g.n_obs + j] = (float)v;
         if (B.obs_f64) B.obs_f64[env * (int64_t)g.n_obs + j] = v;
     }

@@ -62,6 +62,7 @@ class Engine:
         self.obs_final = self._zeros((B, max(program.n_obs, 1)), obs_dtype)
         self.stats = self._zeros((capi.N_STATS,), "float64")
         self.n_constraints = nc
+        self.objective_offset = None     # set by enable_objective_offset() (diff_objective)
         self.yval = self.bry = None
         if dd is not None:     # per-environment Ybus values / branch admittances (kernel 1 output)
             self.yval = self._zeros((B, self.info["nnz_y"], 2), "float64")
@@ -90,8 +91,17 @@ class Engine:
         self.batch_setpoints = capi.Batch.from_buffer_copy(self.batch)
         self.batch_setpoints.sbus = None
         self.batch_setpoints.actions = self._ptr(self.actions_reset)
+        self.batch_setpoints.absolute_actions = 1
         self._states = [self.state]
         self.cur = 0
+
+    def enable_objective_offset(self):
+        """[B] buffer subtracted from the objective in kernel 5 (``diff_objective``)."""
+        if self.objective_offset is None:
+            self.objective_offset = self._zeros((self.num_envs,), "float64")
+            for b in (self.batch, self.batch_final, self.batch_setpoints):
+                b.objective_offset = self._ptr(self.objective_offset)
+        return self.objective_offset
 
     def enable_double_buffer(self):
         """Second state matrix: the next episode can be sampled while the current one is solved."""
@@ -143,15 +153,19 @@ class Engine:
         capi.check(self.lib, self.lib.opfg_philox_uniform(
             seed, first_env, stream_id, out.shape[0], out.shape[1], self._ptr(out), self._stream()))
 
-    def assemble(self, apply_actions: bool = True, scatter_sbus: bool = True):
+    def assemble(self, apply_actions: bool = True, scatter_sbus: bool = True, absolute: bool = False):
         """Kernel 1.  ``apply_actions=False`` only re-scatters Sbus from the current cells;
-        ``scatter_sbus=False`` only writes the set-points."""
+        ``scatter_sbus=False`` only writes the set-points (from ``actions_reset``, always as
+        absolute set-points); ``absolute`` ignores a configured incremental step size."""
         batch = self.batch
         if not apply_actions:
             batch = capi.Batch.from_buffer_copy(self.batch)
             batch.actions = None
         elif not scatter_sbus:
             batch = self.batch_setpoints
+        elif absolute:
+            batch = capi.Batch.from_buffer_copy(self.batch)
+            batch.absolute_actions = 1
         capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(batch), self._stream()))
 
     def pf_solve(self):

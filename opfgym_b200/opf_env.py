@@ -77,10 +77,6 @@ class BatchedOpfEnv:
         unknown = set(kwargs) - _SPLIT_KWARGS
         if unknown:
             raise TypeError(f"unknown keyword arguments: {sorted(unknown)}")
-        for flag, name in ((bus_wise_obs, "bus_wise_obs"), (diff_objective, "diff_objective"),
-                           (diff_action_step_size, "diff_action_step_size")):
-            if flag:
-                raise NotImplementedError(f"{name} is listed under SURVEY.md §8(f) 'next'")
         if add_time_obs:
             raise NotImplementedError("add_time_obs raises TypeError in the reference itself "
                                       "(opf_env.py:545-546 vs time_observation.py:4)")
@@ -128,8 +124,9 @@ class BatchedOpfEnv:
                 if name in add_res_obs:
                     self.obs_keys.extend(extra[name])
         self.add_mean_obs = add_mean_obs
+        self.bus_wise_obs = bool(bus_wise_obs)
         self.observation_space_single = get_obs_and_state_space(
-            net, self.obs_keys, False, add_mean_obs, seed=seed)
+            net, self.obs_keys, False, add_mean_obs, seed=seed, bus_wise_obs=bus_wise_obs)
         self.state_space = get_obs_and_state_space(net, self.state_keys, seed=seed)
         n_actions = sum(len(idxs) for _, _, idxs in self.act_keys)
         self.single_action_space = Box(0, 1, shape=(n_actions,), seed=seed)
@@ -142,6 +139,10 @@ class BatchedOpfEnv:
         self.initial_action = initial_action
         self.steps_per_episode = steps_per_episode
         self.pf_for_obs = any("res_" in unit_type for unit_type, _, _ in self.obs_keys)
+        self.diff_objective = bool(diff_objective)
+        self.diff_action_step_size = diff_action_step_size
+        if self.diff_objective:
+            self.pf_for_obs = True      # opf_env.py:150-153: the initial objective needs a power flow
         self.test_steps, self.validation_steps, self.train_steps = define_test_train_split(**kwargs)
 
         if custom_constraints is None:
@@ -163,7 +164,9 @@ class BatchedOpfEnv:
                                   pwl_price_columns=pwl_price_columns,
                                   # hook-written columns that no kernel reads (they only feed the
                                   # reference's pandapower-OPF baseline) are not materialised
-                                  prune_unused=not keep_all_columns)
+                                  prune_unused=not keep_all_columns,
+                                  diff_action_step_size=diff_action_step_size,
+                                  bus_wise_obs=bus_wise_obs)
         self._engine_args = dict(device=device, tolerance_mva=tolerance_mva,
                                  max_iteration=max_iteration, obs_dtype=obs_dtype,
                                  **(engine_kwargs or {}))
@@ -434,12 +437,16 @@ class BatchedOpfEnv:
             self.engine.actions_reset.fill_(0.5)
         if self.pf_for_obs:
             self.engine.actions.copy_(self.engine.actions_reset)
-        self.engine.assemble(scatter_sbus=self.pf_for_obs)
+        self.engine.assemble(scatter_sbus=self.pf_for_obs, absolute=True)   # opf_env.py:207
         if self.pf_for_obs:
             # the reference re-samples envs whose reset power flow fails (opf_env.py:209-214);
             # here such envs simply start with a NaN observation and are flagged in `converged`
+            if self.diff_objective:
+                self.engine.enable_objective_offset().zero_()
             self.engine.pf_solve()
             self.engine.score()
+            if self.diff_objective:      # opf_env.py:216: initial_obj = objective of the reset state
+                self.engine.objective_offset.copy_(self.engine.objective)
             self.power_flow_available = True
         else:
             self.engine.observe()
@@ -448,8 +455,7 @@ class BatchedOpfEnv:
         obs = self.engine.obs_final if final else self.engine.obs
         if self.add_mean_obs:
             parts, k = [], 0
-            for _, _, idxs in self.obs_keys:
-                n = len(idxs)
+            for n in self.program.obs_segments:
                 if n > 1:
                     parts.append(obs[:, k:k + n].mean(dim=1, keepdim=True))
                 k += n

@@ -42,7 +42,8 @@ def batch_space(space: Box, n: int) -> Box:
     return Box(np.tile(space.low, (n, 1)), np.tile(space.high, (n, 1)), dtype=space.dtype)
 
 
-def get_obs_and_state_space(net, keys, add_time_obs=False, add_mean_obs=False, seed=None) -> Box:
+def get_obs_and_state_space(net, keys, add_time_obs=False, add_mean_obs=False, seed=None,
+                            bus_wise_obs=False) -> Box:
     lows, highs = [], []
     if add_time_obs:
         lows.append(-np.ones(6))
@@ -73,6 +74,11 @@ def get_obs_and_state_space(net, keys, add_time_obs=False, add_mean_obs=False, s
         if "min" not in column and "max" not in column and "scaling" in table.columns:
             scal = table.scaling.loc[idxs].to_numpy(float)
             lo, hi = lo / scal, hi / scal
+        if bus_wise_obs and unit_type == "load":       # opf_env.py:780-784
+            at = table.bus.loc[idxs].to_numpy()
+            buses = sorted(set(at.tolist()))
+            lo = np.array([lo[at == b].sum() for b in buses])
+            hi = np.array([hi[at == b].sum() for b in buses])
         if n > 0:
             lows.append(lo)
             highs.append(hi)

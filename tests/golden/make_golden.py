@@ -10,7 +10,7 @@ CPU oracle (oracle/pf.py).  Every other line that runs -- env construction,
 records, per sample: every per-environment net column after ``reset``, the
 action, and the outputs of ``step``.
 
-Run from the repo root:  python tests/golden/make_golden.py
+Run from the repo root:  python tests/golden/make_golden.py [case names]
 (needs /root/reference; the committed .npz files are what the tests read).
 """
 import os
@@ -52,6 +52,9 @@ def cases(ref_envs):
             constraint_params=dict(only_worst_case_violations=True, penalty_power=2.0,
                                    penalty_factor=1.5, violation_count_penalty=0.1),
             voltage_band=0.02, max_loading=25)),
+        # incremental actions, objective relative to the reset state, loads observed per bus
+        "VoltageControl_diff": (ref_envs.VoltageControl, dict(
+            diff_objective=True, diff_action_step_size=0.2, bus_wise_obs=True)),
         "EcoDispatch_replacement": (ref_envs.EcoDispatch, dict(
             reward_function="replacement",
             reward_function_params=dict(valid_reward=0.5, penalty_weight=0.3),
@@ -64,12 +67,19 @@ def main():
     _ref_stubs.install(profile_steps=PROFILE_STEPS)
     import opfgym.envs as ref_envs
 
+    # pandas >= 3 hands out read-only `.values`; opf_env.py:453-455 scales that array in place
+    # (a private copy under the pandas versions the reference targets) -- restore that behaviour
+    import pandas as pd
+    pd.Series.values = property(lambda self: self.to_numpy().copy())
+    only = set(sys.argv[1:])
     for name, (cls, kw) in cases(ref_envs).items():
+        if only and name not in only:
+            continue
         env = cls(train_data="full_uniform", test_data="full_uniform", seed=7, **kw)
         tables = ("load", "sgen", "storage", "gen", "ext_grid", "poly_cost", "pwl_cost")
         out = {k: [] for k in ("action", "obs", "reward", "valids", "violations", "penalties",
                                "cost", "objective", "vm_pu", "va_degree", "line_loading",
-                               "trafo_loading", "ext_p", "ext_q", "reset_obs")}
+                               "trafo_loading", "ext_p", "ext_q", "reset_obs", "initial_obj")}
         cols = {}
         pre = {}
         original_apply = env._apply_actions
@@ -96,6 +106,7 @@ def main():
                         cols.setdefault((t, c), []).append(pts.reshape(len(df), -1))
                     elif df[c].dtype.kind in "fiub":
                         cols.setdefault((t, c), []).append(df[c].to_numpy(float).copy())
+            out["initial_obj"].append(np.sum(getattr(env, "initial_obj", 0.0)))
             a = env.action_space.sample()
             if k % 4 == 3:
                 a = a * 1.3 - 0.15          # exercise the [0,1] clipping

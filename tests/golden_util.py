@@ -69,6 +69,8 @@ def replay_step(env, z):
     (no sampling), return the engine outputs as numpy."""
     inject(env, z)
     e = env.engine
+    if getattr(env, "diff_objective", False):
+        e.enable_objective_offset().copy_(env.xp.as_tensor(z["out/initial_obj"], device=env.device))
     e.actions.copy_(env.xp.as_tensor(z["out/action"], device=env.device))
     e.step()
     if env.device.type == "cuda":
@@ -90,7 +92,8 @@ def assert_matches(got, z, reward_rtol=1e-6):
     np.testing.assert_allclose(got["line_loading"], z["out/line_loading"], rtol=0, atol=1e-4)
     np.testing.assert_allclose(got["trafo_loading"], z["out/trafo_loading"], rtol=0, atol=1e-4)
     np.testing.assert_allclose(got["reward"], z["out/reward"], rtol=reward_rtol, atol=1e-9)
-    np.testing.assert_allclose(got["objective"], z["out/objective"], rtol=reward_rtol, atol=1e-9)
+    initial = z["out/initial_obj"] if "out/initial_obj" in z.files else 0.0   # diff_objective cases
+    np.testing.assert_allclose(got["objective"], z["out/objective"] - initial, rtol=reward_rtol, atol=1e-9)
     np.testing.assert_allclose(got["cost"], z["out/cost"], rtol=reward_rtol, atol=1e-9)
     np.testing.assert_allclose(got["violations"], z["out/violations"], rtol=1e-6, atol=1e-9)
     np.testing.assert_allclose(got["penalties"], z["out/penalties"], rtol=1e-6, atol=1e-9)

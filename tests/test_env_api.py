@@ -232,3 +232,75 @@ def test_normal_and_mixed_sampling():
     nan_bounds = torch.isnan(mixed.col("storage", "max_q_mvar")).any(dim=1)
     obs, reward, term, _, info = mixed.step(torch.rand(4096, 14, dtype=torch.float64))
     assert info["converged"][~nan_bounds].all() and info["converged"].float().mean() > 0.7
+
+
+def test_diff_objective_and_incremental_actions():
+    """opf_env.py:150-153, 216, 497-498 (diff_objective) and :451-470 (diff_action_step_size)."""
+    plain = make(n=6, add_res_obs=("voltage_magnitude",))
+    diff = make(n=6, add_res_obs=("voltage_magnitude",), diff_objective=True)
+    plain.reset(seed=5)
+    diff.reset(seed=5)
+    initial = plain.get_objective()                       # objective of the reset state (centre action)
+    assert torch.allclose(diff.engine.objective_offset, initial)
+    act = torch.rand(6, 14, dtype=torch.float64)
+    _, r_plain, _, _, _ = plain.step(act)
+    _, r_diff, _, _, _ = diff.step(act)
+    w = plain.reward_function.penalty_weight
+    assert torch.allclose(r_plain - r_diff, initial * (1 - w), atol=1e-12)
+    # incremental set-points: a = 0.5 keeps the set-point, a = 1 moves it by step*(max-min), clamped
+    inc = make(n=4, diff_action_step_size=0.25)
+    inc.reset(seed=5)
+    pos = inc.positions("sgen", inc.act_keys[0][2])
+    q0 = inc.col("sgen", "q_mvar")[:, pos].clone()
+    lo, hi = inc.col("sgen", "min_q_mvar")[:, pos].clone(), inc.col("sgen", "max_q_mvar")[:, pos].clone()
+    scal = inc.static("sgen", "scaling")[pos]
+    assert torch.allclose(q0 * scal, (lo + hi) / 2, atol=1e-12)   # reset: absolute centre action (:207)
+    a = torch.full((4, 14), 0.5, dtype=torch.float64)
+    inc._apply_actions(a)
+    assert torch.allclose(inc.col("sgen", "q_mvar")[:, pos], q0)
+    a[:] = 1.0
+    inc._apply_actions(a)
+    want = torch.minimum(0.25 * (hi - lo) + q0 * scal, hi) / scal
+    assert torch.allclose(inc.col("sgen", "q_mvar")[:, pos], want, atol=1e-12)
+    for _ in range(5):
+        inc._apply_actions(a)
+    assert torch.allclose(inc.col("sgen", "q_mvar")[:, pos] * scal, hi, atol=1e-12)   # clamped at max
+
+
+def test_bus_wise_obs():
+    """opf_env.py:535-536, 780-784, 806-810: loads at one bus are observed as their sum."""
+    class Shared(envs.VoltageControl):
+        def _define_opf(self, *a, **kw):
+            net, profiles = super()._define_opf(*a, **kw)
+            net.load.loc[net.load.index[:30], "bus"] = np.repeat(net.load.bus.to_numpy()[:10], 3)
+            return net, profiles
+
+    plain = make(Shared, n=5)
+    agg = make(Shared, n=5, bus_wise_obs=True)
+    o_plain, _ = plain.reset(seed=9)
+    o_agg, _ = agg.reset(seed=9)
+    net = plain.net
+    buses = net.load.bus.to_numpy()
+    groups = sorted(set(buses.tolist()))
+    assert len(groups) < len(buses), "stand-in grid needs buses with several loads for this test"
+    k_plain = k_agg = 0
+    for (table, column, idxs) in plain.obs_keys:
+        n = len(idxs)
+        if table == "load":
+            at = buses[np.asarray(idxs, int)]
+            part = o_plain[:, k_plain:k_plain + n]
+            want = torch.stack([part[:, torch.as_tensor(at == b)].sum(dim=1) for b in groups], dim=1)
+            got = o_agg[:, k_agg:k_agg + len(groups)]
+            assert torch.allclose(got.double(), want.double(), rtol=1e-6, atol=1e-7)
+            k_agg += len(groups)
+        else:
+            assert torch.equal(o_agg[:, k_agg:k_agg + n], o_plain[:, k_plain:k_plain + n])
+            k_agg += n
+        k_plain += n
+    assert o_agg.shape[1] == k_agg == agg.single_observation_space.shape[0]
+    lo, hi = agg.single_observation_space.low, agg.single_observation_space.high
+    assert (lo <= hi).all()
+    # the means appended by add_mean_obs follow the grouped layout
+    both = make(Shared, n=3, bus_wise_obs=True, add_mean_obs=True)
+    o, _ = both.reset(seed=9)
+    assert o.shape[1] == both.single_observation_space.shape[0]
