@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // the schedule / Ybus tables (their reads are on the critical path of every level); each environment
 // group synchronises on its own named barrier and walks through its share of the batch.
 template <int T>
-__global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
+__global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles, int stages) {
     extern __shared__ __align__(16) double sm[];
     {
         const int4* src = reinterpret_cast<const int4*>(g.tab_base);
@@ -294,11 +294,24 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     const int e_local = threadIdx.x / T;
     double* mine = sm + g.tab_staged_bytes / 8 + (size_t)e_local * env_doubles;
     Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 1 + e_local};
+    // stages: bit 0 = kernel 1 in front, bit 1 = kernel 5 behind (opfg_step's fused form: the
+    // HBM-latency-bound row work of one environment overlaps the shared-memory-bound elimination of
+    // the other E-1 environments of the CTA instead of running as separate launches)
     for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
-        env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
-                     (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr, B.vm + env * (int64_t)g.nb,
-                     B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
+        double* yv = B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr;
+        if (stages & 1) {
+            env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
+                         B.sbus + env * (int64_t)g.nb * 2, yv,
+                         B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0);
+            cx.sync();
+        }
+        env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2, g.n_dyn > 0 ? yv : nullptr,
+                     B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
         cx.sync();
+        if (stages & 2) {
+            env_score(g, cx, mine, B, env, g.n_dyn > 0 ? yv : nullptr, B.state + env * (int64_t)g.n_state);
+            cx.sync();
+        }
     }
 }
 template <int T>
@@ -865,7 +878,11 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     return 0;
 }
 
-int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
+static int pf_launch(const OpfgGrid* G, const OpfgBatch* B, void* stream, int stages);
+
+int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) { return pf_launch(G, B, stream, 0); }
+
+static int pf_launch(const OpfgGrid* G, const OpfgBatch* B, void* stream, int stages) {
     if (!G || !B) return fail("null argument");
     if (!B->sbus || !B->vm || !B->va || !B->converged || !B->iterations) return fail("opfg_pf_solve needs sbus, vm, va, converged, iterations");
     if (B->n_env <= 0) return 0;
@@ -904,7 +921,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
             const int64_t groups = (B->n_env + E - 1) / E;
             const unsigned grid = (unsigned)std::min<int64_t>(groups, n_sm);
-            k_pf_multi<TT><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8));
+            k_pf_multi<TT><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8), stages);
         } else {
             k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
         }
@@ -1065,6 +1082,16 @@ int opfg_fp64_probe(int32_t n_blocks, int32_t iters, double* out, void* stream) 
 }
 
 int opfg_step(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
+#ifndef OPFG_HOSTSIM
+    // fused form: kernels 1 and/or 5 inside the persistent power-flow kernel (OPFG_FUSED_STEP bit mask)
+    static const int fused = getenv("OPFG_FUSED_STEP") ? atoi(getenv("OPFG_FUSED_STEP")) : 0;
+    if (fused && G && B && G->envs_per_cta > 1 && G->has_scoring && G->has_assembly && B->state && B->sbus) {
+        int rc = 0;
+        if (!(fused & 1) && (rc = opfg_assemble(G, B, stream))) return rc;
+        if ((rc = pf_launch(G, B, stream, fused & 3))) return rc;
+        return (fused & 2) ? 0 : opfg_score(G, B, stream);
+    }
+#endif
     int rc = opfg_assemble(G, B, stream);
     if (rc) return rc;
     rc = opfg_pf_solve(G, B, stream);

@@ -193,6 +193,7 @@ class BatchedOpfEnv:
             self._side = self.xp.cuda.Stream(device=self.device)
             self._main_done = self.xp.cuda.Event()
             self._side_done = self.xp.cuda.Event()
+            self._side_kernels = self.xp.cuda.Event()
         self.test = False
         self.power_flow_available = False
 
@@ -503,6 +504,89 @@ class BatchedOpfEnv:
         else:
             self._begin_episode()
         return self._obs_out(), reward, terminated, truncated, info
+
+    # ------------------------------------------------------------- host-buffer (numpy) step
+    def enable_host_io(self):
+        """Pinned host buffers for :meth:`step_host` (the reference's numpy-in / numpy-out
+        ``step``, opf_env.py:371-419).  ``host_actions`` may be filled in place by the caller."""
+        if getattr(self, "_host", None) is None:
+            xp, B = self.xp, self.num_envs
+            cuda = self.device.type == "cuda"
+            pin = lambda *shape, dtype: (xp.empty(shape, dtype=dtype).pin_memory() if cuda
+                                         else xp.empty(shape, dtype=dtype))
+            n_obs = self.single_observation_space.shape[0]
+            self._host = dict(
+                actions=pin(B, max(self.program.n_act, 1), dtype=xp.float64),
+                obs=pin(B, n_obs, dtype=self.engine.obs.dtype), reward=pin(B, dtype=xp.float64),
+                cost=pin(B, dtype=xp.float64), converged=pin(B, dtype=self.engine.converged.dtype),
+                terminated=xp.ones(B, dtype=xp.bool).numpy(), truncated=xp.zeros(B, dtype=xp.bool).numpy())
+            self.host_actions = self._host["actions"].numpy()
+            self._host_np = {k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in self._host.items()}
+        return self._host
+
+    def step_host(self, actions=None):
+        """``step`` for callers that live on the host: ``actions`` is a numpy array / CPU tensor
+        (``None``: use ``self.host_actions`` as filled by the caller); returns numpy views of pinned
+        buffers ``(obs, reward, terminated, truncated, info)`` that stay valid until the next call.
+
+        The copies are part of the pipeline instead of a tail: the next episode's observation is
+        produced by the side stream while the power flow of this step still runs, so its
+        device->host transfer (the bulk of the bytes) overlaps kernel 3/4; only the small per-env
+        results (reward, cost, converged) are copied after kernel 5."""
+        xp, e = self.xp, self.engine
+        h = self.enable_host_io()
+        src = h["actions"]
+        if actions is not None:
+            a = xp.as_tensor(actions)
+            if a.dtype == src.dtype and a.is_contiguous() and (a.is_pinned() or self.device.type != "cuda"):
+                src = a.reshape(src.shape)             # already DMA-able: no staging copy
+            elif a.data_ptr() != src.data_ptr():
+                src.copy_(a.reshape(src.shape))
+        if self.validate_actions and xp.isnan(src).any():
+            raise AssertionError("NaN in actions")     # opf_env.py:382
+        def obs_to_host():
+            keep, self.copy_outputs = self.copy_outputs, False     # no device-side clone on the way out
+            h["obs"].copy_(self._obs_out(), non_blocking=True)
+            self.copy_outputs = keep
+
+        main = xp.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        if self._prefetch:
+            # The persistent power-flow kernel fills every SM (registers and shared memory), so
+            # kernels of the side stream cannot run beside it -- but a copy can.  Order: the next
+            # episode's kernels (sampler, hook programs, observation) first, then the power flow of
+            # this step WHILE the copy engine moves that observation to the host.
+            self._main_done.record(main)               # the other state buffer is free from here on
+            e.actions.copy_(src, non_blocking=True)    # (the action upload overlaps the side kernels)
+            e.select(1 - e.cur)
+            with xp.cuda.stream(self._side):
+                self._side.wait_event(self._main_done)
+                self._begin_episode()
+                self._side_kernels.record(self._side)
+                obs_to_host()
+                self._side_done.record(self._side)
+            e.select(1 - e.cur)
+            main.wait_event(self._side_kernels)
+        else:
+            e.actions.copy_(src, non_blocking=True)
+        e.step(final_obs=True)
+        self.power_flow_available = True
+        reward = e.reward
+        if self.clipped_action_penalty:
+            reward = reward - self._mean_correction(e.actions) * self.clipped_action_penalty
+        h["reward"].copy_(reward, non_blocking=True)
+        h["cost"].copy_(e.cost, non_blocking=True)
+        h["converged"].copy_(e.converged, non_blocking=True)
+        if self._prefetch:
+            main.wait_event(self._side_done)
+            e.select(1 - e.cur)
+        else:
+            self._begin_episode()
+            obs_to_host()
+        if main is not None:
+            main.synchronize()                         # the caller needs the results to act
+        n = self._host_np
+        info = {"cost": n["cost"], "converged": n["converged"].astype(bool, copy=False)}
+        return n["obs"], n["reward"], n["terminated"], n["truncated"], info
 
     def _mean_correction(self, act):
         """opf_env.py:488-491: mean |applied action - requested action|."""

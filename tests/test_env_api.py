@@ -304,3 +304,29 @@ def test_bus_wise_obs():
     both = make(Shared, n=3, bus_wise_obs=True, add_mean_obs=True)
     o, _ = both.reset(seed=9)
     assert o.shape[1] == both.single_observation_space.shape[0]
+
+
+def test_step_host_matches_step():
+    """numpy-in / numpy-out step (pinned buffers, overlapped copies on the GPU) returns exactly what
+    the tensor API returns."""
+    a_env, b_env = make(n=5), make(n=5)
+    a_env.reset(seed=21)
+    b_env.reset(seed=21)
+    for k in range(3):
+        act = np.random.default_rng(k).random((5, 14))
+        obs, reward, term, trunc, info = a_env.step(torch.as_tensor(act))
+        h_obs, h_reward, h_term, h_trunc, h_info = b_env.step_host(act)
+        assert isinstance(h_obs, np.ndarray) and h_obs.shape == (5, 442)
+        np.testing.assert_array_equal(h_obs, obs.numpy())
+        np.testing.assert_array_equal(h_reward, reward.numpy())
+        np.testing.assert_array_equal(h_info["cost"], info["cost"].numpy())
+        np.testing.assert_array_equal(h_info["converged"], info["converged"].numpy())
+        assert h_term.all() and not h_trunc.any()
+    # in-place use of the pinned action buffer
+    b_env.host_actions[:] = 0.25
+    a_env.step(torch.full((5, 14), 0.25, dtype=torch.float64))
+    _, r_dev, _, _, _ = a_env.step(torch.full((5, 14), 0.5, dtype=torch.float64))
+    b_env.step_host()
+    b_env.host_actions[:] = 0.5
+    _, r_host, _, _, _ = b_env.step_host()
+    np.testing.assert_array_equal(r_host, r_dev.numpy())
