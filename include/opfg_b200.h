@@ -252,6 +252,32 @@ void opfg_row_program_destroy(OpfgRowProgram* program);
 int  opfg_row_program_run(const OpfgRowProgram* program, int64_t n_env, double* state, int32_t n_state,
                           void* cuda_stream);
 
+/* ---- fused episode reset ---------------------------------------------------------------------
+ * OpfEnv.reset (opfgym/opf_env.py:180-220) for `full_uniform` data without a reset power flow:
+ * `_sampling` (sampler stages and hook row programs, in the order the env issues them), the initial
+ * action (centre or random, :201-207), `_apply_actions` and `_get_obs` -- ONE launch, one CTA per
+ * environment; the state row is written once and the observation comes out of the same pass.
+ * Results are bit-identical to the sequence opfg_sample_uniform / opfg_row_program_run /
+ * opfg_philox_uniform / opfg_assemble / opfg_observe with stream ids `stream_base + stream_offset`. */
+typedef struct {
+    int32_t kind;                    /* 0: uniform sampler stage, 1: row program stage            */
+    int32_t n_cols;                  /* kind 0                                                    */
+    const int32_t* slots;            /* kind 0, DEVICE [n_cols]                                   */
+    const double* lo;                /* kind 0, DEVICE [n_cols]                                   */
+    const double* hi;
+    const double* div;
+    uint32_t stream_offset;          /* kind 0: Philox stream = stream_base + stream_offset       */
+    const OpfgRowProgram* program;   /* kind 1                                                    */
+} OpfgResetStage;
+typedef struct OpfgResetPlan OpfgResetPlan;
+int  opfg_reset_plan_create(const OpfgResetStage* stages /* host */, int32_t n_stages, OpfgResetPlan** out);
+void opfg_reset_plan_destroy(OpfgResetPlan* plan);
+/* batch needs state, actions (receives the initial action) and an obs buffer.
+ * random_action: 0 = centre action 0.5, 1 = U[0,1) from Philox stream stream_base + action_stream_offset */
+int  opfg_reset_episode(const OpfgGrid* grid, const OpfgBatch* batch, const OpfgResetPlan* plan,
+                        uint64_t seed, uint64_t first_env, uint64_t stream_base, int32_t random_action,
+                        uint32_t action_stream_offset, void* cuda_stream);
+
 /* FP64 FMA throughput probe for the roofline denominator (MEASURED_PEAKS.json has no FP64 figure):
  * every thread runs 8 independent DFMA chains of `iters` steps; flops = 2*8*iters*n_blocks*256.
  * out (device, >= 1 double) keeps the result alive. */

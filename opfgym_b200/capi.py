@@ -79,6 +79,12 @@ class RowOp(C.Structure):
                 ("imm", C.c_double)]
 
 
+class ResetStage(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_cols", C.c_int32), ("slots", C.c_void_p), ("lo", C.c_void_p),
+                ("hi", C.c_void_p), ("div", C.c_void_p), ("stream_offset", C.c_uint32),
+                ("program", C.c_void_p)]
+
+
 class Batch(C.Structure):
     _fields_ = [("n_env", C.c_int64)] + [(n, C.c_void_p) for n in
                 ("actions", "state", "sbus", "vm", "va", "converged", "iterations",
@@ -112,6 +118,10 @@ PROTOTYPES = {
                                           _dp, C.POINTER(C.c_void_p)]),
     "opfg_row_program_destroy": (None, [C.c_void_p]),
     "opfg_row_program_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "opfg_reset_plan_create": (C.c_int, [C.POINTER(ResetStage), C.c_int32, C.POINTER(C.c_void_p)]),
+    "opfg_reset_plan_destroy": (None, [C.c_void_p]),
+    "opfg_reset_episode": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_uint64, C.c_uint64,
+                                     C.c_uint64, C.c_int32, C.c_uint32, C.c_void_p]),
     "opfg_fp64_probe": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "opfg_launch_count": (C.c_int64, []),
 }

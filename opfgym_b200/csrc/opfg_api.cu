@@ -14,6 +14,7 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "opfg_core.h"
@@ -80,6 +81,7 @@ struct OpfgGrid {
     int n_result_cells = 0;
     double flops_score = 0;
     bool has_assembly = false, has_scoring = false;
+    int act_ref_max = -1, obs_ref_max = -1;   // largest state cell the action / observation tables touch
     size_t smem_pf = 0, smem_score = 0;
     int carveout_pct = -1;   // -1: leave the driver's default L1/shared split
     int envs_per_cta = 1;
@@ -182,6 +184,71 @@ OPFG_HHD void row_program_exec(const OpfgRowOp* ops, int n_ops, const double* st
     }
 }
 
+// one stage of a fused episode reset (device form of OpfgResetStage)
+struct ResetStage {
+    int kind, n_cols;
+    const int* slots;
+    const double *lo, *hi, *dv;
+    unsigned stream_off;
+    const OpfgRowOp* ops;
+    int n_ops, n_rows;
+    const double* statics;
+    int sync_after;      // 0: the next stage touches other cells and runs beside this one
+    int item_off;        // first thread of this stage within its group (spreads the group's items)
+    int ops_smem;        // offset (in OpfgRowOp units) of the staged copy of `ops`
+};
+struct OpfgResetPlan {
+    std::vector<ResetStage> host;
+    std::vector<std::vector<int>> reads, writes;     // per stage: state cells read / written
+    ResetStage* dev = nullptr;
+    int max_cell = -1, n_ops_total = 0;
+    // decided per state layout (n_inputs) at the first launch
+    int for_inputs = -1;
+    bool covers_all = false;
+    ~OpfgResetPlan() { dev_free(dev); }
+};
+
+// OpfEnv.reset for one environment (opf_env.py:180-220): sampler stages + hook programs, initial
+// action, set-points, observation.  `S` is the environment's state row -- in the CUDA build a
+// shared-memory copy of its input part, so every stage reads what the previous one wrote at
+// shared-memory latency and the row goes to HBM once, coalesced.
+template <class C>
+OPFG_HD void env_reset(const GridDev& g, const C& cx, const OpfgBatch& B, int64_t env, double* S, const ResetStage* st,
+                       int n_st, const OpfgRowOp* ops_staged, uint64_t seed, uint64_t first_env, uint64_t stream_base,
+                       int random_action, unsigned action_stream_off) {
+    const int T = cx.nthreads();
+    for (int k = 0; k < n_st; ++k) {
+        const ResetStage& s = st[k];
+        const int first = (cx.tid + T - s.item_off % T) % T;
+        if (s.kind == 0) {
+            for (int pr = first; pr < (s.n_cols + 1) / 2; pr += T) {
+                double u[2];
+                philox_two_doubles(seed, first_env + (uint64_t)env, stream_base + s.stream_off, (uint32_t)pr, &u[0], &u[1]);
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 2 * pr + h;
+                    if (j < s.n_cols) S[s.slots[j]] = (s.lo[j] + (s.hi[j] - s.lo[j]) * u[h]) / s.dv[j];
+                }
+            }
+        } else {
+            const OpfgRowOp* ops = ops_staged ? ops_staged + s.ops_smem : s.ops;
+            for (int r = first; r < s.n_rows; r += T) row_program_exec(ops, s.n_ops, s.statics, r, S);
+        }
+        if (s.sync_after) cx.sync();
+    }
+    // initial action (:201-207) and its set-points: thread j owns action j
+    double* act = const_cast<double*>(B.actions) + env * (int64_t)g.n_act;   // receives the initial action
+    for (int j = cx.tid; j < g.n_act; j += T) {
+        double u[2] = {0.5, 0.5};
+        if (random_action)
+            philox_two_doubles(seed, first_env + (uint64_t)env, stream_base + action_stream_off, (uint32_t)(j >> 1), &u[0], &u[1]);
+        act[j] = u[j & 1];
+    }
+    cx.sync();
+    env_assemble(g, cx, act, S, (double*)nullptr, (double*)nullptr, (double*)nullptr, true);
+    cx.sync();
+    gather_obs(g, cx, S, B, env);
+}
+
 // ------------------------------------------------------------------- kernels
 #ifndef OPFG_HOSTSIM
 __global__ void k_row_program(const OpfgRowOp* ops, int n_ops, const double* statics, int n_rows, int64_t n_env,
@@ -193,6 +260,36 @@ __global__ void k_row_program(const OpfgRowOp* ops, int n_ops, const double* sta
     if (idx >= n_env * n_rows) return;
     const int64_t env = idx / n_rows;
     row_program_exec(sops, n_ops, statics, (int)(idx % n_rows), state + env * (int64_t)n_state);
+}
+// One CTA per environment.  Dynamic shared memory: [n_row doubles: input part of the state row]
+// [n_st stages][all row-program ops]; n_row == 0 keeps the row in global memory (tables that
+// reach beyond the input part).
+template <int T>
+__global__ void __launch_bounds__(T) k_reset(GridDev g, OpfgBatch B, const ResetStage* st, int n_st, int n_row,
+                                             int copy_in, int n_ops_total, uint64_t seed, uint64_t first_env,
+                                             uint64_t stream_base, int random_action, unsigned action_stream_off) {
+    extern __shared__ __align__(16) double sm[];
+    Ctx<T> cx{(int)threadIdx.x, nullptr, 0};
+    const int64_t env = blockIdx.x;
+    double* Sg = B.state + env * (int64_t)g.n_state;
+    ResetStage* st_s = reinterpret_cast<ResetStage*>(sm + n_row);
+    OpfgRowOp* ops_s = reinterpret_cast<OpfgRowOp*>(st_s + n_st);
+    for (int i = threadIdx.x; i < n_st * (int)(sizeof(ResetStage) / 8); i += T)
+        reinterpret_cast<double*>(st_s)[i] = reinterpret_cast<const double*>(st)[i];
+    if (copy_in)
+        for (int i = threadIdx.x; i < n_row; i += T) sm[i] = Sg[i];
+    __syncthreads();
+    for (int k = 0; k < n_st; ++k)
+        if (st_s[k].kind == 1)
+            for (int i = threadIdx.x; i < st_s[k].n_ops * 3; i += T)
+                reinterpret_cast<double*>(ops_s + st_s[k].ops_smem)[i] = reinterpret_cast<const double*>(st_s[k].ops)[i];
+    __syncthreads();
+    (void)n_ops_total;
+    env_reset(g, cx, B, env, n_row ? sm : Sg, st_s, n_st, ops_s, seed, first_env, stream_base, random_action, action_stream_off);
+    if (n_row) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_row; i += T) Sg[i] = sm[i];
+    }
 }
 __global__ void k_branch_y(GridDev g) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,7 +368,7 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // Persistent multi-environment CTA: E environments of T threads each share ONE shared-memory copy of
 // the schedule / Ybus tables (their reads are on the critical path of every level); each environment
 // group synchronises on its own named barrier and walks through its share of the batch.
-template <int T>
+template <int T, bool FUSED>
 __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles, int stages) {
     extern __shared__ __align__(16) double sm[];
     {
@@ -299,7 +396,7 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     // the other E-1 environments of the CTA instead of running as separate launches)
     for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
         double* yv = B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr;
-        if (stages & 1) {
+        if (FUSED && (stages & 1)) {
             env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                          B.sbus + env * (int64_t)g.nb * 2, yv,
                          B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0);
@@ -308,7 +405,7 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
         env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2, g.n_dyn > 0 ? yv : nullptr,
                      B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
         cx.sync();
-        if (stages & 2) {
+        if (FUSED && (stages & 2)) {
             env_score(g, cx, mine, B, env, g.n_dyn > 0 ? yv : nullptr, B.state + env * (int64_t)g.n_state);
             cx.sync();
         }
@@ -637,6 +734,11 @@ int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
         check_ref(a->inj_p, a->n_inj, "inj_p"); check_ref(a->inj_q, a->n_inj, "inj_q"); check_ref(a->inj_coef, a->n_inj, "inj_coef");
         for (int i = 0; i < a->n_act; ++i)
             if (a->act_slot[i] < 0 || a->act_slot[i] >= a->n_state) throw std::runtime_error("act_slot out of range");
+        G->act_ref_max = -1;
+        for (int i = 0; i < a->n_act; ++i) {
+            G->act_ref_max = std::max({G->act_ref_max, a->act_slot[i], a->act_lo[i], a->act_hi[i], a->act_div[i]});
+            if (a->act_clamp_lo) G->act_ref_max = std::max({G->act_ref_max, a->act_clamp_lo[i], a->act_clamp_hi[i]});
+        }
         d.act_slot = G->up(a->act_slot, a->n_act);
         d.act_lo = G->up(a->act_lo, a->n_act); d.act_hi = G->up(a->act_hi, a->n_act);
         d.act_div = G->up(a->act_div, a->n_act); d.act_kind = G->up(a->act_kind, a->n_act);
@@ -655,6 +757,10 @@ int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
             p[at] = a->inj_p[e]; q[at] = a->inj_q[e]; c[at] = a->inj_coef[e];
         }
         d.inj_ptr = G->up(ptr); d.inj_p = G->up(p); d.inj_q = G->up(q); d.inj_coef = G->up(c);
+        std::vector<int> order(d.nb);
+        for (int b = 0; b < d.nb; ++b) order[b] = b;
+        std::stable_sort(order.begin(), order.end(), [&](int a_, int b_) { return ptr[a_ + 1] - ptr[a_] > ptr[b_ + 1] - ptr[b_]; });
+        d.inj_order = G->up(order);
         G->has_assembly = true;
         return 0;
     } catch (const std::exception& ex) {
@@ -737,6 +843,9 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
         d.invalid_obj_share = sc->invalid_objective_share;
         d.n_obs = sc->n_obs;
         d.obs_ref = G->tab2(sc->obs_ref, sc->obs_ptr ? sc->obs_ptr[sc->n_obs] : sc->n_obs);
+        G->obs_ref_max = -1;
+        for (int i = 0, n = sc->obs_ptr ? sc->obs_ptr[sc->n_obs] : sc->n_obs; i < n; ++i)
+            G->obs_ref_max = std::max(G->obs_ref_max, sc->obs_ref[i]);
         d.obs_ptr = sc->obs_ptr ? G->tab2(sc->obs_ptr, sc->n_obs + 1) : nullptr;
         // copies of the grid tables that the branch-flow part of kernel 5 reads
         G->score_consts = G->tab2(G->consts_host);
@@ -914,14 +1023,16 @@ static int pf_launch(const OpfgGrid* G, const OpfgBatch* B, void* stream, int st
             const size_t smem_multi = G->d.tab_staged_bytes + (size_t)E * smem;
             static size_t attr_multi = 48 * 1024;
             if (smem_multi > attr_multi) {
-                cudaFuncSetAttribute(k_pf_multi<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
                 attr_multi = smem_multi;
             }
             int n_sm = 148;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
             const int64_t groups = (B->n_env + E - 1) / E;
             const unsigned grid = (unsigned)std::min<int64_t>(groups, n_sm);
-            k_pf_multi<TT><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8), stages);
+            if (stages) k_pf_multi<TT, true><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8), stages);
+            else k_pf_multi<TT, false><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8), 0);
         } else {
             k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
         }
@@ -1063,6 +1174,116 @@ int opfg_row_program_run(const OpfgRowProgram* P, int64_t n_env, double* state, 
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("row program launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_reset_plan_create(const OpfgResetStage* stages, int32_t n_stages, OpfgResetPlan** out) {
+    if (!out || n_stages < 0 || (n_stages > 0 && !stages)) return fail("bad argument");
+    *out = nullptr;
+    static_assert(sizeof(ResetStage) % 8 == 0 && sizeof(OpfgRowOp) == 24, "staging copies whole doubles");
+    try {
+        auto P = std::make_unique<OpfgResetPlan>();
+        for (int k = 0; k < n_stages; ++k) {
+            const OpfgResetStage& a = stages[k];
+            ResetStage s{};
+            std::vector<int> rd, wr;
+            s.kind = a.kind;
+            if (a.kind == 0) {
+                if (!a.slots || !a.lo || !a.hi || !a.div || a.n_cols < 0) return fail("reset stage %d: bad sampler arrays", k);
+                s.n_cols = a.n_cols; s.slots = a.slots; s.lo = a.lo; s.hi = a.hi; s.dv = a.div;
+                s.stream_off = a.stream_offset;
+                wr.resize(a.n_cols);
+#ifdef OPFG_HOSTSIM
+                memcpy(wr.data(), a.slots, sizeof(int) * a.n_cols);
+#else
+                cudaMemcpy(wr.data(), a.slots, sizeof(int) * a.n_cols, cudaMemcpyDeviceToHost);
+#endif
+            } else if (a.kind == 1) {
+                if (!a.program) return fail("reset stage %d: null row program", k);
+                const OpfgRowProgram& rp = *a.program;
+                s.ops = rp.ops; s.statics = rp.statics;   // device copies (host memory in the host build)
+                s.n_ops = rp.n_ops; s.n_rows = rp.n_rows;
+                s.ops_smem = P->n_ops_total;
+                P->n_ops_total += rp.n_ops;
+                for (const OpfgRowOp& o : rp.host_ops)
+                    if (o.op == OPFG_OP_LOAD_STATE || o.op == OPFG_OP_STORE_STATE)
+                        for (int r = 0; r < rp.n_rows; ++r) (o.op == OPFG_OP_LOAD_STATE ? rd : wr).push_back(o.a + r);
+            } else return fail("reset stage %d: unknown kind %d", k, a.kind);
+            for (int c : wr) { if (c < 0) return fail("reset stage %d: negative state cell", k); P->max_cell = std::max(P->max_cell, c); }
+            for (int c : rd) { if (c < 0) return fail("reset stage %d: negative state cell", k); P->max_cell = std::max(P->max_cell, c); }
+            std::sort(rd.begin(), rd.end()); std::sort(wr.begin(), wr.end());
+            P->host.push_back(s); P->reads.push_back(rd); P->writes.push_back(wr);
+        }
+        // stages that touch disjoint cells run side by side (no barrier, items spread over the threads)
+        auto overlap = [](const std::vector<int>& a, const std::vector<int>& b) {
+            size_t i = 0, j = 0;
+            while (i < a.size() && j < b.size()) { if (a[i] == b[j]) return true; if (a[i] < b[j]) ++i; else ++j; }
+            return false;
+        };
+        int group_begin = 0, items = 0;
+        for (int k = 0; k < n_stages; ++k) {
+            ResetStage& s = P->host[k];
+            bool independent = true;
+            for (int j = group_begin; j < k && independent; ++j)
+                independent = !overlap(P->writes[j], P->reads[k]) && !overlap(P->writes[j], P->writes[k]) &&
+                              !overlap(P->reads[j], P->writes[k]);
+            if (!independent) { P->host[k - 1].sync_after = 1; group_begin = k; items = 0; }
+            s.item_off = items;
+            items += s.kind == 0 ? (s.n_cols + 1) / 2 : s.n_rows;
+        }
+        if (n_stages > 0) P->host[n_stages - 1].sync_after = 1;
+        P->dev = (ResetStage*)dev_alloc(sizeof(ResetStage) * P->host.size());
+        if (!P->dev) return fail("device allocation failed");
+        dev_put(P->dev, P->host.data(), sizeof(ResetStage) * P->host.size());
+        *out = P.release();
+    } catch (const std::exception& e) { return fail("opfg_reset_plan_create: %s", e.what()); }
+    return 0;
+}
+
+void opfg_reset_plan_destroy(OpfgResetPlan* plan) { delete plan; }
+
+int opfg_reset_episode(const OpfgGrid* G, const OpfgBatch* B, const OpfgResetPlan* P_, uint64_t seed, uint64_t first_env,
+                       uint64_t stream_base, int32_t random_action, uint32_t action_stream_offset, void* stream) {
+    if (!G || !B || !P_) return fail("null argument");
+    OpfgResetPlan* P = const_cast<OpfgResetPlan*>(P_);
+    if (!G->has_assembly || !G->has_scoring) return fail("opfg_reset_episode needs opfg_set_assembly and opfg_set_scoring");
+    if (!B->state || !B->actions || (!B->obs_f32 && !B->obs_f64)) return fail("opfg_reset_episode needs state, actions and an obs buffer");
+    if (P->max_cell >= G->d.n_state) return fail("reset plan touches cell %d of a %d-cell state row", P->max_cell, G->d.n_state);
+    if (B->n_env <= 0) return 0;
+    const int n_st = (int)P->host.size();
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    Ctx<1> cx;
+    for (int64_t env = 0; env < B->n_env; ++env)
+        env_reset(G->d, cx, *B, env, B->state + env * (int64_t)G->d.n_state, P->host.data(), n_st, (const OpfgRowOp*)nullptr,
+                  seed, first_env, stream_base, random_action, action_stream_offset);
+#else
+    const int n_in = G->d.n_inputs;
+    if (P->for_inputs != n_in) {      // does one reset write every input cell?  (then the row needs no copy-in)
+        std::vector<char> hit(std::max(n_in, 1), 0);
+        for (const auto& w : P->writes) for (int c : w) if (c < n_in) hit[c] = 1;
+        bool all = true;
+        for (int c = 0; c < n_in && all; ++c) all = hit[c];
+        P->covers_all = all; P->for_inputs = n_in;
+    }
+    // the row lives in shared memory if everything the reset touches lies in the input part
+    const bool staged = n_in > 0 && P->max_cell < n_in && G->act_ref_max < n_in && G->obs_ref_max < n_in;
+    const int n_row = staged ? n_in : 0;
+    constexpr int T = 128;
+    const size_t smem = sizeof(double) * n_row + sizeof(ResetStage) * n_st + sizeof(OpfgRowOp) * P->n_ops_total;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        if (cudaFuncSetAttribute(k_reset<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return fail("reset: %zu bytes of shared memory per environment", smem);
+        attr = smem;
+    }
+    k_reset<T><<<(unsigned)B->n_env, T, smem, (cudaStream_t)stream>>>(
+        G->d, *B, P->dev, n_st, n_row, staged && !P->covers_all, P->n_ops_total, seed, first_env, stream_base,
+        random_action, action_stream_offset);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("reset launch: %s", cudaGetErrorString(e));
 #endif
     return 0;
 }

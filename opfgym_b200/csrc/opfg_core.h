@@ -81,6 +81,7 @@ struct GridDev {
     const int* act_slot;
     const int *act_lo, *act_hi, *act_div, *act_kind, *act_clamp_lo, *act_clamp_hi;
     const int* inj_ptr;                // [nb+1] CSR by ppc bus
+    const int* inj_order;              // [nb] buses sorted by descending entry count
     const int *inj_p, *inj_q, *inj_coef;
     // ---- scoring (kernel 5) ----
     int n_pp_bus, res_vm_slot, res_va_slot;
@@ -199,7 +200,12 @@ struct Ctx {
 #define OPFG_TICK_INIT do {} while (0)
 #endif
 
-OPFG_HD double ref_val(const GridDev& g, const double* S, int r) { return r >= 0 ? S[r] : g.consts[-r - 1]; }
+// value of a reference: state cell (r >= 0) or constant (r < 0); one load behind a selected
+// address, so lanes holding different kinds of reference do not diverge
+OPFG_HD double ref_val(const GridDev& g, const double* S, int r) {
+    const double* p = r >= 0 ? S + r : g.consts + (-r - 1);
+    return *p;
+}
 
 // ------------------------------------------------- kernel 1a: branch -> Ybus values
 // Admittances of one branch from its ppc row (pypower makeYbus.py [ext-mem]).
@@ -241,6 +247,26 @@ OPFG_HD double obs_value(const GridDev& g, const double* S, int j) {
     double v = 0.0;
     for (int k = g.obs_ptr[j]; k < g.obs_ptr[j + 1]; ++k) v += ref_val(g, S, g.obs_ref[k]);
     return v;
+}
+
+// observation gather (opf_env.py:532-549); four independent reference chains in flight per thread
+template <class C>
+OPFG_HD void gather_obs(const GridDev& g, const C& cx, const double* S, const OpfgBatch& B, int64_t env) {
+    const int T = cx.nthreads(), n = g.n_obs;
+    float* o32 = B.obs_f32 ? B.obs_f32 + env * (int64_t)n : nullptr;
+    double* o64 = B.obs_f64 ? B.obs_f64 + env * (int64_t)n : nullptr;
+    int j = cx.tid;
+    for (; j + 3 * T < n; j += 4 * T) {
+        const double v0 = obs_value(g, S, j), v1 = obs_value(g, S, j + T), v2 = obs_value(g, S, j + 2 * T),
+                     v3 = obs_value(g, S, j + 3 * T);
+        if (o32) { o32[j] = (float)v0; o32[j + T] = (float)v1; o32[j + 2 * T] = (float)v2; o32[j + 3 * T] = (float)v3; }
+        if (o64) { o64[j] = v0; o64[j + T] = v1; o64[j + 2 * T] = v2; o64[j + 3 * T] = v3; }
+    }
+    for (; j < n; j += T) {
+        const double v = obs_value(g, S, j);
+        if (o32) o32[j] = (float)v;
+        if (o64) o64[j] = v;
+    }
 }
 
 // --------------------------------------- kernel 1b: actions -> set-points -> Sbus
@@ -293,8 +319,9 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
         for (int e = cx.tid; e < g.nnz_y; e += T) ybus_entry(g, g.br_y, e, yval_env + 2 * (size_t)e, bry_env);
     }
     const double inv_base = 1.0 / g.base_mva;
-#pragma unroll 2
-    for (int bus = cx.tid; bus < g.nb; bus += T) {
+    // buses in descending order of their entry count: the lanes of one round carry equal work
+    for (int k = cx.tid; k < g.nb; k += T) {
+        const int bus = g.inj_order[k];
         double p = 0, q = 0;
 #pragma unroll 4
         for (int e = g.inj_ptr[bus]; e < g.inj_ptr[bus + 1]; ++e) {
@@ -792,12 +819,25 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     for (int c = 0; c < nc; ++c) {
         double viol = 0, cnt = 0;
         const bool worst = g.con_worst[c] != 0;
-        for (int e = g.con_ptr[c] + cx.tid; e < g.con_ptr[c + 1]; e += T) {
-            const double v = ref_val(g, S, g.con_value[e]) * g.con_value_scale[e];
-            const double mul = g.con_bound_mul[e];
-            const double hi = ref_val(g, S, g.con_max[e]) * mul, lo = ref_val(g, S, g.con_min[e]) * mul;
+        auto test = [&](double v, double hi, double lo) {
             if (v > hi) { const double x = fabs(v - hi); viol = worst ? (x > viol ? x : viol) : viol + x; cnt += 1; }
             if (v < lo) { const double x = fabs(v - lo); viol = worst ? (x > viol ? x : viol) : viol + x; cnt += 1; }
+        };
+        int e = g.con_ptr[c] + cx.tid;
+        const int e_end = g.con_ptr[c + 1];
+        for (; e + T < e_end; e += 2 * T) {          // two entries per trip: their loads overlap
+            const int f = e + T;
+            const double v0 = ref_val(g, S, g.con_value[e]) * g.con_value_scale[e], m0 = g.con_bound_mul[e];
+            const double v1 = ref_val(g, S, g.con_value[f]) * g.con_value_scale[f], m1 = g.con_bound_mul[f];
+            const double hi0 = ref_val(g, S, g.con_max[e]) * m0, lo0 = ref_val(g, S, g.con_min[e]) * m0;
+            const double hi1 = ref_val(g, S, g.con_max[f]) * m1, lo1 = ref_val(g, S, g.con_min[f]) * m1;
+            test(v0, hi0, lo0);
+            test(v1, hi1, lo1);
+        }
+        for (; e < e_end; e += T) {
+            const double mul = g.con_bound_mul[e];
+            test(ref_val(g, S, g.con_value[e]) * g.con_value_scale[e], ref_val(g, S, g.con_max[e]) * mul,
+                 ref_val(g, S, g.con_min[e]) * mul);
         }
         cnt = cx.block_sum(cnt);
         viol = worst ? cx.block_max(viol) : cx.block_sum(viol);
@@ -869,12 +909,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
 #endif
         }
     }
-    // observation gather (opf_env.py:532-549)
-    for (int j = cx.tid; j < g.n_obs; j += T) {
-        const double v = obs_value(g, S, j);
-        if (B.obs_f32) B.obs_f32[env * (int64_t)g.n_obs + j] = (float)v;
-        if (B.obs_f64) B.obs_f64[env * (int64_t)g.n_obs + j] = v;
-    }
+    gather_obs(g, cx, S, B, env);
 }
 
 // ------------------------------------------------------------------------ Philox

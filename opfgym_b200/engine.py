@@ -15,6 +15,17 @@ from . import capi
 from .compiler import EnvProgram, fill_descs
 
 
+class ResetPlan:
+    def __init__(self, lib, handle, keep):
+        self.lib, self.handle, self.keep = lib, handle, keep     # `keep`: device arrays the plan points to
+
+    def __del__(self):
+        try:
+            self.lib.opfg_reset_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class Engine:
     def __init__(self, program: EnvProgram, num_envs: int, device=None,
                  tolerance_mva: float = 1e-8, max_iteration: int = 10, init: str = "dc",
@@ -142,7 +153,37 @@ class Engine:
         """View ``S[:, slice]`` of one (table, column): shape [B, n_rows]."""
         return self.state[:, self.program.layout.slice(table, column)]
 
+    trace = None     # a list while the env layer records one episode reset for ``make_reset_plan``
+
+    def make_reset_plan(self, trace, stream_base: int):
+        """Fused-reset plan from a recorded sequence of sampler / row-program calls."""
+        stages, keep = [], []
+        for item in trace:
+            if item[0] == "sample":
+                _, slots, lo, hi, div, stream_id = item
+                keep += [slots, lo, hi, div]
+                stages.append(capi.ResetStage(kind=0, n_cols=int(slots.shape[0]), slots=self._ptr(slots).value,
+                                              lo=self._ptr(lo).value, hi=self._ptr(hi).value,
+                                              div=self._ptr(div).value,
+                                              stream_offset=stream_id - stream_base))
+            else:
+                keep.append(item[1])
+                stages.append(capi.ResetStage(kind=1, program=item[1].handle.value))
+        arr = (capi.ResetStage * max(len(stages), 1))(*stages)
+        h = C.c_void_p()
+        capi.check(self.lib, self.lib.opfg_reset_plan_create(arr, len(stages), C.byref(h)))
+        return ResetPlan(self.lib, h, keep)
+
+    def reset_episode(self, plan, seed: int, first_env: int, stream_base: int, random_action: bool,
+                      action_stream_offset: int):
+        """ONE launch: sampler stages + hook programs + initial action + set-points + observation."""
+        capi.check(self.lib, self.lib.opfg_reset_episode(
+            self.handle, C.byref(self.batch_setpoints), plan.handle, seed, first_env, stream_base,
+            int(random_action), action_stream_offset, self._stream()))
+
     def sample_uniform(self, slots, lo, hi, div, seed: int, first_env: int, stream_id: int):
+        if self.trace is not None:
+            self.trace.append(("sample", slots, lo, hi, div, stream_id))
         n = int(slots.shape[0])
         capi.check(self.lib, self.lib.opfg_sample_uniform(
             seed, first_env, stream_id, self.num_envs, n, self._ptr(slots), self._ptr(lo),

@@ -152,6 +152,8 @@ class CompiledRowProgram:
 
     def run(self):
         e = self.engine
+        if e.trace is not None:
+            e.trace.append(("program", self))
         capi.check(self.lib, self.lib.opfg_row_program_run(
             self.handle, e.num_envs, e._ptr(e.state), e.program.layout.n, e._stream()))
 

@@ -330,3 +330,30 @@ def test_step_host_matches_step():
     b_env.host_actions[:] = 0.5
     _, r_host, _, _, _ = b_env.step_host()
     np.testing.assert_array_equal(r_host, r_dev.numpy())
+
+
+@pytest.mark.parametrize("cls_name,kw", [("VoltageControl", {}), ("LoadShedding", {}),
+                                         ("EcoDispatch", {"initial_action": "random"}),
+                                         ("MaxRenewable", {})])
+def test_fused_reset_equals_kernel_sequence(cls_name, kw):
+    """opfg_reset_episode (one launch) vs the recorded sequence sampler / hook programs / initial
+    action / set-points / observe: bit-identical state rows and observations, episode after episode."""
+    cls = getattr(envs, cls_name)
+    fused = make(cls, n=4, **kw)                     # automatic for the built-in envs at small batch sizes
+    plain = make(cls, n=4, fused_reset=False, **kw)
+    assert fused.fused_reset and not plain.fused_reset
+    of, _ = fused.reset(seed=31)          # recorded
+    op, _ = plain.reset(seed=31)
+    assert torch.equal(of, op)
+    n_act = fused.single_action_space.shape[0]
+    for k in range(3):
+        act = torch.rand(4, n_act, dtype=torch.float64, generator=torch.Generator().manual_seed(k))
+        rf, rp = fused.step(act), plain.step(act)      # auto-reset: replayed by the fused kernel
+        assert fused._reset_plans and not plain._reset_plans
+        assert torch.equal(rf[0], rp[0]) and torch.equal(rf[1], rp[1])
+        n_in = fused.program.layout.n_inputs
+        assert torch.equal(fused.engine.state[:, :n_in], plain.engine.state[:, :n_in])
+        assert torch.equal(fused.engine.actions_reset, plain.engine.actions_reset)
+    of, _ = fused.reset(seed=77)
+    op, _ = plain.reset(seed=77)
+    assert torch.equal(of, op)

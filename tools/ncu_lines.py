@@ -30,7 +30,8 @@ for f in os.listdir(tmp):
             m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
             if m:
                 lines.append((file_, line_, m.group(2)))
-csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+extra = os.environ.get("NCU_FILTER", "").split()     # e.g. NCU_FILTER="-k regex:k_score" for multi-kernel reports
+csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + extra, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(csvtxt)))
 hdr_i = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
 hdr = rows[hdr_i]
