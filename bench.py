@@ -214,7 +214,8 @@ def gpu_arm(args):
     # ---- end to end through the public API with HOST buffers ("e2e") ---------------------
     # env.step_host: actions from a pinned host buffer, results (next observation, reward, cost,
     # converged) back in pinned host memory, stream-synchronised before it returns -- every step
-    h_act = [torch.rand(B, n_act, dtype=torch.float64).pin_memory() for _ in range(4)]
+    # float32 actions: the dtype of the reference's action space (gym.spaces.Box default, opf_env.py:130)
+    h_act = [torch.rand(B, n_act, dtype=torch.float32).pin_memory() for _ in range(4)]
     e2e_sink = []
 
     def e2e_step(i):
@@ -226,7 +227,7 @@ def gpu_arm(args):
     e2e_steps = max(5, args.steps // 2)
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
-    h2d = B * n_act * 8
+    h2d = B * n_act * 4
     d2h = B * n_obs * 4 + B * 8 + B * 8 + B      # observation f32, reward, cost, converged
 
     # ---- FP64 peak probe (roofline denominator not in MEASURED_PEAKS.json) -----------------

@@ -153,7 +153,7 @@ struct OpfgGrid {
 };
 
 struct OpfgRowProgram {
-    int n_rows = 0, n_ops = 0;
+    int n_rows = 0, n_ops = 0, n_regs = 1;
     OpfgRowOp* ops = nullptr;        // device
     double* statics = nullptr;       // device
     std::vector<OpfgRowOp> host_ops;
@@ -161,24 +161,27 @@ struct OpfgRowProgram {
     ~OpfgRowProgram() { dev_free(ops); dev_free(statics); }
 };
 
-OPFG_HHD void row_program_exec(const OpfgRowOp* ops, int n_ops, const double* statics, int row, double* S) {
-    double r[16];
+// `r` is the program's register file, register i at r[i * rs]: a shared-memory column per thread in
+// the CUDA build (a per-thread local array would be 128 B x 2 048 threads per SM -- it spills out of
+// L1 and the interpreter ends up bound by local-memory traffic), a plain array in the host build.
+OPFG_HHD void row_program_exec(const OpfgRowOp* ops, int n_ops, const double* statics, int row, double* S, double* r,
+                               int rs) {
     for (int i = 0; i < n_ops; ++i) {
         const OpfgRowOp o = ops[i];
         switch (o.op) {
-            case OPFG_OP_LOAD_STATE: r[o.dst] = S[o.a + row]; break;
-            case OPFG_OP_LOAD_STATIC: r[o.dst] = statics[o.a + row]; break;
-            case OPFG_OP_CONST: r[o.dst] = o.imm; break;
-            case OPFG_OP_ADD: r[o.dst] = r[o.a] + r[o.b]; break;
-            case OPFG_OP_SUB: r[o.dst] = r[o.a] - r[o.b]; break;
-            case OPFG_OP_MUL: r[o.dst] = r[o.a] * r[o.b]; break;
-            case OPFG_OP_DIV: r[o.dst] = r[o.a] / r[o.b]; break;
-            case OPFG_OP_SQRT: r[o.dst] = sqrt(r[o.a]); break;
-            case OPFG_OP_NEG: r[o.dst] = -r[o.a]; break;
-            case OPFG_OP_MIN: r[o.dst] = fmin(r[o.a], r[o.b]); break;
-            case OPFG_OP_MAX: r[o.dst] = fmax(r[o.a], r[o.b]); break;
-            case OPFG_OP_ABS: r[o.dst] = fabs(r[o.a]); break;
-            case OPFG_OP_STORE_STATE: S[o.a + row] = r[o.b]; break;
+            case OPFG_OP_LOAD_STATE: r[o.dst * rs] = S[o.a + row]; break;
+            case OPFG_OP_LOAD_STATIC: r[o.dst * rs] = statics[o.a + row]; break;
+            case OPFG_OP_CONST: r[o.dst * rs] = o.imm; break;
+            case OPFG_OP_ADD: r[o.dst * rs] = r[o.a * rs] + r[o.b * rs]; break;
+            case OPFG_OP_SUB: r[o.dst * rs] = r[o.a * rs] - r[o.b * rs]; break;
+            case OPFG_OP_MUL: r[o.dst * rs] = r[o.a * rs] * r[o.b * rs]; break;
+            case OPFG_OP_DIV: r[o.dst * rs] = r[o.a * rs] / r[o.b * rs]; break;
+            case OPFG_OP_SQRT: r[o.dst * rs] = sqrt(r[o.a * rs]); break;
+            case OPFG_OP_NEG: r[o.dst * rs] = -r[o.a * rs]; break;
+            case OPFG_OP_MIN: r[o.dst * rs] = fmin(r[o.a * rs], r[o.b * rs]); break;
+            case OPFG_OP_MAX: r[o.dst * rs] = fmax(r[o.a * rs], r[o.b * rs]); break;
+            case OPFG_OP_ABS: r[o.dst * rs] = fabs(r[o.a * rs]); break;
+            case OPFG_OP_STORE_STATE: S[o.a + row] = r[o.b * rs]; break;
             default: break;
         }
     }
@@ -201,7 +204,7 @@ struct OpfgResetPlan {
     std::vector<ResetStage> host;
     std::vector<std::vector<int>> reads, writes;     // per stage: state cells read / written
     ResetStage* dev = nullptr;
-    int max_cell = -1, n_ops_total = 0;
+    int max_cell = -1, n_ops_total = 0, n_regs = 1;
     // decided per state layout (n_inputs) at the first launch
     int for_inputs = -1;
     bool covers_all = false;
@@ -214,7 +217,7 @@ struct OpfgResetPlan {
 // shared-memory latency and the row goes to HBM once, coalesced.
 template <class C>
 OPFG_HD void env_reset(const GridDev& g, const C& cx, const OpfgBatch& B, int64_t env, double* S, const ResetStage* st,
-                       int n_st, const OpfgRowOp* ops_staged, uint64_t seed, uint64_t first_env, uint64_t stream_base,
+                       int n_st, const OpfgRowOp* ops_staged, double* regs, int reg_stride, uint64_t seed, uint64_t first_env, uint64_t stream_base,
                        int random_action, unsigned action_stream_off) {
     const int T = cx.nthreads();
     for (int k = 0; k < n_st; ++k) {
@@ -231,7 +234,7 @@ OPFG_HD void env_reset(const GridDev& g, const C& cx, const OpfgBatch& B, int64_
             }
         } else {
             const OpfgRowOp* ops = ops_staged ? ops_staged + s.ops_smem : s.ops;
-            for (int r = first; r < s.n_rows; r += T) row_program_exec(ops, s.n_ops, s.statics, r, S);
+            for (int r = first; r < s.n_rows; r += T) row_program_exec(ops, s.n_ops, s.statics, r, S, regs, reg_stride);
         }
         if (s.sync_after) cx.sync();
     }
@@ -251,19 +254,36 @@ OPFG_HD void env_reset(const GridDev& g, const C& cx, const OpfgBatch& B, int64_
 
 // ------------------------------------------------------------------- kernels
 #ifndef OPFG_HOSTSIM
+// Elementwise kernels.  A 256-thread block is split into 256/W environment lanes of W item lanes
+// (W a power of two): blockIdx.x walks item chunks, blockIdx.y environment groups, and a thread keeps
+// its item while it loops over environments -- no 64-bit division per thread (it used to cost more
+// than the work itself), per-item table values loaded once.
+struct ItemGrid { dim3 grid; int w_log2; };
+static ItemGrid item_grid(int64_t n_env, int n_items) {
+    int w_log2 = 0;
+    while ((1 << w_log2) < n_items && w_log2 < 8) ++w_log2;
+    const int W = 1 << w_log2, epb = 256 / W;
+    static const int64_t y_cap = getenv("OPFG_ITEM_GRID_Y") ? atoll(getenv("OPFG_ITEM_GRID_Y")) : 8192;
+    const int64_t groups = (n_env + epb - 1) / epb;
+    return {dim3((unsigned)((n_items + W - 1) / W), (unsigned)std::max<int64_t>(1, std::min<int64_t>(groups, y_cap))), w_log2};
+}
+#define OPFG_ITEM_LOOP(item, env, n_env_, w_log2)                                                   \
+    const int item = (int)(blockIdx.x << (w_log2)) + (int)(threadIdx.x & ((1u << (w_log2)) - 1u));  \
+    const int64_t env_step_ = (int64_t)gridDim.y * (256 >> (w_log2));                               \
+    for (int64_t env = (int64_t)blockIdx.y * (256 >> (w_log2)) + (threadIdx.x >> (w_log2)); env < (n_env_); env += env_step_)
 __global__ void k_row_program(const OpfgRowOp* ops, int n_ops, const double* statics, int n_rows, int64_t n_env,
-                              double* state, int n_state) {
+                              double* state, int n_state, int w_log2) {
+    extern __shared__ __align__(16) double regs[];      // [n_regs][256] register file, one column per thread
     __shared__ OpfgRowOp sops[96];
     for (int i = threadIdx.x; i < n_ops; i += blockDim.x) sops[i] = ops[i];
     __syncthreads();
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_env * n_rows) return;
-    const int64_t env = idx / n_rows;
-    row_program_exec(sops, n_ops, statics, (int)(idx % n_rows), state + env * (int64_t)n_state);
+    OPFG_ITEM_LOOP(row, env, n_env, w_log2)
+        if (row < n_rows)
+            row_program_exec(sops, n_ops, statics, row, state + env * (int64_t)n_state, regs + threadIdx.x, 256);
 }
 // One CTA per environment.  Dynamic shared memory: [n_row doubles: input part of the state row]
-// [n_st stages][all row-program ops]; n_row == 0 keeps the row in global memory (tables that
-// reach beyond the input part).
+// [n_st stages][all row-program ops][n_regs x T register file]; n_row == 0 keeps the row in global
+// memory (tables that reach beyond the input part).
 template <int T>
 __global__ void __launch_bounds__(T) k_reset(GridDev g, OpfgBatch B, const ResetStage* st, int n_st, int n_row,
                                              int copy_in, int n_ops_total, uint64_t seed, uint64_t first_env,
@@ -284,8 +304,8 @@ __global__ void __launch_bounds__(T) k_reset(GridDev g, OpfgBatch B, const Reset
             for (int i = threadIdx.x; i < st_s[k].n_ops * 3; i += T)
                 reinterpret_cast<double*>(ops_s + st_s[k].ops_smem)[i] = reinterpret_cast<const double*>(st_s[k].ops)[i];
     __syncthreads();
-    (void)n_ops_total;
-    env_reset(g, cx, B, env, n_row ? sm : Sg, st_s, n_st, ops_s, seed, first_env, stream_base, random_action, action_stream_off);
+    double* regs = reinterpret_cast<double*>(ops_s + n_ops_total) + threadIdx.x;
+    env_reset(g, cx, B, env, n_row ? sm : Sg, st_s, n_st, ops_s, regs, T, seed, first_env, stream_base, random_action, action_stream_off);
     if (n_row) {
         __syncthreads();
         for (int i = threadIdx.x; i < n_row; i += T) Sg[i] = sm[i];
@@ -299,33 +319,33 @@ __global__ void k_ybus(GridDev g, double* y_val) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e < g.nnz_y) ybus_entry(g, g.br_y, e, y_val + 2 * (size_t)e);
 }
-__global__ void k_philox(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols, double* out) {
-    const int pairs = (n_cols + 1) / 2;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_env * pairs) return;
-    const int64_t b = idx / pairs;
-    const int pr = (int)(idx % pairs);
-    double u0, u1;
-    philox_two_doubles(seed, first_env + (uint64_t)b, stream, (uint32_t)pr, &u0, &u1);
-    double* row = out + b * (int64_t)n_cols;
-    row[2 * pr] = u0;
-    if (2 * pr + 1 < n_cols) row[2 * pr + 1] = u1;
+__global__ void k_philox(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols, double* out,
+                         int w_log2) {
+    OPFG_ITEM_LOOP(pr, b, n_env, w_log2) {
+        if (2 * pr >= n_cols) break;
+        double u0, u1;
+        philox_two_doubles(seed, first_env + (uint64_t)b, stream, (uint32_t)pr, &u0, &u1);
+        double* row = out + b * (int64_t)n_cols;
+        row[2 * pr] = u0;
+        if (2 * pr + 1 < n_cols) row[2 * pr + 1] = u1;
+    }
 }
 __global__ void k_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols,
                                  const int* slots, const double* lo, const double* hi, const double* dv,
-                                 double* state, int n_state) {
-    const int pairs = (n_cols + 1) / 2;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_env * pairs) return;
-    const int64_t b = idx / pairs;
-    const int pr = (int)(idx % pairs);
-    double u[2];
-    philox_two_doubles(seed, first_env + (uint64_t)b, stream, (uint32_t)pr, &u[0], &u[1]);
-    double* row = state + b * (int64_t)n_state;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int j = 2 * pr + h;
-        if (j < n_cols) row[slots[j]] = (lo[j] + (hi[j] - lo[j]) * u[h]) / dv[j];
+                                 double* state, int n_state, int w_log2) {
+    const int pr0 = (int)(blockIdx.x << w_log2) + (int)(threadIdx.x & ((1u << w_log2) - 1u));
+    if (2 * pr0 >= n_cols) return;
+    const int j0 = 2 * pr0, j1 = 2 * pr0 + 1;
+    const bool two = j1 < n_cols;
+    const int s0 = slots[j0], s1 = two ? slots[j1] : 0;
+    const double lo0 = lo[j0], w0 = hi[j0] - lo0, d0 = dv[j0];
+    const double lo1 = two ? lo[j1] : 0.0, w1 = two ? hi[j1] - lo1 : 0.0, d1 = two ? dv[j1] : 1.0;
+    OPFG_ITEM_LOOP(pr, b, n_env, w_log2) {
+        double u0, u1;
+        philox_two_doubles(seed, first_env + (uint64_t)b, stream, (uint32_t)pr, &u0, &u1);
+        double* row = state + b * (int64_t)n_state;
+        row[s0] = (lo0 + w0 * u0) / d0;
+        if (two) row[s1] = (lo1 + w1 * u1) / d1;
     }
 }
 template <int T>
@@ -420,14 +440,13 @@ __global__ void __launch_bounds__(T) k_score(GridDev g, OpfgBatch B) {
               B.state + env * (int64_t)g.n_state);
 }
 
-__global__ void k_observe(GridDev g, OpfgBatch B) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= B.n_env * g.n_obs) return;
-    const int64_t env = idx / g.n_obs;
-    const int j = (int)(idx % g.n_obs);
-    const double v = obs_value(g, B.state + env * (int64_t)g.n_state, j);
-    if (B.obs_f32) B.obs_f32[idx] = (float)v;
-    if (B.obs_f64) B.obs_f64[idx] = v;
+__global__ void k_observe(GridDev g, OpfgBatch B, int w_log2) {
+    OPFG_ITEM_LOOP(j, env, B.n_env, w_log2) {
+        if (j >= g.n_obs) break;
+        const double v = obs_value(g, B.state + env * (int64_t)g.n_state, j);
+        if (B.obs_f32) B.obs_f32[env * (int64_t)g.n_obs + j] = (float)v;
+        if (B.obs_f64) B.obs_f64[env * (int64_t)g.n_obs + j] = v;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_fp64_probe(int iters, double* out) {
@@ -924,8 +943,8 @@ int opfg_philox_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
             if (2 * pr + 1 < n_cols) out[b * n_cols + 2 * pr + 1] = u1;
         }
 #else
-    const int64_t total = n_env * pairs;
-    k_philox<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(seed, first_env, stream_id, n_env, n_cols, out);
+    const ItemGrid ig = item_grid(n_env, pairs);
+    k_philox<<<ig.grid, 256, 0, (cudaStream_t)cuda_stream>>>(seed, first_env, stream_id, n_env, n_cols, out, ig.w_log2);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("philox launch: %s", cudaGetErrorString(e));
@@ -951,9 +970,9 @@ int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
             }
         }
 #else
-    const int64_t total = n_env * pairs;
-    k_sample_uniform<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
-        seed, first_env, stream_id, n_env, n_cols, slots, lo, hi, dv, state, n_state);
+    const ItemGrid ig = item_grid(n_env, pairs);
+    k_sample_uniform<<<ig.grid, 256, 0, (cudaStream_t)cuda_stream>>>(
+        seed, first_env, stream_id, n_env, n_cols, slots, lo, hi, dv, state, n_state, ig.w_log2);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("sample launch: %s", cudaGetErrorString(e));
@@ -1113,8 +1132,8 @@ int opfg_observe(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             if (B->obs_f64) B->obs_f64[env * G->d.n_obs + j] = v;
         }
 #else
-    const int64_t total = B->n_env * G->d.n_obs;
-    k_observe<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(G->d, *B);
+    const ItemGrid ig = item_grid(B->n_env, G->d.n_obs);
+    k_observe<<<ig.grid, 256, 0, (cudaStream_t)stream>>>(G->d, *B, ig.w_log2);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("observe launch: %s", cudaGetErrorString(e));
@@ -1147,6 +1166,8 @@ int opfg_row_program_create(int32_t n_rows, int32_t n_ops, const OpfgRowOp* ops,
     }
     auto* P = new OpfgRowProgram();
     P->n_rows = n_rows; P->n_ops = n_ops;
+    for (int i = 0; i < n_ops; ++i)
+        if (ops[i].op != OPFG_OP_STORE_STATE) P->n_regs = std::max(P->n_regs, ops[i].dst + 1);
     P->host_ops.assign(ops, ops + n_ops);
     P->host_statics.assign(statics, statics + n_static);
     P->ops = (OpfgRowOp*)dev_alloc(sizeof(OpfgRowOp) * n_ops);
@@ -1166,11 +1187,11 @@ int opfg_row_program_run(const OpfgRowProgram* P, int64_t n_env, double* state, 
     (void)stream;
     for (int64_t env = 0; env < n_env; ++env)
         for (int row = 0; row < P->n_rows; ++row)
-            row_program_exec(P->ops, P->n_ops, P->statics, row, state + env * (int64_t)n_state);
+            { double r[16]; row_program_exec(P->ops, P->n_ops, P->statics, row, state + env * (int64_t)n_state, r, 1); }
 #else
-    const int64_t total = n_env * P->n_rows;
-    k_row_program<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        P->ops, P->n_ops, P->statics, P->n_rows, n_env, state, n_state);
+    const ItemGrid ig = item_grid(n_env, P->n_rows);
+    k_row_program<<<ig.grid, 256, sizeof(double) * 256 * P->n_regs, (cudaStream_t)stream>>>(
+        P->ops, P->n_ops, P->statics, P->n_rows, n_env, state, n_state, ig.w_log2);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("row program launch: %s", cudaGetErrorString(e));
@@ -1206,6 +1227,7 @@ int opfg_reset_plan_create(const OpfgResetStage* stages, int32_t n_stages, OpfgR
                 s.n_ops = rp.n_ops; s.n_rows = rp.n_rows;
                 s.ops_smem = P->n_ops_total;
                 P->n_ops_total += rp.n_ops;
+                P->n_regs = std::max(P->n_regs, rp.n_regs);
                 for (const OpfgRowOp& o : rp.host_ops)
                     if (o.op == OPFG_OP_LOAD_STATE || o.op == OPFG_OP_STORE_STATE)
                         for (int r = 0; r < rp.n_rows; ++r) (o.op == OPFG_OP_LOAD_STATE ? rd : wr).push_back(o.a + r);
@@ -1255,9 +1277,10 @@ int opfg_reset_episode(const OpfgGrid* G, const OpfgBatch* B, const OpfgResetPla
 #ifdef OPFG_HOSTSIM
     (void)stream;
     Ctx<1> cx;
+    double host_regs[16];
     for (int64_t env = 0; env < B->n_env; ++env)
         env_reset(G->d, cx, *B, env, B->state + env * (int64_t)G->d.n_state, P->host.data(), n_st, (const OpfgRowOp*)nullptr,
-                  seed, first_env, stream_base, random_action, action_stream_offset);
+                  host_regs, 1, seed, first_env, stream_base, random_action, action_stream_offset);
 #else
     const int n_in = G->d.n_inputs;
     if (P->for_inputs != n_in) {      // does one reset write every input cell?  (then the row needs no copy-in)
@@ -1271,7 +1294,8 @@ int opfg_reset_episode(const OpfgGrid* G, const OpfgBatch* B, const OpfgResetPla
     const bool staged = n_in > 0 && P->max_cell < n_in && G->act_ref_max < n_in && G->obs_ref_max < n_in;
     const int n_row = staged ? n_in : 0;
     constexpr int T = 128;
-    const size_t smem = sizeof(double) * n_row + sizeof(ResetStage) * n_st + sizeof(OpfgRowOp) * P->n_ops_total;
+    const size_t smem = sizeof(double) * n_row + sizeof(ResetStage) * n_st + sizeof(OpfgRowOp) * P->n_ops_total +
+                        sizeof(double) * T * P->n_regs;
     static size_t attr = 48 * 1024;
     if (smem > attr) {
         if (cudaFuncSetAttribute(k_reset<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

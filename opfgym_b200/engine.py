@@ -114,9 +114,9 @@ class Engine:
                 b.objective_offset = self._ptr(self.objective_offset)
         return self.objective_offset
 
-    def enable_double_buffer(self):
-        """Second state matrix: the next episode can be sampled while the current one is solved."""
-        if len(self._states) == 1:
+    def enable_double_buffer(self, n: int = 2):
+        """More state matrices: later episodes can be sampled while the current one is solved."""
+        while len(self._states) < n:
             self._states.append(self.state.clone())
 
     def select(self, index: int):

@@ -208,6 +208,8 @@ class BatchedOpfEnv:
             self._main_done = self.xp.cuda.Event()
             self._side_done = self.xp.cuda.Event()
             self._side_kernels = self.xp.cuda.Event()
+            self._ready_events = (self.xp.cuda.Event(), self.xp.cuda.Event())
+        self._pipe = None     # step_host's look-ahead: episode k+1 already sampled, its observation on the host
         self.test = False
         self.power_flow_available = False
 
@@ -437,6 +439,7 @@ class BatchedOpfEnv:
             self.seed = int(seed)
             self._episode = 0
         options = options or {}
+        self._pipe = None
         self.test = options.get("test", False)
         self._begin_episode(options.get("step", None))
         return self._obs_out(), {}
@@ -507,15 +510,19 @@ class BatchedOpfEnv:
         if self.validate_actions and xp.isnan(act).any():   # host sync; off by default
             raise AssertionError("NaN in actions")     # opf_env.py:382
         e = self.engine
+        if self._pipe is not None:
+            raise RuntimeError("step() after step_host(): the host pipeline holds pre-sampled episodes; "
+                               "call reset() before switching back to the tensor API")
         if self._prefetch:
             main = xp.cuda.current_stream(self.device)
             self._main_done.record(main)
-            e.select(1 - e.cur)                       # launches below target the NEXT episode's buffer
+            cur, nxt = e.cur, (e.cur + 1) % len(e._states)
+            e.select(nxt)                             # launches below target the NEXT episode's buffer
             with xp.cuda.stream(self._side):
                 self._side.wait_event(self._main_done)
                 self._begin_episode()
                 self._side_done.record(self._side)
-            e.select(1 - e.cur)
+            e.select(cur)
         self.engine.actions.copy_(act.reshape(self.engine.actions.shape))
         self.engine.step(final_obs=True)
         self.power_flow_available = True
@@ -534,7 +541,7 @@ class BatchedOpfEnv:
         terminated, truncated = (keep(self._flags[0]), keep(self._flags[1]))
         if self._prefetch:
             xp.cuda.current_stream(self.device).wait_event(self._side_done)
-            e.select(1 - e.cur)                       # the prefetched episode becomes the current one
+            e.select(nxt)                             # the prefetched episode becomes the current one
         else:
             self._begin_episode()
         return self._obs_out(), reward, terminated, truncated, info
@@ -551,7 +558,8 @@ class BatchedOpfEnv:
             n_obs = self.single_observation_space.shape[0]
             self._host = dict(
                 actions=pin(B, max(self.program.n_act, 1), dtype=xp.float64),
-                obs=pin(B, n_obs, dtype=self.engine.obs.dtype), reward=pin(B, dtype=xp.float64),
+                obs=pin(B, n_obs, dtype=self.engine.obs.dtype),
+                obs_alt=pin(B, n_obs, dtype=self.engine.obs.dtype), reward=pin(B, dtype=xp.float64),
                 cost=pin(B, dtype=xp.float64), converged=pin(B, dtype=self.engine.converged.dtype),
                 terminated=xp.ones(B, dtype=xp.bool).numpy(), truncated=xp.zeros(B, dtype=xp.bool).numpy())
             self.host_actions = self._host["actions"].numpy()
@@ -572,37 +580,54 @@ class BatchedOpfEnv:
         src = h["actions"]
         if actions is not None:
             a = xp.as_tensor(actions)
-            if a.dtype == src.dtype and a.is_contiguous() and (a.is_pinned() or self.device.type != "cuda"):
-                src = a.reshape(src.shape)             # already DMA-able: no staging copy
+            if a.is_floating_point() and a.is_contiguous() and (a.is_pinned() or self.device.type != "cuda"):
+                src = a.reshape(src.shape)             # already DMA-able (any float dtype; gym's Box
+                                                       # default is float32): no staging copy
             elif a.data_ptr() != src.data_ptr():
                 src.copy_(a.reshape(src.shape))
         if self.validate_actions and xp.isnan(src).any():
             raise AssertionError("NaN in actions")     # opf_env.py:382
-        def obs_to_host():
+        def obs_to_host(dst):
             keep, self.copy_outputs = self.copy_outputs, False     # no device-side clone on the way out
-            h["obs"].copy_(self._obs_out(), non_blocking=True)
+            dst.copy_(self._obs_out(), non_blocking=True)
             self.copy_outputs = keep
 
         main = xp.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        obs_now = h["obs"]
         if self._prefetch:
-            # The persistent power-flow kernel fills every SM (registers and shared memory), so
-            # kernels of the side stream cannot run beside it -- but a copy can.  Order: the next
-            # episode's kernels (sampler, hook programs, observation) first, then the power flow of
-            # this step WHILE the copy engine moves that observation to the host.
-            self._main_done.record(main)               # the other state buffer is free from here on
-            e.actions.copy_(src, non_blocking=True)    # (the action upload overlaps the side kernels)
-            e.select(1 - e.cur)
-            with xp.cuda.stream(self._side):
-                self._side.wait_event(self._main_done)
-                self._begin_episode()
-                self._side_kernels.record(self._side)
-                obs_to_host()
-                self._side_done.record(self._side)
-            e.select(1 - e.cur)
-            main.wait_event(self._side_kernels)
+            # Two episodes ahead.  The persistent power-flow kernel fills every SM (registers and
+            # shared memory): kernels of another stream cannot run beside it, but a copy can.  So the
+            # observation this call returns (episode k+1) was sampled and sent to the host during the
+            # PREVIOUS call; this call's side-stream work prepares episode k+2 behind the step's own
+            # kernels, and its 58 MB transfer runs on the copy engine under the next power flow (and
+            # under whatever the caller does between two calls).
+            e.enable_double_buffer(3)
+            pipe = self._pipe
+
+            def sample_ahead(buf, dst):
+                cur = e.cur
+                e.select(buf)
+                with xp.cuda.stream(self._side):
+                    self._side.wait_event(self._main_done)
+                    self._begin_episode()
+                    obs_to_host(dst)
+                    ready = self._ready_events[dst is h["obs"]]
+                    ready.record(self._side)
+                e.select(cur)
+                return ready
+
+            self._main_done.record(main)               # buffers of finished episodes are free from here on
+            if pipe is None:                           # first call after reset: episode k+1 is not there yet
+                nxt = (e.cur + 1) % 3
+                pipe = dict(buf=nxt, obs="obs", ready=sample_ahead(nxt, h["obs"]))
+            e.actions.copy_(src, non_blocking=True)    # this step's own work goes to the GPU first
+            e.step(final_obs=True)
+            free = 3 - e.cur - pipe["buf"]             # the buffer of the episode before this one
+            other = "obs_alt" if pipe["obs"] == "obs" else "obs"
+            ahead = dict(buf=free, obs=other, ready=sample_ahead(free, h[other]))
         else:
             e.actions.copy_(src, non_blocking=True)
-        e.step(final_obs=True)
+            e.step(final_obs=True)
         self.power_flow_available = True
         reward = e.reward
         if self.clipped_action_penalty:
@@ -611,16 +636,19 @@ class BatchedOpfEnv:
         h["cost"].copy_(e.cost, non_blocking=True)
         h["converged"].copy_(e.converged, non_blocking=True)
         if self._prefetch:
-            main.wait_event(self._side_done)
-            e.select(1 - e.cur)
+            main.synchronize()                         # the caller needs the results to act
+            pipe["ready"].synchronize()                # (sent during the previous call)
+            obs_now = h[pipe["obs"]]
+            e.select(pipe["buf"])                      # episode k+1 becomes the current one
+            self._pipe = ahead
         else:
             self._begin_episode()
-            obs_to_host()
-        if main is not None:
-            main.synchronize()                         # the caller needs the results to act
+            obs_to_host(h["obs"])
+            if main is not None:
+                main.synchronize()
         n = self._host_np
         info = {"cost": n["cost"], "converged": n["converged"].astype(bool, copy=False)}
-        return n["obs"], n["reward"], n["terminated"], n["truncated"], info
+        return obs_now.numpy(), n["reward"], n["terminated"], n["truncated"], info
 
     def _mean_correction(self, act):
         """opf_env.py:488-491: mean |applied action - requested action|."""
