@@ -388,7 +388,19 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // Persistent multi-environment CTA: E environments of T threads each share ONE shared-memory copy of
 // the schedule / Ybus tables (their reads are on the critical path of every level); each environment
 // group synchronises on its own named barrier and walks through its share of the batch.
-template <int T, bool FUSED>
+// Tables of the staged arena, in allocation order: the LU schedule ("hot", always staged) and the
+// Ybus / DC / q-limit tables ("cold", staged only when they fit beside the environments).
+#define OPFG_HOT_TABLES(X)                                                                              \
+    X(bus_of_int) X(type_int) X(vm0_int) X(va0_int) X(level_ptr) X(fill_ids) X(diag_mode) X(dp_ptr) X(dp_pack) \
+    X(dp_own) X(eg_ptr) X(eg_item) X(off_ptr) X(off_hdr) X(op_pack) X(up_ptr) X(up_pack)
+#define OPFG_COLD_TABLES(X) X(y_ptr) X(y_meta) X(y_val) X(dc_val) X(dc_rhs0) X(qlim_bus) X(qlim_min) X(qlim_max)
+
+// The kernel receives a view of GridDev in which every staged table pointer holds its BYTE OFFSET in
+// the arena (staged_view below).  Adding the offset to the shared-memory base is one instruction and
+// leaves the address space known to the compiler (LDS instead of generic loads); the earlier
+// "if the pointer lies in the staged range, move it" form was re-evaluated at the use sites under
+// the 96-register cap and cost 10 % of the kernel's instructions.
+template <int T, bool FUSED, bool COLD>
 __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles, int stages) {
     extern __shared__ __align__(16) double sm[];
     {
@@ -397,16 +409,10 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
         for (int i = threadIdx.x; i < g.tab_staged_bytes / 16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const char* sbase = reinterpret_cast<const char*>(sm);
-#define OPFG_REBASE(field)                                                                        \
-    if (reinterpret_cast<const char*>(g.field) - g.tab_base < g.tab_staged_bytes)                  \
-        g.field = reinterpret_cast<decltype(g.field)>(sbase + (reinterpret_cast<const char*>(g.field) - g.tab_base))
-    OPFG_REBASE(bus_of_int); OPFG_REBASE(type_int); OPFG_REBASE(vm0_int); OPFG_REBASE(va0_int);
-    OPFG_REBASE(level_ptr); OPFG_REBASE(fill_ids); OPFG_REBASE(diag_mode);
-    OPFG_REBASE(dp_ptr); OPFG_REBASE(dp_pack); OPFG_REBASE(off_ptr); OPFG_REBASE(off_hdr); OPFG_REBASE(op_pack);
-    OPFG_REBASE(up_ptr); OPFG_REBASE(up_pack); OPFG_REBASE(y_ptr); OPFG_REBASE(y_meta); OPFG_REBASE(y_val);
-    OPFG_REBASE(dc_val); OPFG_REBASE(dc_rhs0);
-    OPFG_REBASE(qlim_bus); OPFG_REBASE(qlim_min); OPFG_REBASE(qlim_max);
+    char* sbase = reinterpret_cast<char*>(sm);
+#define OPFG_REBASE(field) g.field = reinterpret_cast<decltype(g.field)>(sbase + (unsigned)reinterpret_cast<size_t>(g.field));
+    OPFG_HOT_TABLES(OPFG_REBASE)
+    if (COLD) { OPFG_COLD_TABLES(OPFG_REBASE) }
 #undef OPFG_REBASE
     const int e_local = threadIdx.x / T;
     double* mine = sm + g.tab_staged_bytes / 8 + (size_t)e_local * env_doubles;
@@ -506,6 +512,16 @@ __global__ void __launch_bounds__(1024) k_score_multi(GridDev g, OpfgBatch B, in
             for (int i = g.n_inputs + tid; i < g.n_state; i += T) Sg[i] = row[i];
         cx.sync();
     }
+}
+
+// staged view of the grid for k_pf_multi: table pointers -> byte offsets in the arena
+static GridDev staged_view(const GridDev& d, bool cold) {
+    GridDev view = d;
+#define OPFG_TO_OFFSET(field) view.field = reinterpret_cast<decltype(view.field)>((size_t)(reinterpret_cast<const char*>(d.field) - d.tab_base));
+    OPFG_HOT_TABLES(OPFG_TO_OFFSET)
+    if (cold) { OPFG_COLD_TABLES(OPFG_TO_OFFSET) }
+#undef OPFG_TO_OFFSET
+    return view;
 }
 
 #define OPFG_DISPATCH_T(T_, ...)                                     \
@@ -637,15 +653,37 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             d.nnz_y_nonref = s.y_ptr[s.n];
             // per level: one lane per pivot, or eight lanes per pivot (component-parallel gather)
             std::vector<unsigned char> mode(s.n_levels, 0);
+            // Eager gather pays where few environments fit an SM and the phase latency is exposed
+            // (meshed 372-bus grid: -7 %); with ten resident environments the kernel is bound by
+            // shared-memory throughput and the extra partial-sum traffic costs 2 %.
+            const bool eager = getenv("OPFG_EAGER_GATHER") ? atoi(getenv("OPFG_EAGER_GATHER")) != 0
+                             : pf_smem_doubles(s.n_blocks, s.n, nb, T, 0) * sizeof(double) * 4 > 227 * 1024;
+            if (!eager) {
+                for (int k = 0; k < s.n; ++k) s.dp_own[k] = s.dp_ptr[k];
+                s.eg_ptr.assign(s.n_levels + 1, 0);
+                s.eg_k.clear(); s.eg_begin.clear(); s.eg_count.clear();
+            }
+            std::vector<U2> eg(s.eg_k.size());
+            for (size_t i = 0; i < eg.size(); ++i) {
+                if (s.eg_count[i] > 0xffff) throw std::runtime_error("eager gather item with more than 65535 pairs");
+                eg[i] = U2{(uint32_t)s.eg_k[i] | ((uint32_t)s.eg_count[i] << 16), (uint32_t)s.eg_begin[i]};
+            }
             for (int l = 0; l < s.n_levels; ++l) {
-                int items = s.level_ptr[l + 1] - s.level_ptr[l], maxp = 0;
-                for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) maxp = std::max(maxp, s.dp_ptr[k + 1] - s.dp_ptr[k]);
+                int items = s.level_ptr[l + 1] - s.level_ptr[l] + s.eg_ptr[l + 1] - s.eg_ptr[l], maxp = 0;
+                for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) maxp = std::max(maxp, s.dp_ptr[k + 1] - s.dp_own[k]);
+                for (int i = s.eg_ptr[l]; i < s.eg_ptr[l + 1]; ++i) maxp = std::max(maxp, s.eg_count[i]);
+                if (getenv("OPFG_DEBUG_SCHEDULE"))
+                    fprintf(stderr, "level %d: own %d eager %d max pairs %d (own max %d) off items %d\n", l,
+                            s.level_ptr[l + 1] - s.level_ptr[l], s.eg_ptr[l + 1] - s.eg_ptr[l], maxp,
+                            [&] { int m = 0; for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) m = std::max(m, s.dp_ptr[k + 1] - s.dp_ptr[k]); return m; }(),
+                            s.off_ptr[l + 1] - s.off_ptr[l]);
                 const double narrow = std::ceil(items / (double)T) * (45.0 + 30.0 * maxp);
                 const double wide = std::ceil(items * 8 / (double)T) * (75.0 + 12.0 * maxp);
                 mode[l] = wide < narrow ? 1 : 0;
             }
             d.diag_mode = G->tab(mode);
             d.dp_ptr = G->tab(s.dp_ptr); d.dp_pack = G->tab(dp);
+            d.dp_own = G->tab(s.dp_own); d.eg_ptr = G->tab(s.eg_ptr); d.eg_item = G->tab(eg);
             d.off_ptr = G->tab(s.off_ptr); d.off_hdr = G->tab(hdr); d.op_pack = G->tab(op);
             d.up_ptr = G->tab(s.up_ptr); d.up_pack = G->tab(upk);
             d.tab_hot_bytes = (int)((G->tab_used + 15) & ~size_t(15));   // LU schedule ends here
@@ -1042,16 +1080,23 @@ static int pf_launch(const OpfgGrid* G, const OpfgBatch* B, void* stream, int st
             const size_t smem_multi = G->d.tab_staged_bytes + (size_t)E * smem;
             static size_t attr_multi = 48 * 1024;
             if (smem_multi > attr_multi) {
-                cudaFuncSetAttribute(k_pf_multi<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                cudaFuncSetAttribute(k_pf_multi<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
                 attr_multi = smem_multi;
             }
             int n_sm = 148;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
             const int64_t groups = (B->n_env + E - 1) / E;
             const unsigned grid = (unsigned)std::min<int64_t>(groups, n_sm);
-            if (stages) k_pf_multi<TT, true><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8), stages);
-            else k_pf_multi<TT, false><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(G->d, *B, E, (int)(smem / 8), 0);
+            const bool cold = G->d.tab_staged_bytes == G->d.tab_bytes;
+            const GridDev view = staged_view(G->d, cold);
+            const int env_doubles = (int)(smem / 8);
+            if (stages && cold) k_pf_multi<TT, true, true><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, stages);
+            else if (stages) k_pf_multi<TT, true, false><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, stages);
+            else if (cold) k_pf_multi<TT, false, true><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, 0);
+            else k_pf_multi<TT, false, false><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, 0);
         } else {
             k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
         }

@@ -43,6 +43,9 @@ struct GridDev {
     // packed 16-bit block / pivot ids (n_blocks, nb < 65536 is checked at grid creation)
     const int* dp_ptr;                 // [n+1] pair ranges of the diagonal items
     const U2* dp_pack;                 // {l | w<<16, m}
+    const int* dp_own;                 // [n] first pair of the pivot's own item (sources one level below)
+    const int* eg_ptr;                 // [n_levels+1] eager gather items per diagonal phase
+    const U2* eg_item;                 // {k | n_pairs<<16, first pair}
     const int* off_ptr;                // [n_levels+1] off-diagonal item ranges
     const U2* off_hdr;                 // [n_items+1] {tgt | (piv+1)<<16, first pair}; last entry = sentinel
     const uint32_t* op_pack;           // l | w<<16
@@ -427,11 +430,13 @@ OPFG_HD void jacobian_entry(const GridDev& g, const PfSmem& s, const double* yv,
 }
 
 // ---- diagonal pivot: D_k -= sum L~(k,m) W(m,k), y_k -= sum L~(k,m) t_m, invert, t_k = D^-1 y_k
-// (a) one lane per pivot
-OPFG_HD void lu_diag_item(const GridDev& g, const PfSmem& s, int k) {
-    D2 r0 = ld2(s.lu + 2 * k), r1 = ld2(s.lu1 + 2 * k), y = ld2(s.rhs + 2 * k);
-    const int pe = g.dp_ptr[k + 1];
-    for (int p = g.dp_ptr[k]; p < pe; ++p) {
+// The sum runs in increasing m.  Its part over sources more than one level below k is applied
+// EAGERLY, by separate items in the phases right after those source levels finish (the top of the
+// elimination tree would otherwise walk its whole history in one long dependent chain while most
+// lanes idle); the partial sums wait in D_k / y_k, so the order of additions -- and every bit of
+// the result -- is that of the single gather.
+OPFG_HD void lu_gather_pairs(const GridDev& g, const PfSmem& s, int p, int pe, D2& r0, D2& r1, D2& y) {
+    for (; p < pe; ++p) {
         const U2 id = g.dp_pack[p];
         const int li = 2 * (int)(id.x & 0xffffu), wi = 2 * (int)(id.x >> 16);
         const D2 l0 = ld2(s.lu + li), l1 = ld2(s.lu1 + li), w0 = ld2(s.lu + wi), w1 = ld2(s.lu1 + wi),
@@ -440,6 +445,19 @@ OPFG_HD void lu_diag_item(const GridDev& g, const PfSmem& s, int k) {
         r1.x = fma(-l1.y, w1.x, fma(-l1.x, w0.x, r1.x));  r1.y = fma(-l1.y, w1.y, fma(-l1.x, w0.y, r1.y));
         y.x = fma(-l0.y, t.y, fma(-l0.x, t.x, y.x));      y.y = fma(-l1.y, t.y, fma(-l1.x, t.x, y.y));
     }
+}
+OPFG_HD void lu_eager_item(const GridDev& g, const PfSmem& s, U2 it) {
+    const int k = (int)(it.x & 0xffffu);
+    D2 r0 = ld2(s.lu + 2 * k), r1 = ld2(s.lu1 + 2 * k), y = ld2(s.rhs + 2 * k);
+    lu_gather_pairs(g, s, (int)it.y, (int)it.y + (int)(it.x >> 16), r0, r1, y);
+    st2(s.lu + 2 * k, r0.x, r0.y);
+    st2(s.lu1 + 2 * k, r1.x, r1.y);
+    st2(s.rhs + 2 * k, y.x, y.y);
+}
+// (a) one lane per pivot
+OPFG_HD void lu_diag_item(const GridDev& g, const PfSmem& s, int k) {
+    D2 r0 = ld2(s.lu + 2 * k), r1 = ld2(s.lu1 + 2 * k), y = ld2(s.rhs + 2 * k);
+    lu_gather_pairs(g, s, g.dp_own[k], g.dp_ptr[k + 1], r0, r1, y);
     const double r = 1.0 / fma(r0.x, r1.y, -(r0.y * r1.x));
     const double ia = r1.y * r, ib = -r0.y * r, ic = -r1.x * r, id_ = r0.x * r;
     st2(s.lu + 2 * k, ia, ib);
@@ -449,11 +467,14 @@ OPFG_HD void lu_diag_item(const GridDev& g, const PfSmem& s, int k) {
 
 // (b) eight lanes per pivot: lane `sub` < 4 owns element (sub>>1, sub&1) of the block,
 // lanes 4 and 5 own y_0 and y_1 (short, independent gather chains instead of one long one)
-OPFG_HD double lu_diag_component(const GridDev& g, const PfSmem& s, int k, int sub) {
+OPFG_HD double* lu_component_cell(const PfSmem& s, int k, int sub) {
     const int r = sub < 4 ? (sub >> 1) : (sub - 4);
-    double acc = sub < 4 ? (r ? s.lu1 : s.lu)[2 * k + (sub & 1)] : s.rhs[2 * k + r];
-    const int pe = g.dp_ptr[k + 1];
-    for (int p = g.dp_ptr[k]; p < pe; ++p) {
+    return sub < 4 ? (r ? s.lu1 : s.lu) + 2 * k + (sub & 1) : s.rhs + 2 * k + r;
+}
+OPFG_HD double lu_diag_component(const GridDev& g, const PfSmem& s, int k, int sub, int p, int pe) {
+    const int r = sub < 4 ? (sub >> 1) : (sub - 4);
+    double acc = *lu_component_cell(s, k, sub);
+    for (; p < pe; ++p) {
         const U2 id = g.dp_pack[p];
         const D2 l = ld2((r ? s.lu1 : s.lu) + 2 * (id.x & 0xffffu));
         double wa, wb;
@@ -611,18 +632,26 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         ++it;
         for (int l = 0; l < g.n_levels; ++l) {
             const int lb = g.level_ptr[l], le = g.level_ptr[l + 1];
+            const int n_own = le - lb, eb = g.eg_ptr[l], n_items = n_own + g.eg_ptr[l + 1] - eb;
             if (cx.wide_diag(g.diag_mode[l])) {
                 const int sub = cx.tid & 7, grp = cx.tid >> 3, ngrp = T >> 3;
-                for (int base = lb; base < le; base += ngrp) {       // uniform trip count per warp
-                    const int k = base + grp;
-                    const bool on = k < le && sub < 6;
-                    const double acc = on ? lu_diag_component(g, s, k, sub) : 0.0;
+                for (int base = 0; base < n_items; base += ngrp) {   // uniform trip count per warp
+                    const int idx = base + grp;
+                    const bool own = idx < n_own && sub < 6, eager = idx >= n_own && idx < n_items && sub < 6;
+                    int k = lb + idx, p = 0, pe = 0;
+                    if (own) { p = g.dp_own[k]; pe = g.dp_ptr[k + 1]; }
+                    else if (eager) { const U2 it = g.eg_item[eb + idx - n_own]; k = (int)(it.x & 0xffffu); p = (int)it.y; pe = p + (int)(it.x >> 16); }
+                    const double acc = (own || eager) ? lu_diag_component(g, s, k, sub, p, pe) : 0.0;
                     double a, b, c, d, y0, y1;
                     cx.gather8(acc, a, b, c, d, y0, y1);
-                    if (on) lu_diag_finish(s, k, sub, a, b, c, d, y0, y1);
+                    if (own) lu_diag_finish(s, k, sub, a, b, c, d, y0, y1);
+                    else if (eager) *lu_component_cell(s, k, sub) = acc;
                 }
             } else {
-                for (int k = lb + cx.tid; k < le; k += T) lu_diag_item(g, s, k);
+                for (int idx = cx.tid; idx < n_items; idx += T) {
+                    if (idx < n_own) lu_diag_item(g, s, lb + idx);
+                    else lu_eager_item(g, s, g.eg_item[eb + idx - n_own]);
+                }
             }
             cx.sync();
             OPFG_TICK(16 + l);

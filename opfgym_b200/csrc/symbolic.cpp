@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <array>
 #include <map>
 #include <set>
 #include <stdexcept>
@@ -263,6 +264,28 @@ void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchH
         s.dp_l.insert(s.dp_l.end(), dl[k].begin(), dl[k].end());
         s.dp_w.insert(s.dp_w.end(), dw[k].begin(), dw[k].end());
         s.dp_m.insert(s.dp_m.end(), dm[k].begin(), dm[k].end());
+    }
+    {   // eager gather schedule (pair lists are in increasing m, hence grouped by source level)
+        std::vector<int> level_of(n, 0);
+        for (int l = 0; l < s.n_levels; ++l)
+            for (int k = o.level_ptr[l]; k < o.level_ptr[l + 1]; ++k) level_of[k] = l;
+        s.dp_own.assign(n, 0);
+        std::vector<std::vector<std::array<int, 3>>> per_phase(s.n_levels + 1);
+        for (int k = 0; k < n; ++k) {
+            int p = s.dp_ptr[k];
+            const int pe = s.dp_ptr[k + 1];
+            while (p < pe && level_of[s.dp_m[p]] < level_of[k] - 1) {
+                const int ls = level_of[s.dp_m[p]], begin = p;
+                while (p < pe && level_of[s.dp_m[p]] == ls) ++p;
+                per_phase[ls + 1].push_back({k, begin, p - begin});
+            }
+            s.dp_own[k] = p;
+        }
+        s.eg_ptr.assign(s.n_levels + 1, 0);
+        for (int l = 0; l < s.n_levels; ++l) {
+            for (const auto& it : per_phase[l]) { s.eg_k.push_back(it[0]); s.eg_begin.push_back(it[1]); s.eg_count.push_back(it[2]); }
+            s.eg_ptr[l + 1] = (int)s.eg_k.size();
+        }
     }
     // off-diagonal items per level: every U block (needs scaling), L blocks only if they gather
     s.off_ptr.assign(s.n_levels + 1, 0);

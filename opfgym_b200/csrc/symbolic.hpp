@@ -31,6 +31,12 @@ struct Symbolic {
     std::vector<int> fill_ids;                 // blocks absent from the Ybus pattern (start at zero)
     // diag k: D_k -= L~(k,m) * W(m,k), y_k -= L~(k,m) * t_m   over pairs in increasing m
     std::vector<int> dp_ptr, dp_l, dp_w, dp_m;
+    // eager gather: the pairs of pivot k whose source sits more than one level below k are applied
+    // as soon as that source level is finished (phase = source level + 1), by an item of their own;
+    // pivot k's own item starts at dp_own[k] (sources of the level right below) and inverts.
+    std::vector<int> dp_own;                   // [n]
+    std::vector<int> eg_ptr;                   // [n_levels+1] eager item ranges per diagonal phase
+    std::vector<int> eg_k, eg_begin, eg_count; // target pivot, first pair, number of pairs
     // off-diagonal work items, grouped by level of their pivot
     std::vector<int> off_ptr;                  // [n_levels+1] item ranges
     std::vector<int> off_tgt, off_piv;         // target block; pivot whose inverse scales it (U blocks) or -1 (L blocks)

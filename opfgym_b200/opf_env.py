@@ -209,6 +209,7 @@ class BatchedOpfEnv:
             self._side_done = self.xp.cuda.Event()
             self._side_kernels = self.xp.cuda.Event()
             self._ready_events = (self.xp.cuda.Event(), self.xp.cuda.Event())
+            self._results_copied = self.xp.cuda.Event()
         self._pipe = None     # step_host's look-ahead: episode k+1 already sampled, its observation on the host
         self.test = False
         self.power_flow_available = False
@@ -604,27 +605,36 @@ class BatchedOpfEnv:
             e.enable_double_buffer(3)
             pipe = self._pipe
 
-            def sample_ahead(buf, dst):
+            def sample_ahead(buf, dst, after=None):
+                """Side stream: kernels of the next episode into state buffer `buf`; then (once the
+                event `after` has passed -- the copy engine serves requests in order, and the
+                small per-step results must not queue behind 58 MB) its observation to `dst`."""
                 cur = e.cur
                 e.select(buf)
                 with xp.cuda.stream(self._side):
                     self._side.wait_event(self._main_done)
                     self._begin_episode()
-                    obs_to_host(dst)
-                    ready = self._ready_events[dst is h["obs"]]
-                    ready.record(self._side)
                 e.select(cur)
-                return ready
+
+                def copy():
+                    with xp.cuda.stream(self._side):
+                        if after is not None:
+                            self._side.wait_event(after)
+                        obs_to_host(dst)
+                        ready = self._ready_events[dst is h["obs"]]
+                        ready.record(self._side)
+                    return ready
+                return copy
 
             self._main_done.record(main)               # buffers of finished episodes are free from here on
             if pipe is None:                           # first call after reset: episode k+1 is not there yet
                 nxt = (e.cur + 1) % 3
-                pipe = dict(buf=nxt, obs="obs", ready=sample_ahead(nxt, h["obs"]))
+                pipe = dict(buf=nxt, obs="obs", ready=sample_ahead(nxt, h["obs"])())
             e.actions.copy_(src, non_blocking=True)    # this step's own work goes to the GPU first
             e.step(final_obs=True)
             free = 3 - e.cur - pipe["buf"]             # the buffer of the episode before this one
             other = "obs_alt" if pipe["obs"] == "obs" else "obs"
-            ahead = dict(buf=free, obs=other, ready=sample_ahead(free, h[other]))
+            copy_ahead = sample_ahead(free, h[other], after=self._results_copied)
         else:
             e.actions.copy_(src, non_blocking=True)
             e.step(final_obs=True)
@@ -636,6 +646,8 @@ class BatchedOpfEnv:
         h["cost"].copy_(e.cost, non_blocking=True)
         h["converged"].copy_(e.converged, non_blocking=True)
         if self._prefetch:
+            self._results_copied.record(main)
+            ahead = dict(buf=free, obs=other, ready=copy_ahead())
             main.synchronize()                         # the caller needs the results to act
             pipe["ready"].synchronize()                # (sent during the previous call)
             obs_now = h[pipe["obs"]]

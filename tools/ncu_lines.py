@@ -40,20 +40,26 @@ stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
 body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
 if len(body) != len(lines):
     print(f"warning: {len(body)} ncu rows vs {len(lines)} nvdisasm instructions", file=sys.stderr)
-agg = collections.defaultdict(lambda: [0, 0, 0, collections.Counter()])
-ti = ts = 0
+agg = collections.defaultdict(lambda: [0, 0, 0, collections.Counter(), 0, 0])
+ti = ts = tw = 0
+wf_i = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
+wfi_i = hdr.index("L1 Wavefronts Shared Ideal") if "L1 Wavefronts Shared Ideal" in hdr else None
+sort_key = os.environ.get("NCU_SORT", "samples")      # samples | wavefronts | inst
 for r, (f, ln, txt) in zip(body, lines):
     n = int(r[ci["Instructions Executed"]] or 0)
     s = int(r[ci["# Samples"]] or 0)
     th = int(r[ci["Thread Instructions Executed"]] or 0)
     a = agg[(f, ln)]
     a[0] += n; a[1] += s; a[2] += th
+    if wf_i is not None:
+        w = int(r[wf_i] or 0); a[4] += w; tw += w
+        a[5] += int(r[wfi_i] or 0) if wfi_i is not None else 0
     for i in stall_cols:
         v = r[i]
         if v and v != "0":
             a[3][hdr[i]] += int(v)
     ti += n; ts += s
-print(f"total warp-instructions {ti}  samples {ts}")
+print(f"total warp-instructions {ti}  samples {ts}  shared-memory wavefronts {tw}")
 src_cache = {}
 def src(f, ln):
     for base in ("opfgym_b200/csrc", "include"):
@@ -64,7 +70,9 @@ def src(f, ln):
             L = src_cache[p]
             return L[ln - 1].strip()[:90] if 0 < ln <= len(L) else ""
     return ""
-for (f, ln), (n, s, th, st) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+order = {"samples": 1, "inst": 0, "wavefronts": 4}[sort_key]
+for (f, ln), (n, s, th, st, w, wi) in sorted(agg.items(), key=lambda kv: -kv[1][order])[:top]:
     lanes = th / n if n else 0
     tops = ",".join(f"{k[6:]}:{v}" for k, v in st.most_common(3))
-    print(f"{s/ts*100:5.1f}%smp {n/ti*100:5.1f}%inst lanes={lanes:4.1f} {f}:{ln:<4} {src(f, ln)}   [{tops}]")
+    wf = f" {w/tw*100:5.1f}%wf(x{w/wi:.2f})" if tw and wi else (f" {w/tw*100:5.1f}%wf" if tw else "")
+    print(f"{s/ts*100:5.1f}%smp {n/ti*100:5.1f}%inst{wf} lanes={lanes:4.1f} {f}:{ln:<4} {src(f, ln)}   [{tops}]")
