@@ -11,4 +11,11 @@ for cls, n in ((envs.VoltageControl, 40), (envs.EcoDispatch, 12), (envs.LoadShed
     torch.cuda.synchronize()
     assert out[4]["converged"].all()
     env.close()
+    # unfused reset sequence, host-buffer step (three state buffers, side-stream look-ahead)
+    env = cls(num_envs=n, fused_reset=False, **kw)
+    env.reset(seed=2)
+    for _ in range(3):
+        out = env.step_host(torch.rand(n, env.single_action_space.shape[0]).numpy())
+    assert out[4]["converged"].all()
+    env.close()
 print("sanitizer run ok")
