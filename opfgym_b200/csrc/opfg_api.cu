@@ -128,12 +128,7 @@ struct OpfgGrid {
     template <class T>
     const T* tab2(const std::vector<T>& v) { return tab2(v.data(), v.size()); }
     std::vector<double> consts_host;
-    const double* score_consts = nullptr;
-    const double* score_br_y = nullptr;
-    const int *score_br_f = nullptr, *score_br_t = nullptr;
-    int score_envs_per_cta = 1;
     int score_threads = 32;
-    size_t score_env_bytes = 0;
 
     template <class T>
     const T* up(const std::vector<T>& v) {
@@ -464,54 +459,6 @@ __global__ void __launch_bounds__(256) k_fp64_probe(int iters, double* out) {
     }
     const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
-}
-
-// Kernel 5, persistent multi-environment form: scoring tables AND each environment's state row are
-// staged in shared memory (one coalesced sweep in, results + observation out), so the many small
-// reference-chasing reads of constraints / costs / observation gather never leave the SM.
-template <int T>
-__global__ void __launch_bounds__(1024) k_score_multi(GridDev g, OpfgBatch B, int E, int env_doubles,
-                                                     const double* consts, const double* br_y, const int* br_f,
-                                                     const int* br_t) {
-    extern __shared__ __align__(16) double sm[];
-    {
-        const int4* src = reinterpret_cast<const int4*>(g.tab2_base);
-        int4* dst = reinterpret_cast<int4*>(sm);
-        for (int i = threadIdx.x; i < g.tab2_bytes / 16; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const char* sbase = reinterpret_cast<const char*>(sm);
-    g.consts = consts; g.br_y = const_cast<double*>(br_y); g.br_f = br_f; g.br_t = br_t;
-#define OPFG_REBASE2(field) g.field = (decltype(g.field))(sbase + (reinterpret_cast<const char*>(g.field) - g.tab2_base))
-    OPFG_REBASE2(pp_lookup); OPFG_REBASE2(br_loading_slot); OPFG_REBASE2(br_flow_slot); OPFG_REBASE2(rate_f); OPFG_REBASE2(rate_t);
-    OPFG_REBASE2(gen_bus); OPFG_REBASE2(gen_q_share); OPFG_REBASE2(gen_p_slot); OPFG_REBASE2(gen_q_slot);
-    OPFG_REBASE2(con_ptr); OPFG_REBASE2(con_value); OPFG_REBASE2(con_value_scale); OPFG_REBASE2(con_min); OPFG_REBASE2(con_max);
-    OPFG_REBASE2(con_bound_mul); OPFG_REBASE2(con_autoscale); OPFG_REBASE2(con_worst); OPFG_REBASE2(con_pfactor);
-    OPFG_REBASE2(con_ppower); OPFG_REBASE2(con_pcount);
-    OPFG_REBASE2(poly_p); OPFG_REBASE2(poly_q); OPFG_REBASE2(poly_p_mul); OPFG_REBASE2(poly_q_mul); OPFG_REBASE2(poly_coef);
-    OPFG_REBASE2(pwl_v); OPFG_REBASE2(pwl_v_mul); OPFG_REBASE2(pwl_seg); OPFG_REBASE2(obs_ref);
-    if (g.obs_ptr) OPFG_REBASE2(obs_ptr);
-    OPFG_REBASE2(consts); OPFG_REBASE2(br_y); OPFG_REBASE2(br_f); OPFG_REBASE2(br_t);
-#undef OPFG_REBASE2
-    const int e_local = threadIdx.x / T, tid = threadIdx.x % T;
-    double* mine = sm + g.tab2_bytes / 8 + (size_t)e_local * env_doubles;
-    double* row = mine;                                           // [n_state] staged state row
-    double* scratch = mine + g.n_state + (g.n_state & 1);
-    Ctx<T> cx{tid, scratch + score_smem_doubles(g.nb, g.nbr, T) - 2 * (T / 32 + 1), 1 + e_local};
-    for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
-        double* Sg = B.state + env * (int64_t)g.n_state;
-        if (B.converged[env]) {
-            const double2* src = reinterpret_cast<const double2*>(Sg);
-            double2* dst = reinterpret_cast<double2*>(row);
-            for (int i = tid; i < g.n_state / 2; i += T) dst[i] = src[i];
-        }
-        cx.sync();
-        env_score(g, cx, scratch, B, env, (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr, row);
-        cx.sync();
-        if (B.converged[env])
-            for (int i = g.n_inputs + tid; i < g.n_state; i += T) Sg[i] = row[i];
-        cx.sync();
-    }
 }
 
 // staged view of the grid for k_pf_multi: table pointers -> byte offsets in the arena
@@ -904,11 +851,6 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
         for (int i = 0, n = sc->obs_ptr ? sc->obs_ptr[sc->n_obs] : sc->n_obs; i < n; ++i)
             G->obs_ref_max = std::max(G->obs_ref_max, sc->obs_ref[i]);
         d.obs_ptr = sc->obs_ptr ? G->tab2(sc->obs_ptr, sc->n_obs + 1) : nullptr;
-        // copies of the grid tables that the branch-flow part of kernel 5 reads
-        G->score_consts = G->tab2(G->consts_host);
-        G->score_br_y = G->tab2((const double*)d.br_y, 8 * (size_t)nbr, true);
-        G->score_br_f = G->tab2(d.br_f, nbr, true);
-        G->score_br_t = G->tab2(d.br_t, nbr, true);
         d.tab2_base = G->tab2_base;
         d.tab2_bytes = (int)((G->tab2_used + 15) & ~size_t(15));
         d.n_inputs = sc->n_inputs;
@@ -920,20 +862,10 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
         for (int gI = 0; gI < ng; ++gI) cells += (sc->gen_p_slot[gI] >= 0) + (sc->gen_q_slot[gI] >= 0);
         G->n_result_cells = cells;
         G->flops_score = 60.0 * nbr + 30.0 * d.nb + 10.0 * n_el + 14.0 * d.n_poly + 20.0 * d.n_pwl * d.n_pwl_seg + 40.0;
-        {   // multi-environment CTAs for kernel 5: tables + the state row staged in shared memory
-            // one warp per environment on small grids: reductions are pure shuffles, no named barriers
+        {   // one warp per environment on small grids: reductions are pure shuffles, no barriers
             int T = (d.nb + nbr <= 600) ? 32 : d.threads;
             if (const char* tv = getenv("OPFG_SCORE_THREADS")) T = atoi(tv);
             G->score_threads = T;
-            const size_t env_doubles = score_smem_doubles(d.nb, nbr, T) + (size_t)d.n_state + 2;
-            G->score_env_bytes = (env_doubles * 8 + 31) & ~size_t(31);
-            int E = (int)((227 * 1024 - (size_t)d.tab2_bytes) / G->score_env_bytes);
-            const int cap = T == 32 ? 1024 / T : std::min(15, 1024 / T);
-            E = std::min(E, cap);
-            if (const char* ev = getenv("OPFG_SCORE_ENVS_PER_CTA")) E = std::min(atoi(ev), cap);
-            if (!getenv("OPFG_SCORE_ENVS_PER_CTA")) E = 1;   // measured: no faster than one CTA per environment
-            if (E < 2 || (d.n_state & 1) || (size_t)d.tab2_bytes * 3 > 227 * 1024) E = 1;
-            G->score_envs_per_cta = E;
         }
         G->has_scoring = true;
         return 0;
@@ -1129,20 +1061,7 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             cudaFuncSetAttribute(k_score<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_smem = smem;
         }
-        if (G->score_envs_per_cta > 1) {
-            const int E = G->score_envs_per_cta;
-            const size_t smem_multi = G->d.tab2_bytes + (size_t)E * G->score_env_bytes;
-            static size_t attr_multi = 48 * 1024;
-            if (smem_multi > attr_multi) {
-                cudaFuncSetAttribute(k_score_multi<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                attr_multi = smem_multi;
-            }
-            int n_sm = 148;
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
-            const int64_t groups = (B->n_env + E - 1) / E;
-            k_score_multi<TT><<<(unsigned)std::min<int64_t>(groups, n_sm), TT * E, smem_multi, (cudaStream_t)stream>>>(
-                G->d, *B, E, (int)(G->score_env_bytes / 8), G->score_consts, G->score_br_y, G->score_br_f, G->score_br_t);
-        } else if (TT == 32) {
+        if (TT == 32) {
             static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
             const size_t per_env = (smem + 15) & ~size_t(15);
             static size_t attr_w = 48 * 1024;
