@@ -274,8 +274,8 @@ def gpu_arm(args):
     flops_per_step = info["flops_per_iter"] * (iters + 1) + info["flops_score"]
     roofline = {"bound": "hbm", "kernel": "k_pf (fused mismatch + Jacobian + block sparse LU + solves)",
                 "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                "peak_source": peak_src, "traffic": 82.65e6 * B / 32768,
-                "traffic_source": "profiles/r01a_k_pf_metrics.csv (dram read+write per launch of 32768 envs)",
+                "peak_source": peak_src, "traffic": 84.16e6 * B / 32768,
+                "traffic_source": "profiles/r01i_k_pf_multi_metrics.csv (dram read 64.12 + write 20.04 MB per launch of 32768 envs)",
                 "kernel_ms": pf_ms, "kernel_share_of_step": pf_ms / (ms_total / args.steps),
                 "algorithmic_bytes_per_env_step": bytes_per_step,
                 "note": "latency-bound FP64 sparse path: HBM fraction is small by construction "
