@@ -328,8 +328,6 @@ class BatchedOpfEnv:
         """opf_env.py:286-315: N(mean, std*diff) around the profile mean, clipped to the data range.
         (As in the reference, `relative_std` ends up multiplied by the range twice, A.6 quirk 9.)"""
         assert sample_new, "Currently only implemented for sample_new=True"
-        if truncated:
-            raise NotImplementedError("truncated normal (scipy.stats.truncnorm) is not on the device")
         xp = self.xp
         if "_normal" not in self._sample_cache:
             plan = []
@@ -351,15 +349,24 @@ class BatchedOpfEnv:
             n = cols.shape[0]
             u = xp.empty((self.num_envs, 2 * n), dtype=xp.float64, device=self.device)
             self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
-            z = xp.sqrt(-2.0 * xp.log1p(-u[:, :n])) * xp.cos(2.0 * np.pi * u[:, n:])    # Box-Muller
-            self.engine.state[:, cols] = xp.minimum(xp.maximum(mean + sigma * z, lo), hi)
+            if truncated:
+                # scipy.stats.truncnorm.rvs(a, b, loc, scale) as the reference calls it (:307-308): a
+                # standard normal truncated to [a, b] = [min, max] -- bounds in STANDARD units, A.6
+                # quirk -- then shifted and scaled; inverse-CDF sampling from one uniform per value
+                std_normal = xp.distributions.Normal(0.0, 1.0)
+                ca, cb = std_normal.cdf(lo), std_normal.cdf(hi)
+                p = (ca + u[:, :n] * (cb - ca)).clamp(1e-300, 1.0 - 1e-16)
+                self.engine.state[:, cols] = mean + sigma * xp.special.ndtri(p)
+            else:
+                z = xp.sqrt(-2.0 * xp.log1p(-u[:, :n])) * xp.cos(2.0 * np.pi * u[:, n:])    # Box-Muller
+                self.engine.state[:, cols] = xp.minimum(xp.maximum(mean + sigma * z, lo), hi)
 
     def _set_simbench_state(self, step=None, test=False, noise_factor=0.1,
                             noise_distribution="uniform", interpolate_steps=False, **_):
         """opf_env.py:317-372: gather one profile row per environment, multiply by
         uniform noise, clip to the profile range, store unscaled."""
-        if noise_distribution != "uniform" or interpolate_steps:
-            raise NotImplementedError("normal noise / interpolation: SURVEY.md §8(f) rank 3")
+        if noise_distribution not in ("uniform", "normal"):
+            raise NotImplementedError(f"noise distribution {noise_distribution!r}")
         xp, B = self.xp, self.num_envs
         if not hasattr(self, "_prof_dev"):
             self._prof_dev = {}
@@ -391,10 +398,22 @@ class BatchedOpfEnv:
             if not self.program.layout.has(unit_type, column):
                 continue
             values = table[step_idx]
-            if noise_factor:
+            if interpolate_steps:                      # :349-353 random point between two profile steps
+                nxt = table[(step_idx + 1).clamp(max=table.shape[0] - 1)]
+                if "r" not in locals():
+                    r = xp.empty((B, 1), dtype=xp.float64, device=self.device)
+                    self.engine.philox_uniform(r, self.seed, self.first_env, self._next_stream())
+                values = values * r + nxt * (1.0 - r)
+            if noise_factor and noise_distribution == "uniform":
                 u = xp.empty(values.shape, dtype=xp.float64, device=self.device)
                 self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
                 values = values * (u * (2.0 * noise_factor) + (1.0 - noise_factor))
+            elif noise_factor:                         # :360-363 N(data, |data| * noise_factor)
+                n = values.shape[1]
+                u = xp.empty((B, 2 * n), dtype=xp.float64, device=self.device)
+                self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
+                z = xp.sqrt(-2.0 * xp.log1p(-u[:, :n])) * xp.cos(2.0 * np.pi * u[:, n:])
+                values = values + values.abs() * noise_factor * z
             self.col(unit_type, column).copy_(xp.minimum(xp.maximum(values, pmin), pmax))
 
     def _sampling(self, step=None, test=False, sample_new=True, **kwargs):

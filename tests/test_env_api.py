@@ -357,3 +357,43 @@ def test_fused_reset_equals_kernel_sequence(cls_name, kw):
     of, _ = fused.reset(seed=77)
     op, _ = plain.reset(seed=77)
     assert torch.equal(of, op)
+
+
+def test_truncated_normal_noise_and_interpolation_samplers():
+    """opf_env.py:304-308 (truncnorm), :349-353 (interpolate_steps), :360-363 (normal noise)."""
+    env = make(n=2048, train_data="normal_around_mean", n_profile_steps=4 * 672,
+               sampling_params={"relative_std": 0.3, "truncated": True})
+    env.reset(seed=3)
+    df = env.net.load
+    lo = torch.as_tensor((df.min_min_p_mw / df.scaling).to_numpy().copy())
+    hi = torch.as_tensor((df.max_max_p_mw / df.scaling).to_numpy().copy())
+    mean = torch.as_tensor(df.mean_p_mw.to_numpy().copy())
+    sigma = 0.3 * (hi - lo) ** 2
+    z = (env.col("load", "p_mw") - mean) / sigma
+    # scipy's truncnorm(a, b, loc, scale): the STANDARD normal is truncated to [a, b] = [min, max]
+    assert (z >= lo - 1e-9).all() and (z <= hi + 1e-9).all()
+    wide = (hi - lo) > 0.05
+    assert z[:, wide].std() > 0
+
+    noisy = make(n=4096, train_data="noisy_simbench", n_profile_steps=4 * 672,
+                 sampling_params={"noise_factor": 0.05, "noise_distribution": "normal"})
+    noisy.reset(seed=4, options={"step": 100})
+    prof = noisy.profiles[("load", "p_mw")]
+    data = torch.as_tensor(prof.to_numpy()[100].copy())
+    pmin, pmax = torch.as_tensor(prof.to_numpy().min(axis=0)), torch.as_tensor(prof.to_numpy().max(axis=0))
+    p = noisy.col("load", "p_mw")
+    assert (p >= pmin - 1e-12).all() and (p <= pmax + 1e-12).all()
+    col = int(torch.argmax(torch.minimum(data - pmin, pmax - data) / data.abs().clamp_min(1e-9)))   # least clipped
+    rel = (p[:, col] - data[col]) / data[col].abs()
+    assert abs(float(rel.mean())) < 0.01 and abs(float(rel.std()) - 0.05) < 0.01
+
+    inter = make(n=64, train_data="noisy_simbench", n_profile_steps=4 * 672,
+                 sampling_params={"noise_factor": 0.0, "interpolate_steps": True})
+    inter.reset(seed=5, options={"step": 200})
+    a, b = (torch.as_tensor(prof.to_numpy()[k].copy()) for k in (200, 201))
+    p = inter.col("load", "p_mw")
+    lo2, hi2 = torch.minimum(a, b), torch.maximum(a, b)
+    assert (p >= lo2 - 1e-12).all() and (p <= hi2 + 1e-12).all()
+    moved = (a - b).abs() > 1e-9
+    r = ((p - b) / (a - b))[:, moved]                  # data*r + next*(1-r): one r per environment
+    assert torch.allclose(r, r[:, :1].expand_as(r), atol=1e-9) and r[:, 0].std() > 0.1
