@@ -383,20 +383,23 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // Persistent multi-environment CTA: E environments of T threads each share ONE shared-memory copy of
 // the schedule / Ybus tables (their reads are on the critical path of every level); each environment
 // group synchronises on its own named barrier and walks through its share of the batch.
-// Tables of the staged arena, in allocation order: the LU schedule ("hot", always staged) and the
-// Ybus / DC / q-limit tables ("cold", staged only when they fit beside the environments).
-#define OPFG_HOT_TABLES(X)                                                                              \
-    X(bus_of_int) X(type_int) X(vm0_int) X(va0_int) X(level_ptr) X(fill_ids) X(diag_mode) X(dp_ptr) X(dp_pack) \
-    X(dp_own) X(eg_ptr) X(eg_item) X(off_ptr) X(off_hdr) X(op_pack) X(up_ptr) X(up_pack)
-#define OPFG_COLD_TABLES(X) X(y_ptr) X(y_meta) X(y_val) X(dc_val) X(dc_rhs0) X(qlim_bus) X(qlim_min) X(qlim_max)
+// Tables of the staged arena, in allocation order: the LU schedule ("hot", always staged), the Ybus
+// tables ("warm", read in every iteration) and the start-value / DC-factor / q-limit tables ("cold",
+// read once per solve).  STAGE = 0 stages the hot part, 1 hot + warm, 2 everything -- whichever lets
+// the most environments share an SM.
+#define OPFG_HOT_TABLES(X)                                                                      \
+    X(bus_of_int) X(type_int) X(level_ptr) X(fill_ids) X(diag_mode) X(dp_ptr) X(dp_pack) X(dp_own) \
+    X(eg_ptr) X(eg_item) X(off_ptr) X(off_hdr) X(op_pack) X(up_ptr) X(up_pack)
+#define OPFG_WARM_TABLES(X) X(y_ptr) X(y_meta) X(y_val)
+#define OPFG_COLD_TABLES(X) X(vm0_int) X(va0_int) X(dc_val) X(dc_rhs0) X(qlim_bus) X(qlim_min) X(qlim_max)
 
 // The kernel receives a view of GridDev in which every staged table pointer holds its BYTE OFFSET in
 // the arena (staged_view below).  Adding the offset to the shared-memory base is one instruction and
 // leaves the address space known to the compiler (LDS instead of generic loads); the earlier
 // "if the pointer lies in the staged range, move it" form was re-evaluated at the use sites under
 // the 96-register cap and cost 10 % of the kernel's instructions.
-template <int T, bool FUSED, bool COLD>
-__global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles, int stages) {
+template <int T, int STAGE>
+__global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
     {
         const int4* src = reinterpret_cast<const int4*>(g.tab_base);
@@ -407,29 +410,17 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     char* sbase = reinterpret_cast<char*>(sm);
 #define OPFG_REBASE(field) g.field = reinterpret_cast<decltype(g.field)>(sbase + (unsigned)reinterpret_cast<size_t>(g.field));
     OPFG_HOT_TABLES(OPFG_REBASE)
-    if (COLD) { OPFG_COLD_TABLES(OPFG_REBASE) }
+    if (STAGE >= 1) { OPFG_WARM_TABLES(OPFG_REBASE) }
+    if (STAGE >= 2) { OPFG_COLD_TABLES(OPFG_REBASE) }
 #undef OPFG_REBASE
     const int e_local = threadIdx.x / T;
     double* mine = sm + g.tab_staged_bytes / 8 + (size_t)e_local * env_doubles;
     Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 1 + e_local};
-    // stages: bit 0 = kernel 1 in front, bit 1 = kernel 5 behind (opfg_step's fused form: the
-    // HBM-latency-bound row work of one environment overlaps the shared-memory-bound elimination of
-    // the other E-1 environments of the CTA instead of running as separate launches)
     for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
-        double* yv = B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr;
-        if (FUSED && (stages & 1)) {
-            env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
-                         B.sbus + env * (int64_t)g.nb * 2, yv,
-                         B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0);
-            cx.sync();
-        }
-        env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2, g.n_dyn > 0 ? yv : nullptr,
+        env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
+                     (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
                      B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
         cx.sync();
-        if (FUSED && (stages & 2)) {
-            env_score(g, cx, mine, B, env, g.n_dyn > 0 ? yv : nullptr, B.state + env * (int64_t)g.n_state);
-            cx.sync();
-        }
     }
 }
 template <int T>
@@ -462,11 +453,12 @@ __global__ void __launch_bounds__(256) k_fp64_probe(int iters, double* out) {
 }
 
 // staged view of the grid for k_pf_multi: table pointers -> byte offsets in the arena
-static GridDev staged_view(const GridDev& d, bool cold) {
+static GridDev staged_view(const GridDev& d, int stage) {
     GridDev view = d;
 #define OPFG_TO_OFFSET(field) view.field = reinterpret_cast<decltype(view.field)>((size_t)(reinterpret_cast<const char*>(d.field) - d.tab_base));
     OPFG_HOT_TABLES(OPFG_TO_OFFSET)
-    if (cold) { OPFG_COLD_TABLES(OPFG_TO_OFFSET) }
+    if (stage >= 1) { OPFG_WARM_TABLES(OPFG_TO_OFFSET) }
+    if (stage >= 2) { OPFG_COLD_TABLES(OPFG_TO_OFFSET) }
 #undef OPFG_TO_OFFSET
     return view;
 }
@@ -581,7 +573,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                        4 * (s.op_l.size() + s.up_w.size() + s.fill_ids.size()) + 24 * s.y_col.size() +
                        8 * (size_t)s.n_blocks + 16 * (size_t)s.n_levels + 64 * 32);
         d.bus_of_int = G->tab(s.bus_of_int); d.int_of_bus = G->up(s.int_of_bus);
-        d.type_int = G->tab(type_int); d.vm0_int = G->tab(vm0); d.va0_int = G->tab(va0);
+        d.type_int = G->tab(type_int);
         d.level_ptr = G->tab(s.level_ptr); d.fill_ids = G->tab(s.fill_ids);
         if (s.n_blocks >= 65535 || nb >= 65535) { delete G; return fail("grid too large for 16-bit schedule ids (%d blocks)", s.n_blocks); }
         {   // pack the schedule into 16-bit ids (halves the L1 footprint of the shared tables)
@@ -641,6 +633,8 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         d.br_y = (double*)G->up(std::vector<double>(8 * (size_t)nbr, 0.0));
         double* y_val = G->tab(std::vector<double>(2 * s.y_col.size(), 0.0));
         d.y_val = y_val;
+        d.tab_warm_bytes = (int)((G->tab_used + 15) & ~size_t(15));   // tables read in every iteration end here
+        d.vm0_int = G->tab(vm0); d.va0_int = G->tab(va0);              // start values, DC factor, q-limits: once per solve
 
         // DC start: scalar factor of B' on the same schedule + constant part of its rhs
         std::vector<double> dc_val, dc_rhs0(s.n, 0.0);
@@ -686,14 +680,16 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
             const size_t budget = 227 * 1024;
-            const int cap = std::min(15, 640 / T);    // named barriers 1..15; k_pf_multi is bounded to 640 threads
-            d.tab_staged_bytes = d.tab_bytes;
-            int E = std::min((int)((budget - d.tab_bytes) / G->smem_pf), cap);
-            if (E < 2 || (size_t)d.tab_bytes * 3 > budget) {
-                // large grid: stage only the LU schedule; the Ybus / DC tables stay in global memory
-                d.tab_staged_bytes = d.tab_hot_bytes;
-                E = (size_t)d.tab_hot_bytes < budget ? std::min((int)((budget - d.tab_hot_bytes) / G->smem_pf), cap) : 1;
-            }
+            const int cap = std::min(15, 768 / T);    // named barriers 1..15; k_pf_multi is bounded to 768 threads
+            // stage everything if at least two environments still fit; else the tables read in every
+            // iteration; else only the LU schedule.  (Measured on the 122-bus grid: an 11th environment
+            // bought by leaving the start-value / DC tables in global memory is a net loss, 1.46 vs 1.41 ms.)
+            auto fit = [&](int bytes) { return (size_t)bytes < budget ? std::min((int)((budget - bytes) / G->smem_pf), cap) : 0; };
+            const int sizes[3] = {d.tab_hot_bytes, d.tab_warm_bytes, d.tab_bytes};
+            int level = fit(sizes[2]) >= 2 ? 2 : ((fit(sizes[1]) >= 2 && (size_t)sizes[1] * 3 <= budget) ? 1 : 0);
+            if (const char* sv = getenv("OPFG_STAGE")) level = std::max(0, std::min(2, atoi(sv)));
+            d.tab_staged_bytes = sizes[level];
+            int E = fit(sizes[level]);
             if (const char* ev = getenv("OPFG_ENVS_PER_CTA")) E = std::min(atoi(ev), cap);
             if (E < 2) E = 1;
             G->envs_per_cta = E;
@@ -976,11 +972,7 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     return 0;
 }
 
-static int pf_launch(const OpfgGrid* G, const OpfgBatch* B, void* stream, int stages);
-
-int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) { return pf_launch(G, B, stream, 0); }
-
-static int pf_launch(const OpfgGrid* G, const OpfgBatch* B, void* stream, int stages) {
+int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (!G || !B) return fail("null argument");
     if (!B->sbus || !B->vm || !B->va || !B->converged || !B->iterations) return fail("opfg_pf_solve needs sbus, vm, va, converged, iterations");
     if (B->n_env <= 0) return 0;
@@ -1012,23 +1004,21 @@ static int pf_launch(const OpfgGrid* G, const OpfgBatch* B, void* stream, int st
             const size_t smem_multi = G->d.tab_staged_bytes + (size_t)E * smem;
             static size_t attr_multi = 48 * 1024;
             if (smem_multi > attr_multi) {
-                cudaFuncSetAttribute(k_pf_multi<TT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                cudaFuncSetAttribute(k_pf_multi<TT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                cudaFuncSetAttribute(k_pf_multi<TT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                cudaFuncSetAttribute(k_pf_multi<TT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                cudaFuncSetAttribute(k_pf_multi<TT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
                 attr_multi = smem_multi;
             }
             int n_sm = 148;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
             const int64_t groups = (B->n_env + E - 1) / E;
             const unsigned grid = (unsigned)std::min<int64_t>(groups, n_sm);
-            const bool cold = G->d.tab_staged_bytes == G->d.tab_bytes;
-            const GridDev view = staged_view(G->d, cold);
+            const int stage = G->d.tab_staged_bytes == G->d.tab_bytes ? 2 : (G->d.tab_staged_bytes == G->d.tab_warm_bytes ? 1 : 0);
+            const GridDev view = staged_view(G->d, stage);
             const int env_doubles = (int)(smem / 8);
-            if (stages && cold) k_pf_multi<TT, true, true><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, stages);
-            else if (stages) k_pf_multi<TT, true, false><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, stages);
-            else if (cold) k_pf_multi<TT, false, true><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, 0);
-            else k_pf_multi<TT, false, false><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles, 0);
+            if (stage == 2) k_pf_multi<TT, 2><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
+            else if (stage == 1) k_pf_multi<TT, 1><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
+            else k_pf_multi<TT, 0><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
         } else {
             k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
         }
@@ -1291,16 +1281,6 @@ int opfg_fp64_probe(int32_t n_blocks, int32_t iters, double* out, void* stream) 
 }
 
 int opfg_step(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
-#ifndef OPFG_HOSTSIM
-    // fused form: kernels 1 and/or 5 inside the persistent power-flow kernel (OPFG_FUSED_STEP bit mask)
-    static const int fused = getenv("OPFG_FUSED_STEP") ? atoi(getenv("OPFG_FUSED_STEP")) : 0;
-    if (fused && G && B && G->envs_per_cta > 1 && G->has_scoring && G->has_assembly && B->state && B->sbus) {
-        int rc = 0;
-        if (!(fused & 1) && (rc = opfg_assemble(G, B, stream))) return rc;
-        if ((rc = pf_launch(G, B, stream, fused & 3))) return rc;
-        return (fused & 2) ? 0 : opfg_score(G, B, stream);
-    }
-#endif
     int rc = opfg_assemble(G, B, stream);
     if (rc) return rc;
     rc = opfg_pf_solve(G, B, stream);

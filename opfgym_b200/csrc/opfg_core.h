@@ -109,7 +109,8 @@ struct GridDev {
     const int* obs_ptr;      // nullptr: one ref per observation
     const char* tab_base;              // contiguous arena holding the power-flow tables
     int tab_bytes;
-    int tab_hot_bytes;                 // prefix holding the LU schedule (the Ybus / DC tables follow)
+    int tab_hot_bytes;                 // prefix holding the LU schedule
+    int tab_warm_bytes;                // ... plus the Ybus tables (start values / DC factor / q-limits follow)
     int tab_staged_bytes;              // how much of the arena the multi-environment kernel stages
     const char* tab2_base;             // contiguous arena holding the scoring tables
     int tab2_bytes;
