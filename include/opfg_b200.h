@@ -195,6 +195,9 @@ typedef struct {
                                        opf_env.py:497-498: -costs - initial_obj)                    */
     int32_t absolute_actions;       /* != 0: kernel 1 ignores act_diff_step (reset applies the initial
                                        action as an absolute set-point, opf_env.py:207)             */
+    int32_t stats_slots;            /* > 1: `stats` is [stats_slots][OPFG_N_STATS] and environment b adds to
+                                       row b % stats_slots (the caller sums the rows); thousands of
+                                       atomics on ONE row serialise in L2 (0.11 ms of kernel 5 at 32 768 envs) */
 } OpfgBatch;
 
 enum { OPFG_STAT_N = 0, OPFG_STAT_CONVERGED = 1, OPFG_STAT_VALID = 2, OPFG_STAT_SUM_REWARD = 3,

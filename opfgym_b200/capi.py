@@ -90,7 +90,7 @@ class Batch(C.Structure):
                 ("actions", "state", "sbus", "vm", "va", "converged", "iterations",
                  "reward", "objective", "penalty", "cost", "valids", "violations",
                  "penalties", "obs_f32", "obs_f64", "stats", "yval", "bry", "objective_offset")] + [
-                ("absolute_actions", C.c_int32)]
+                ("absolute_actions", C.c_int32), ("stats_slots", C.c_int32)]
 
 
 # every symbol include/opfg_b200.h declares: name -> (restype, argtypes)

@@ -741,6 +741,7 @@ OPFG_HD double pwl_cost(const GridDev& g, const double* S, int row, double v) {
 template <class C>
 OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBatch& B, int64_t env,
                        const double* yval_env, double* S) {
+    double* const stats = B.stats ? B.stats + (B.stats_slots > 1 ? (size_t)((uint64_t)env % (uint32_t)B.stats_slots) * OPFG_N_STATS : 0) : nullptr;
     const int T = cx.nthreads();
     const int nb = g.nb, nbr = g.nbr, nc = g.n_con;
     ScoreSmem s;
@@ -771,9 +772,9 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
             if (B.penalty) B.penalty[env] = (double)nc;
             if (B.cost) B.cost[env] = NAN;
 #ifdef OPFG_DEVICE_BUILD
-            if (B.stats) atomicAdd(B.stats + OPFG_STAT_N, 1.0);
+            if (stats) atomicAdd(stats + OPFG_STAT_N, 1.0);
 #else
-            if (B.stats) B.stats[OPFG_STAT_N] += 1.0;
+            if (stats) stats[OPFG_STAT_N] += 1.0;
 #endif
         }
         return;
@@ -882,9 +883,9 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
             if (B.violations) B.violations[env * nc + c] = viol;
             if (B.penalties) B.penalties[env * nc + c] = pen;
 #ifdef OPFG_DEVICE_BUILD
-            if (B.stats && cnt > 0 && c < OPFG_N_STATS - OPFG_STAT_VIOLATED0) atomicAdd(B.stats + OPFG_STAT_VIOLATED0 + c, 1.0);
+            if (stats && cnt > 0 && c < OPFG_N_STATS - OPFG_STAT_VIOLATED0) atomicAdd(stats + OPFG_STAT_VIOLATED0 + c, 1.0);
 #else
-            if (B.stats && cnt > 0 && c < OPFG_N_STATS - OPFG_STAT_VIOLATED0) B.stats[OPFG_STAT_VIOLATED0 + c] += 1.0;
+            if (stats && cnt > 0 && c < OPFG_N_STATS - OPFG_STAT_VIOLATED0) stats[OPFG_STAT_VIOLATED0 + c] += 1.0;
 #endif
         }
     }
@@ -919,23 +920,23 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         if (B.objective) B.objective[env] = objective;
         if (B.penalty) B.penalty[env] = pen_sum;
         if (B.cost) B.cost[env] = cost;
-        if (B.stats) {
+        if (stats) {
             const double it = B.iterations ? (double)B.iterations[env] : 0.0;
 #ifdef OPFG_DEVICE_BUILD
-            atomicAdd(B.stats + OPFG_STAT_N, 1.0);
-            atomicAdd(B.stats + OPFG_STAT_CONVERGED, 1.0);
-            if (all_valid) atomicAdd(B.stats + OPFG_STAT_VALID, 1.0);
-            atomicAdd(B.stats + OPFG_STAT_SUM_REWARD, r);
-            atomicAdd(B.stats + OPFG_STAT_SUM_REWARD_SQ, r * r);
-            atomicAdd(B.stats + OPFG_STAT_SUM_OBJECTIVE, objective);
-            atomicAdd(B.stats + OPFG_STAT_SUM_PENALTY, pen_sum);
-            atomicAdd(B.stats + OPFG_STAT_SUM_ITERS, it);
+            atomicAdd(stats + OPFG_STAT_N, 1.0);
+            atomicAdd(stats + OPFG_STAT_CONVERGED, 1.0);
+            if (all_valid) atomicAdd(stats + OPFG_STAT_VALID, 1.0);
+            atomicAdd(stats + OPFG_STAT_SUM_REWARD, r);
+            atomicAdd(stats + OPFG_STAT_SUM_REWARD_SQ, r * r);
+            atomicAdd(stats + OPFG_STAT_SUM_OBJECTIVE, objective);
+            atomicAdd(stats + OPFG_STAT_SUM_PENALTY, pen_sum);
+            atomicAdd(stats + OPFG_STAT_SUM_ITERS, it);
 #else
-            B.stats[OPFG_STAT_N] += 1.0; B.stats[OPFG_STAT_CONVERGED] += 1.0;
-            if (all_valid) B.stats[OPFG_STAT_VALID] += 1.0;
-            B.stats[OPFG_STAT_SUM_REWARD] += r; B.stats[OPFG_STAT_SUM_REWARD_SQ] += r * r;
-            B.stats[OPFG_STAT_SUM_OBJECTIVE] += objective; B.stats[OPFG_STAT_SUM_PENALTY] += pen_sum;
-            B.stats[OPFG_STAT_SUM_ITERS] += it;
+            stats[OPFG_STAT_N] += 1.0; stats[OPFG_STAT_CONVERGED] += 1.0;
+            if (all_valid) stats[OPFG_STAT_VALID] += 1.0;
+            stats[OPFG_STAT_SUM_REWARD] += r; stats[OPFG_STAT_SUM_REWARD_SQ] += r * r;
+            stats[OPFG_STAT_SUM_OBJECTIVE] += objective; stats[OPFG_STAT_SUM_PENALTY] += pen_sum;
+            stats[OPFG_STAT_SUM_ITERS] += it;
 #endif
         }
     }

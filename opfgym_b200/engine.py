@@ -27,6 +27,7 @@ class ResetPlan:
 
 
 class Engine:
+    STATS_SLOTS = 128
     def __init__(self, program: EnvProgram, num_envs: int, device=None,
                  tolerance_mva: float = 1e-8, max_iteration: int = 10, init: str = "dc",
                  enforce_q_lims: bool = True, threads_per_env: int = 0, ordering: int = 0,
@@ -71,7 +72,8 @@ class Engine:
         self.obs = self._zeros((B, max(program.n_obs, 1)), obs_dtype)
         # observation of the episode that just ended (kernel 5) vs. of the freshly reset one
         self.obs_final = self._zeros((B, max(program.n_obs, 1)), obs_dtype)
-        self.stats = self._zeros((capi.N_STATS,), "float64")
+        # per-environment statistics are added to row (env % STATS_SLOTS): atomics on one row serialise
+        self.stats = self._zeros((self.STATS_SLOTS, capi.N_STATS), "float64")
         self.n_constraints = nc
         self.objective_offset = None     # set by enable_objective_offset() (diff_objective)
         self.yval = self.bry = None
@@ -88,7 +90,7 @@ class Engine:
             penalties=self._ptr(self.penalties),
             obs_f32=self._ptr(self.obs) if obs_dtype == "float32" else None,
             obs_f64=self._ptr(self.obs) if obs_dtype == "float64" else None,
-            stats=self._ptr(self.stats),
+            stats=self._ptr(self.stats), stats_slots=self.STATS_SLOTS,
             yval=self._ptr(self.yval) if self.yval is not None else None,
             bry=self._ptr(self.bry) if self.bry is not None else None)
         self.batch_final = capi.Batch.from_buffer_copy(self.batch)

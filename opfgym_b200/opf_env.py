@@ -782,7 +782,7 @@ class BatchedOpfEnv:
     def episode_statistics(self, reduce: bool = True) -> dict:
         """Running sums accumulated by kernel 5's epilogue; with ``torch.distributed``
         initialised they are all-reduced over ranks (the path's only collective)."""
-        stats = self.engine.stats.clone()
+        stats = self.engine.stats.sum(dim=0)
         if reduce and self.world_size > 1:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
