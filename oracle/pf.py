@@ -12,7 +12,9 @@ result-table formulas.
 
 PARITY STATUS: **unpinned at the pandapower boundary** -- the reference's own
 tests hold no power-flow number.  What *is* pinned
-(tests/test_oracle_pf.py): the WSCC 9-bus textbook solution (App. C.4), the
+(tests/test_oracle_pf.py, tests/test_ieee14.py): the WSCC 9-bus textbook solution
+(App. C.4), the published IEEE 14-bus solution (off-nominal taps, bus shunt, five
+PV buses; voltages, angles, generator P/Q and losses to the printed precision), the
 2-bus closed form (App. C.5), and the invariants of App. C.6.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
