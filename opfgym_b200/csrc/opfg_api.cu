@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // "if the pointer lies in the staged range, move it" form was re-evaluated at the use sites under
 // the 96-register cap and cost 10 % of the kernel's instructions.
 template <int T, int STAGE>
-__global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
+__global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
     {
         const int4* src = reinterpret_cast<const int4*>(g.tab_base);
@@ -680,7 +680,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
             const size_t budget = 227 * 1024;
-            const int cap = std::min(15, 768 / T);    // named barriers 1..15; k_pf_multi is bounded to 768 threads
+            const int cap = std::min(15, 640 / T);    // named barriers 1..15; k_pf_multi is bounded to 640 threads
             // stage everything if at least two environments still fit; else the tables read in every
             // iteration; else only the LU schedule.  (Measured on the 122-bus grid: an 11th environment
             // bought by leaving the start-value / DC tables in global memory is a net loss, 1.46 vs 1.41 ms.)
