@@ -459,6 +459,10 @@ class BatchedOpfEnv:
             self.seed = int(seed)
             self._episode = 0
         options = options or {}
+        if self._pipe is not None:
+            # step_host's look-ahead may still be sampling / copying on the side stream, and it shares
+            # the device observation buffer with the reset below
+            self.xp.cuda.current_stream(self.device).wait_stream(self._side)
         self._pipe = None
         self.test = options.get("test", False)
         self._begin_episode(options.get("step", None))
