@@ -398,8 +398,12 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // leaves the address space known to the compiler (LDS instead of generic loads); the earlier
 // "if the pointer lies in the staged range, move it" form was re-evaluated at the use sites under
 // the 96-register cap and cost 10 % of the kernel's instructions.
-template <int T, int STAGE>
+// MODE = STAGE | (4 if the Ybus values are per environment): with the shared table the compiler
+// knows the values live in shared memory (LDS instead of generic loads in the row pass).
+template <int T, int MODE>
 __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
+    constexpr int STAGE = MODE & 3;
+    constexpr bool DYN = (MODE & 4) != 0;
     extern __shared__ __align__(16) double sm[];
     {
         const int4* src = reinterpret_cast<const int4*>(g.tab_base);
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E,
     Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 1 + e_local};
     for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
         env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
-                     (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+                     DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
                      B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
         cx.sync();
     }
@@ -1004,9 +1008,8 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             const size_t smem_multi = G->d.tab_staged_bytes + (size_t)E * smem;
             static size_t attr_multi = 48 * 1024;
             if (smem_multi > attr_multi) {
-                cudaFuncSetAttribute(k_pf_multi<TT, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                cudaFuncSetAttribute(k_pf_multi<TT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                cudaFuncSetAttribute(k_pf_multi<TT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+                for (auto* fn : {k_pf_multi<TT, 0>, k_pf_multi<TT, 1>, k_pf_multi<TT, 2>, k_pf_multi<TT, 4>, k_pf_multi<TT, 5>, k_pf_multi<TT, 6>})
+                    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
                 attr_multi = smem_multi;
             }
             int n_sm = 148;
@@ -1016,9 +1019,16 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             const int stage = G->d.tab_staged_bytes == G->d.tab_bytes ? 2 : (G->d.tab_staged_bytes == G->d.tab_warm_bytes ? 1 : 0);
             const GridDev view = staged_view(G->d, stage);
             const int env_doubles = (int)(smem / 8);
-            if (stage == 2) k_pf_multi<TT, 2><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
-            else if (stage == 1) k_pf_multi<TT, 1><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
-            else k_pf_multi<TT, 0><<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
+            void (*fn)(GridDev, OpfgBatch, int, int) = nullptr;
+            switch (stage | ((G->d.n_dyn > 0 && B->yval) ? 4 : 0)) {
+                case 0: fn = k_pf_multi<TT, 0>; break;
+                case 1: fn = k_pf_multi<TT, 1>; break;
+                case 2: fn = k_pf_multi<TT, 2>; break;
+                case 4: fn = k_pf_multi<TT, 4>; break;
+                case 5: fn = k_pf_multi<TT, 5>; break;
+                default: fn = k_pf_multi<TT, 6>; break;
+            }
+            fn<<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
         } else {
             k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
         }
