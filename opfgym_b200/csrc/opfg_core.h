@@ -389,7 +389,6 @@ OPFG_HD double row_mismatch(const GridDev& g, const PfSmem& s, const double* yv,
     D2 sp = ldg2(sbus + 2 * g.bus_of_int[i]);                // P, Q set-point (global, issued early)
     const D2 vi = ld2(s.vri + 2 * i);
     const bool pq = s.bus_type[i] == OPFG_PQ;
-    if (s.qadd) sp.y += s.qadd[i];
     const int e0 = g.y_ptr[i], e1 = g.y_ptr[i + 1];
     double ir = 0, ii = 0, dr = 0, di = 0;
     for (int e = e0; e < e1; ++e) {
@@ -407,6 +406,7 @@ OPFG_HD double row_mismatch(const GridDev& g, const PfSmem& s, const double* yv,
         st2(s.lu + 2 * i, -Q + ai, (ar + P) * inv_vmi);
         st2(s.lu1 + 2 * i, pq ? P - ar : 0.0, pq ? (ai + Q) * inv_vmi : 1.0);
     }
+    if (s.qadd) sp.y += s.qadd[i];                           // first use of the set-point: its L2 latency hid behind the row
     const double dp = P - sp.x, dq = pq ? Q - sp.y : 0.0;
     st2(s.rhs + 2 * i, -dp, -dq);
     if (dp != dp || dq != dq) return NAN;
