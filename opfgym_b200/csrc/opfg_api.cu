@@ -306,6 +306,53 @@ __global__ void __launch_bounds__(T) k_reset(GridDev g, OpfgBatch B, const Reset
         for (int i = threadIdx.x; i < n_row; i += T) Sg[i] = sm[i];
     }
 }
+// DC start for all environments: va[b, bus_of_int[i]] = theta0[i] + sum_bus P[b, bus] * Binv_t[bus, i]
+// with P[b, bus] = Re Sbus[b, bus] (rows of Binv_t for reference buses are zero).  64 environments x 64
+// angles per CTA, 4 x 4 per thread, K in steps of 16 buses through shared memory, 128-bit shared loads
+// (plain FP64 FMA: 1 Gflop is no work for tensor cores).
+__global__ void __launch_bounds__(256) k_dc_start(GridDev g, OpfgBatch B) {
+    __shared__ __align__(16) double p_s[16][64 + 2];     // [bus][env]
+    __shared__ __align__(16) double b_s[16][64];         // [bus][i]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // angle group, environment group
+    const int64_t env0 = (int64_t)blockIdx.x * 64;
+    const int i0 = blockIdx.y * 64, n = g.n, nb = g.nb;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < nb; k0 += 16) {
+        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+            const int e = idx >> 4, kk = idx & 15;                   // consecutive threads: consecutive buses of one env
+            const int64_t env = env0 + e;
+            p_s[kk][e] = (k0 + kk < nb && env < B.n_env) ? B.sbus[(env * nb + k0 + kk) * 2] : 0.0;
+        }
+        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+            const int kk = idx >> 6, i = idx & 63;
+            b_s[kk][i] = g.dc_binv_t[(size_t)(k0 + kk) * g.dc_ld + i0 + i];   // zero padded to 16 x 64 tiles
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const double2 p01 = *reinterpret_cast<const double2*>(&p_s[kk][ty * 4]);
+            const double2 p23 = *reinterpret_cast<const double2*>(&p_s[kk][ty * 4 + 2]);
+            const double2 b01 = *reinterpret_cast<const double2*>(&b_s[kk][tx * 4]);
+            const double2 b23 = *reinterpret_cast<const double2*>(&b_s[kk][tx * 4 + 2]);
+            const double pv[4] = {p01.x, p01.y, p23.x, p23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][c] = fma(pv[a], bv[c], acc[a][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int64_t env = env0 + ty * 4 + a;
+        if (env >= B.n_env) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + tx * 4 + c;
+            if (i < n) B.va[env * nb + g.bus_of_int[i]] = acc[a][c] + g.dc_theta0[i];
+        }
+    }
+}
 __global__ void k_branch_y(GridDev g) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < g.nbr) branch_admittance(g.br_param + 6 * (size_t)l, g.br_y + 8 * (size_t)l);
@@ -658,6 +705,42 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         }
         for (int k = 0; k < s.n; ++k) dc_rhs0[k] -= ysh[2 * s.bus_of_int[k]];
         d.dc_val = G->tab(dc_val); d.dc_rhs0 = G->tab(dc_rhs0);
+        d.dc_pre = 0; d.dc_binv_t = nullptr; d.dc_theta0 = nullptr; d.dc_ld = 0;
+        // Dense pre-pass for the DC start: theta = B'^-1 (P + rhs0) for ALL environments as one FP64
+        // GEMM (k_dc_start).  Inside the persistent kernel the same solve is 2 x levels barrier phases
+        // of dependent scalar work: 17 % of the kernel on the 372-bus grid, where two environments
+        // share an SM and the latency is exposed -- the pre-pass takes 11 % off the solve there.  On
+        // the 122-bus grid (ten environments per SM) the in-kernel solve costs 0.14 ms and the GEMM
+        // 0.17 ms, so it stays in the kernel.  B'^-1 is built column by column with the same factor.
+        const bool dc_prepass = getenv("OPFG_DC_PREPASS") ? atoi(getenv("OPFG_DC_PREPASS")) != 0
+                              : pf_smem_doubles(s.n_blocks, s.n, nb, T, 0) * sizeof(double) * 4 > 227 * 1024;
+        if (desc->init_dc && s.n > 0 && dc_prepass) {
+            const int n = s.n, ld = (n + 63) / 64 * 64, kp = (nb + 15) / 16 * 16;   // rows: ppc bus order (coalesced P reads)
+            std::vector<double> binv_t((size_t)kp * ld, 0.0), x(n), theta0(n, 0.0);
+            auto solve = [&](std::vector<double>& v) {
+                for (int l = 0; l < s.n_levels; ++l)
+                    for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) {
+                        double y = v[k];
+                        for (int p = s.dp_ptr[k]; p < s.dp_ptr[k + 1]; ++p) y = std::fma(-dc_val[s.dp_l[p]], v[s.dp_m[p]], y);
+                        v[k] = y * dc_val[k];
+                    }
+                for (int l = s.n_levels - 1; l >= 0; --l)
+                    for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) {
+                        double xx = v[k];
+                        for (int p = s.up_ptr[k]; p < s.up_ptr[k + 1]; ++p) xx = std::fma(-dc_val[s.up_w[p]], v[s.up_j[p]], xx);
+                        v[k] = xx;
+                    }
+            };
+            for (int c = 0; c < n; ++c) {
+                std::fill(x.begin(), x.end(), 0.0);
+                x[c] = 1.0;
+                solve(x);                                  // column c of B'^-1
+                for (int i = 0; i < n; ++i) binv_t[(size_t)s.bus_of_int[c] * ld + i] = x[i];
+            }
+            theta0 = dc_rhs0;
+            solve(theta0);
+            d.dc_binv_t = G->up(binv_t); d.dc_theta0 = G->up(theta0); d.dc_ld = ld; d.dc_pre = 1;
+        }
         {   // enforce_q_lims tables: one entry per PV bus with an active limit
             std::vector<int> qb;
             std::vector<double> qmn, qmx;
@@ -984,11 +1067,25 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     (void)stream;
     Ctx<1> cx;
     std::vector<double> sm(pf_smem_doubles(G->d.n_blocks, G->d.n, G->d.nb, 32, G->d.n_qlim));
+    if (G->d.dc_pre) {   // the dense DC pre-pass, as a plain loop
+        const GridDev& d = G->d;
+        for (int64_t env = 0; env < B->n_env; ++env)
+            for (int i = 0; i < d.n; ++i) {
+                double acc = 0.0;
+                for (int bus = 0; bus < d.nb; ++bus)
+                    acc = std::fma(B->sbus[(env * d.nb + bus) * 2], d.dc_binv_t[(size_t)bus * d.dc_ld + i], acc);
+                B->va[env * d.nb + d.bus_of_int[i]] = acc + d.dc_theta0[i];
+            }
+    }
     for (int64_t env = 0; env < B->n_env; ++env)
         env_pf_solve(G->d, cx, sm.data(), B->sbus + env * (int64_t)G->d.nb * 2,
                      (G->d.n_dyn > 0 && B->yval) ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr, B->vm + env * (int64_t)G->d.nb,
                      B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);
 #else
+    if (G->d.dc_pre) {
+        k_dc_start<<<dim3((unsigned)((B->n_env + 63) / 64), (unsigned)((G->d.n + 63) / 64)), 256, 0, (cudaStream_t)stream>>>(G->d, *B);
+        ++g_launches;
+    }
     const size_t smem = G->smem_pf;
     OPFG_DISPATCH_T(G->d.threads, {
         static size_t attr_smem = 48 * 1024;

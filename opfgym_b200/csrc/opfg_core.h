@@ -30,6 +30,10 @@ struct GridDev {
     int threads;
     double base_mva, tol;
     int max_iter, init_dc;
+    int dc_pre;                        // 1: the DC start comes from the dense pre-pass (k_dc_start) through va
+    const double* dc_binv_t;           // [n_pad_k][n_pad_i] transpose of B'^-1, zero padded (pre-pass)
+    const double* dc_theta0;           // [n] B'^-1 * (constant part of the DC right-hand side)
+    int dc_ld;                         // leading dimension (n_pad_i) of dc_binv_t
     // numbering
     const int* bus_of_int;
     const int* int_of_bus;
@@ -556,7 +560,7 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         cx.sync();
     }
 
-    if (g.init_dc) {   // pandapower init='dc': B' theta = P on the shared, pre-factorised B'
+    if (g.init_dc && !g.dc_pre) {   // pandapower init='dc': B' theta = P on the shared, pre-factorised B'
         for (int k = cx.tid; k < n; k += T) s.rhs[k] = sbus[2 * g.bus_of_int[k]] + g.dc_rhs0[k];
         cx.sync();
         for (int l = 0; l < g.n_levels; ++l) {
@@ -587,10 +591,10 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
     // output buffers (L2) instead of shared memory, which buys one more resident environment per SM
     for (int i = cx.tid; i < nb; i += T) {
         const double vm = g.vm0_int[i];
-        const double va = (g.init_dc && i < n) ? s.rhs[i] : g.va0_int[i];
+        const int bus = g.bus_of_int[i];
+        const double va = (g.init_dc && i < n) ? (g.dc_pre ? va_out[bus] : s.rhs[i]) : g.va0_int[i];
         double sn, cs;
         sincos(va, &sn, &cs);
-        const int bus = g.bus_of_int[i];
         vm_out[bus] = vm; va_out[bus] = va; s.ivm[i] = 1.0 / vm;
         st2(s.vri + 2 * i, vm * cs, vm * sn);
     }
