@@ -317,17 +317,29 @@ __global__ void __launch_bounds__(256) k_dc_start(GridDev g, OpfgBatch B) {
     const int64_t env0 = (int64_t)blockIdx.x * 64;
     const int i0 = blockIdx.y * 64, n = g.n, nb = g.nb;
     double acc[4][4] = {};
-    for (int k0 = 0; k0 < nb; k0 += 16) {
-        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
+    // the next 16-bus slice travels from global memory to registers while the current one is multiplied
+    double p_next[4], b_next[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = threadIdx.x + 256 * r;
             const int e = idx >> 4, kk = idx & 15;                   // consecutive threads: consecutive buses of one env
             const int64_t env = env0 + e;
-            p_s[kk][e] = (k0 + kk < nb && env < B.n_env) ? B.sbus[(env * nb + k0 + kk) * 2] : 0.0;
+            p_next[r] = (k0 + kk < nb && env < B.n_env) ? B.sbus[(env * nb + k0 + kk) * 2] : 0.0;
+            const int kb = idx >> 6, i = idx & 63;
+            b_next[r] = g.dc_binv_t[(size_t)(k0 + kb) * g.dc_ld + i0 + i];   // zero padded to 16 x 64 tiles
         }
-        for (int idx = threadIdx.x; idx < 16 * 64; idx += 256) {
-            const int kk = idx >> 6, i = idx & 63;
-            b_s[kk][i] = g.dc_binv_t[(size_t)(k0 + kk) * g.dc_ld + i0 + i];   // zero padded to 16 x 64 tiles
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < nb; k0 += 16) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = threadIdx.x + 256 * r;
+            p_s[idx & 15][idx >> 4] = p_next[r];
+            b_s[idx >> 6][idx & 63] = b_next[r];
         }
         __syncthreads();
+        if (k0 + 16 < nb) fetch(k0 + 16);
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
             const double2 p01 = *reinterpret_cast<const double2*>(&p_s[kk][ty * 4]);
