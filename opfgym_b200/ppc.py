@@ -90,6 +90,10 @@ class _DSU:
                 self.p[ra] = rb
 
 
+UNSUPPORTED_TABLES = ("trafo3w", "impedance", "ward", "xward", "dcline", "motor", "asymmetric_load",
+                      "asymmetric_sgen", "svc", "tcsc", "ssc", "vsc")
+
+
 class PpcBuilder:
     """Topology is analysed once; ``build(net)`` refreshes the numeric columns.
 
@@ -105,6 +109,14 @@ class PpcBuilder:
         self.calculate_voltage_angles = calculate_voltage_angles
         self.trafo_model = trafo_model
         self.dynamic_service = tuple(dynamic_service)
+        # element tables of pandapower that this builder does not model: fail loudly instead of
+        # solving a different network (adapter coverage)
+        for table in UNSUPPORTED_TABLES:
+            df = getattr(net, table, None) if not isinstance(net, dict) else net.get(table)
+            if df is not None and len(df):
+                raise NotImplementedError(
+                    f"net.{table} has {len(df)} rows: {table} elements are not modelled by PpcBuilder "
+                    "(supported: bus, line, trafo, switch, load, sgen, storage, gen, ext_grid, shunt)")
         self._analyse(net)
 
     # ------------------------------------------------------------------ topology

@@ -44,3 +44,15 @@ def test_adapter_on_hostsim():
 @pytest.mark.gpu
 def test_adapter_on_cuda(cuda_lib):
     _check({})
+
+
+def test_unsupported_element_tables_fail_loudly():
+    """A pandapower net with element types the builder does not model must not be solved silently."""
+    import pandas as pd
+    from opfgym_b200 import grids
+    from opfgym_b200.ppc import PpcBuilder
+    net, _ = grids.build_simbench_net("1-MV-semiurb--1-sw", n_profile_steps=96)
+    PpcBuilder(net)                                            # fine as it is
+    net.trafo3w = pd.DataFrame({"hv_bus": [0], "mv_bus": [1], "lv_bus": [2]})
+    with pytest.raises(NotImplementedError, match="trafo3w"):
+        PpcBuilder(net)
