@@ -286,7 +286,7 @@ def gpu_arm(args):
     achieved_gbs = bytes_per_step * B / (pf_ms * 1e-3) / 1e9
     iters = stats["mean_iterations"]
     flops_per_step = info["flops_per_iter"] * (iters + 1) + info["flops_score"]
-    roofline = {"bound": "hbm", "kernel": "k_pf (fused mismatch + Jacobian + block sparse LU + solves)",
+    roofline = {"bound": "hbm", "kernel": "opfg_pf_solve = k_dc_start (DC-start GEMM, ~5 %) + k_pf_multi (fused mismatch + Jacobian + block sparse LU + solves)",
                 "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "peak_source": peak_src, "traffic": 84.16e6 * B / 32768,
                 "traffic_source": "profiles/r01i_k_pf_multi_metrics.csv (dram read 64.12 + write 20.04 MB per launch of 32768 envs)",

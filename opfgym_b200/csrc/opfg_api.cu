@@ -307,60 +307,77 @@ __global__ void __launch_bounds__(T) k_reset(GridDev g, OpfgBatch B, const Reset
     }
 }
 // DC start for all environments: va[b, bus_of_int[i]] = theta0[i] + sum_bus P[b, bus] * Binv_t[bus, i]
-// with P[b, bus] = Re Sbus[b, bus] (rows of Binv_t for reference buses are zero).  64 environments x 64
-// angles per CTA, 4 x 4 per thread, K in steps of 16 buses through shared memory, 128-bit shared loads
-// (plain FP64 FMA: 1 Gflop is no work for tensor cores).
-__global__ void __launch_bounds__(256) k_dc_start(GridDev g, OpfgBatch B) {
-    __shared__ __align__(16) double p_s[16][64 + 2];     // [bus][env]
-    __shared__ __align__(16) double b_s[16][64];         // [bus][i]
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // angle group, environment group
-    const int64_t env0 = (int64_t)blockIdx.x * 64;
+// with P[b, bus] = Re Sbus[b, bus] (rows of Binv_t for reference buses are zero).  128 environments x
+// 64 angles per CTA, 8 x 4 per thread (32 FMAs per 8 shared-memory wavefronts: FP64-pipe bound, the
+// 4 x 4 version was bound by the LSU pipe), K in slices of 16 buses through a three-stage cp.async
+// pipeline.  Plain FP64 FMA: 1 Gflop is no work for tensor cores.
+constexpr int DC_ENVS = 128, DC_ST = 3;
+constexpr size_t DC_SMEM = DC_ST * (16 * (DC_ENVS + 2) + 16 * 64) * sizeof(double);
+__global__ void __launch_bounds__(256, 2) k_dc_start(GridDev g, OpfgBatch B) {
+    extern __shared__ __align__(16) double dc_sm[];
+    double (*p_s)[16][DC_ENVS + 2] = reinterpret_cast<double (*)[16][DC_ENVS + 2]>(dc_sm);                   // [stage][bus][env]
+    double (*b_s)[16][64] = reinterpret_cast<double (*)[16][64]>(dc_sm + DC_ST * 16 * (DC_ENVS + 2));     // [stage][bus][i]
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;          // angles tx + 16 c, environments 8 ty + a
+    const int64_t env0 = (int64_t)blockIdx.x * DC_ENVS;
     const int i0 = blockIdx.y * 64, n = g.n, nb = g.nb;
-    double acc[4][4] = {};
-    // the next 16-bus slice travels from global memory to registers while the current one is multiplied
-    double p_next[4], b_next[4];
-    auto fetch = [&](int k0) {
+    const int n_slices = (nb + 15) / 16;
+    const int pe = threadIdx.x >> 4, pk = threadIdx.x & 15;         // P: environments pe + 16 r, bus pk
+    const int bk = threadIdx.x >> 6, bi = threadIdx.x & 63;         // B: buses bk + 4 r, angle bi
+    auto issue = [&](int slice) {
+        if (slice < n_slices) {
+            const int st = slice % DC_ST, k0 = slice * 16;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int idx = threadIdx.x + 256 * r;
-            const int e = idx >> 4, kk = idx & 15;                   // consecutive threads: consecutive buses of one env
-            const int64_t env = env0 + e;
-            p_next[r] = (k0 + kk < nb && env < B.n_env) ? B.sbus[(env * nb + k0 + kk) * 2] : 0.0;
-            const int kb = idx >> 6, i = idx & 63;
-            b_next[r] = g.dc_binv_t[(size_t)(k0 + kb) * g.dc_ld + i0 + i];   // zero padded to 16 x 64 tiles
+            for (int r = 0; r < DC_ENVS / 16; ++r) {
+                const int e = pe + 16 * r;
+                const int64_t env = env0 + e;
+                double* dst = &p_s[st][pk][e];
+                if (k0 + pk < nb && env < B.n_env) {
+                    const double* src = B.sbus + (env * nb + k0 + pk) * 2;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src));
+                } else {
+                    *dst = 0.0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double* bsrc = g.dc_binv_t + (size_t)(k0 + bk + 4 * r) * g.dc_ld + i0 + bi;   // zero padded tiles
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(&b_s[st][bk + 4 * r][bi])), "l"(bsrc));
+            }
         }
+        asm volatile("cp.async.commit_group;");
     };
-    fetch(0);
-    for (int k0 = 0; k0 < nb; k0 += 16) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int idx = threadIdx.x + 256 * r;
-            p_s[idx & 15][idx >> 4] = p_next[r];
-            b_s[idx >> 6][idx & 63] = b_next[r];
-        }
+    double acc[8][4] = {};
+    issue(0);
+    issue(1);
+    for (int slice = 0; slice < n_slices; ++slice) {
+        issue(slice + 2);
+        asm volatile("cp.async.wait_group 2;");
         __syncthreads();
-        if (k0 + 16 < nb) fetch(k0 + 16);
-#pragma unroll
+        const int st = slice % DC_ST;
+#pragma unroll 4
         for (int kk = 0; kk < 16; ++kk) {
-            const double2 p01 = *reinterpret_cast<const double2*>(&p_s[kk][ty * 4]);
-            const double2 p23 = *reinterpret_cast<const double2*>(&p_s[kk][ty * 4 + 2]);
-            const double2 b01 = *reinterpret_cast<const double2*>(&b_s[kk][tx * 4]);
-            const double2 b23 = *reinterpret_cast<const double2*>(&b_s[kk][tx * 4 + 2]);
-            const double pv[4] = {p01.x, p01.y, p23.x, p23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+            double pv[8];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int h = 0; h < 4; ++h) {
+                const double2 t = *reinterpret_cast<const double2*>(&p_s[st][kk][ty * 8 + 2 * h]);
+                pv[2 * h] = t.x; pv[2 * h + 1] = t.y;
+            }
+            // angles tx, tx+16, tx+32, tx+48: the 16 lanes of a row read 128 contiguous bytes per load
+            const double bv[4] = {b_s[st][kk][tx], b_s[st][kk][tx + 16], b_s[st][kk][tx + 32], b_s[st][kk][tx + 48]};
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[a][c] = fma(pv[a], bv[c], acc[a][c]);
         }
-        __syncthreads();
+        __syncthreads();                                    // the stage is refilled by the next issue()
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int64_t env = env0 + ty * 4 + a;
+    for (int a = 0; a < 8; ++a) {
+        const int64_t env = env0 + ty * 8 + a;
         if (env >= B.n_env) continue;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const int i = i0 + tx * 4 + c;
+            const int i = i0 + tx + 16 * c;
             if (i < n) B.va[env * nb + g.bus_of_int[i]] = acc[a][c] + g.dc_theta0[i];
         }
     }
@@ -720,12 +737,10 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         d.dc_pre = 0; d.dc_binv_t = nullptr; d.dc_theta0 = nullptr; d.dc_ld = 0;
         // Dense pre-pass for the DC start: theta = B'^-1 (P + rhs0) for ALL environments as one FP64
         // GEMM (k_dc_start).  Inside the persistent kernel the same solve is 2 x levels barrier phases
-        // of dependent scalar work: 17 % of the kernel on the 372-bus grid, where two environments
-        // share an SM and the latency is exposed -- the pre-pass takes 11 % off the solve there.  On
-        // the 122-bus grid (ten environments per SM) the in-kernel solve costs 0.14 ms and the GEMM
-        // 0.17 ms, so it stays in the kernel.  B'^-1 is built column by column with the same factor.
-        const bool dc_prepass = getenv("OPFG_DC_PREPASS") ? atoi(getenv("OPFG_DC_PREPASS")) != 0
-                              : pf_smem_doubles(s.n_blocks, s.n, nb, T, 0) * sizeof(double) * 4 > 227 * 1024;
+        // of dependent scalar work: 17 % of the kernel on the 372-bus grid (4.47 -> 3.82 ms with the
+        // pre-pass), 11 % on the 122-bus grid (0.14 ms in the kernel against 0.08 ms for the GEMM).
+        // B'^-1 is built column by column with the factor the kernel would use.
+        const bool dc_prepass = getenv("OPFG_DC_PREPASS") ? atoi(getenv("OPFG_DC_PREPASS")) != 0 : true;
         if (desc->init_dc && s.n > 0 && dc_prepass) {
             const int n = s.n, ld = (n + 63) / 64 * 64, kp = (nb + 15) / 16 * 16;   // rows: ppc bus order (coalesced P reads)
             std::vector<double> binv_t((size_t)kp * ld, 0.0), x(n), theta0(n, 0.0);
@@ -1095,7 +1110,9 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                      B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);
 #else
     if (G->d.dc_pre) {
-        k_dc_start<<<dim3((unsigned)((B->n_env + 63) / 64), (unsigned)((G->d.n + 63) / 64)), 256, 0, (cudaStream_t)stream>>>(G->d, *B);
+        static bool dc_attr = false;
+        if (!dc_attr) { cudaFuncSetAttribute(k_dc_start, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM); dc_attr = true; }
+        k_dc_start<<<dim3((unsigned)((B->n_env + DC_ENVS - 1) / DC_ENVS), (unsigned)((G->d.n + 63) / 64)), 256, DC_SMEM, (cudaStream_t)stream>>>(G->d, *B);
         ++g_launches;
     }
     const size_t smem = G->smem_pf;
