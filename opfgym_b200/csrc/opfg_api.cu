@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // MODE = STAGE | (4 if the Ybus values are per environment): with the shared table the compiler
 // knows the values live in shared memory (LDS instead of generic loads in the row pass).
 template <int T, int MODE>
-__global__ void __launch_bounds__(640) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
+__global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
     constexpr int STAGE = MODE & 3;
     constexpr bool DYN = (MODE & 4) != 0;
     extern __shared__ __align__(16) double sm[];
@@ -733,7 +733,6 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             if (t < s.n && f >= s.n) dc_rhs0[t] += b * va_ref[br.f];
         }
         for (int k = 0; k < s.n; ++k) dc_rhs0[k] -= ysh[2 * s.bus_of_int[k]];
-        d.dc_val = G->tab(dc_val); d.dc_rhs0 = G->tab(dc_rhs0);
         d.dc_pre = 0; d.dc_binv_t = nullptr; d.dc_theta0 = nullptr; d.dc_ld = 0;
         // Dense pre-pass for the DC start: theta = B'^-1 (P + rhs0) for ALL environments as one FP64
         // GEMM (k_dc_start).  Inside the persistent kernel the same solve is 2 x levels barrier phases
@@ -768,6 +767,13 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             solve(theta0);
             d.dc_binv_t = G->up(binv_t); d.dc_theta0 = G->up(theta0); d.dc_ld = ld; d.dc_pre = 1;
         }
+        if (d.dc_pre) {
+            // the kernel never touches the sparse DC factor then: it stays out of the staged arena
+            // (4.6 KB on the 122-bus grid -- exactly what an 11th environment per SM was missing)
+            d.dc_val = d.dc_rhs0 = reinterpret_cast<const double*>(G->tab_base);
+        } else {
+            d.dc_val = G->tab(dc_val); d.dc_rhs0 = G->tab(dc_rhs0);
+        }
         {   // enforce_q_lims tables: one entry per PV bus with an active limit
             std::vector<int> qb;
             std::vector<double> qmn, qmx;
@@ -794,7 +800,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
             const size_t budget = 227 * 1024;
-            const int cap = std::min(15, 640 / T);    // named barriers 1..15; k_pf_multi is bounded to 640 threads
+            const int cap = std::min(15, 768 / T);    // named barriers 1..15; k_pf_multi is bounded to 768 threads
             // stage everything if at least two environments still fit; else the tables read in every
             // iteration; else only the LU schedule.  (Measured on the 122-bus grid: an 11th environment
             // bought by leaving the start-value / DC tables in global memory is a net loss, 1.46 vs 1.41 ms.)
@@ -804,7 +810,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             if (const char* sv = getenv("OPFG_STAGE")) level = std::max(0, std::min(2, atoi(sv)));
             d.tab_staged_bytes = sizes[level];
             int E = fit(sizes[level]);
-            if (const char* ev = getenv("OPFG_ENVS_PER_CTA")) E = std::min(atoi(ev), cap);
+            if (const char* ev = getenv("OPFG_ENVS_PER_CTA")) E = std::min(atoi(ev), E);   // can only lower it
             if (E < 2) E = 1;
             G->envs_per_cta = E;
         }
