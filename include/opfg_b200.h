@@ -27,6 +27,17 @@
  *   opfg_score            pfsoln/_extract_results + OpfEnv.calculate_reward opf_env.py:515-530
  *                         + OpfEnv._get_obs (kernel 5)
  *   opfg_step             OpfEnv.step                       opfgym/opf_env.py:374-419
+ *   opfg_observe          OpfEnv._get_obs after reset       opfgym/opf_env.py:218, 532-549
+ *   opfg_row_program_*    the `_sampling` overrides of the benchmark envs
+ *                         (envs/voltage_control.py:121-133, load_shedding.py:131-149, ...)
+ *   opfg_reset_plan_*,    OpfEnv.reset without a reset power flow (opf_env.py:180-220): sampler,
+ *   opfg_reset_episode    hooks, initial action, _apply_actions, _get_obs in one launch
+ *   opfg_set_dynamic_branches  pandapower's per-call branch / Ybus rebuild when trafo.tap_pos or
+ *                         *.in_service are actions or contingencies
+ *
+ * opfg_pf_solve may issue two launches: the DC start of all environments as one FP64 GEMM
+ * (B'^-1 is built at opfg_grid_create) and the persistent Newton-Raphson kernel; the `va` buffer
+ * carries the start angles between them.
  */
 #ifndef OPFG_B200_H
 #define OPFG_B200_H
