@@ -852,11 +852,13 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     double pen_sum = 0;
     bool all_valid = true;
     for (int c = 0; c < nc; ++c) {
-        double viol = 0, cnt = 0;
+        // only_worst_case_violations (constraints.py:77-80, 113-122): the worst upper-bound violation
+        // PLUS the worst lower-bound violation -- two running maxima, added after the reduction
+        double viol = 0, viol_lo = 0, cnt = 0;
         const bool worst = g.con_worst[c] != 0;
         auto test = [&](double v, double hi, double lo) {
             if (v > hi) { const double x = fabs(v - hi); viol = worst ? (x > viol ? x : viol) : viol + x; cnt += 1; }
-            if (v < lo) { const double x = fabs(v - lo); viol = worst ? (x > viol ? x : viol) : viol + x; cnt += 1; }
+            if (v < lo) { const double x = fabs(v - lo); if (worst) viol_lo = x > viol_lo ? x : viol_lo; else viol += x; cnt += 1; }
         };
         int e = g.con_ptr[c] + cx.tid;
         const int e_end = g.con_ptr[c + 1];
@@ -875,7 +877,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
                  ref_val(g, S, g.con_min[e]) * mul);
         }
         cnt = cx.block_sum(cnt);
-        viol = worst ? cx.block_max(viol) : cx.block_sum(viol);
+        viol = worst ? cx.block_max(viol) + cx.block_max(viol_lo) : cx.block_sum(viol);
         viol *= g.con_autoscale[c];
         const double pp = g.con_ppower[c];
         const double vp = pp == 1.0 ? viol : (pp == 2.0 ? viol * viol : pow(viol, pp));   // pow() is ~100 instructions

@@ -105,16 +105,52 @@ class Engine:
         self.batch_setpoints.sbus = None
         self.batch_setpoints.actions = self._ptr(self.actions_reset)
         self.batch_setpoints.absolute_actions = 1
+        self._linked = [self.batch, self.batch_final, self.batch_setpoints]   # batches that follow select()
         self._states = [self.state]
         self.cur = 0
+        self.aux = None
+        self.batch_aux = None
+        self.batch_nostats = None
 
     def enable_objective_offset(self):
         """[B] buffer subtracted from the objective in kernel 5 (``diff_objective``)."""
         if self.objective_offset is None:
             self.objective_offset = self._zeros((self.num_envs,), "float64")
-            for b in (self.batch, self.batch_final, self.batch_setpoints):
+            for b in self._linked:
                 b.objective_offset = self._ptr(self.objective_offset)
         return self.objective_offset
+
+    class _Aux:
+        pass
+
+    def enable_aux_results(self):
+        """Second set of per-step result buffers WITHOUT statistics, for power flows that are not
+        the agent's step: the reset power flow (``pf_for_obs``), contingency passes.  The buffers the
+        last ``step`` filled (and may have handed out as aliases) stay untouched, and the episode
+        statistics only count agent steps (round-1 advisor finding)."""
+        if self.aux is None:
+            a = self._Aux()
+            for name in ("converged", "iterations", "reward", "objective", "penalty", "cost",
+                         "valids", "violations", "penalties"):
+                setattr(a, name, self._zeros(tuple(getattr(self, name).shape),
+                                             str(getattr(self, name).dtype).replace("torch.", "")))
+            self.aux = a
+            self.batch_aux = capi.Batch.from_buffer_copy(self.batch)
+            for name in ("converged", "iterations", "reward", "objective", "penalty", "cost",
+                         "valids", "violations", "penalties"):
+                setattr(self.batch_aux, name, self._ptr(getattr(a, name)))
+            self.batch_aux.stats = None
+            self._linked.append(self.batch_aux)
+        return self.aux
+
+    def nostats_batch(self):
+        """The main batch without the statistics epilogue (``run_power_flow`` re-scores the current
+        state; that is not an agent step)."""
+        if self.batch_nostats is None:
+            self.batch_nostats = capi.Batch.from_buffer_copy(self.batch)
+            self.batch_nostats.stats = None
+            self._linked.append(self.batch_nostats)
+        return self.batch_nostats
 
     def enable_double_buffer(self, n: int = 2):
         """More state matrices: later episodes can be sampled while the current one is solved."""
@@ -126,7 +162,7 @@ class Engine:
         self.cur = index
         self.state = self._states[index]
         ptr = self._ptr(self.state)
-        for b in (self.batch, self.batch_final, self.batch_setpoints):
+        for b in self._linked:
             b.state = ptr
 
     # ------------------------------------------------------- device plumbing (torch)
@@ -211,11 +247,11 @@ class Engine:
             batch.absolute_actions = 1
         capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(batch), self._stream()))
 
-    def pf_solve(self):
-        capi.check(self.lib, self.lib.opfg_pf_solve(self.handle, C.byref(self.batch), self._stream()))
+    def pf_solve(self, batch=None):
+        capi.check(self.lib, self.lib.opfg_pf_solve(self.handle, C.byref(batch or self.batch), self._stream()))
 
-    def score(self):
-        capi.check(self.lib, self.lib.opfg_score(self.handle, C.byref(self.batch), self._stream()))
+    def score(self, batch=None):
+        capi.check(self.lib, self.lib.opfg_score(self.handle, C.byref(batch or self.batch), self._stream()))
 
     def observe(self):
         capi.check(self.lib, self.lib.opfg_observe(self.handle, C.byref(self.batch), self._stream()))

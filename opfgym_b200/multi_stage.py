@@ -43,12 +43,17 @@ class MultiStageBatchedOpfEnv(BatchedOpfEnv):
         self.step_in_episode.zero_()
         return out
 
+    def step_host(self, actions=None):
+        raise NotImplementedError("step_host pipelines single-step episodes; multi-stage episodes advance "
+                                  "per environment -- use step() and copy what the host needs")
+
     def step(self, actions):
         xp, e = self.xp, self.engine
         act = xp.as_tensor(actions, device=self.device)
         e.actions.copy_(act.reshape(e.actions.shape))
         e.step(final_obs=True)
         self.power_flow_available = True
+        self._results = e
         self.step_in_episode += 1
         nc = max(len(self.constraints), 1)
         info = {"valids": e.valids[:, :nc].bool(), "violations": e.violations[:, :nc].clone(),
@@ -83,8 +88,7 @@ class MultiStageBatchedOpfEnv(BatchedOpfEnv):
         e.state[:, act_cols] = xp.where(done[:, None], e.state[:, act_cols], kept)
         if self.pf_for_obs:
             e.assemble(apply_actions=False)
-            e.pf_solve()
-            e.score()
+            self._reset_power_flow()
         else:
             e.observe()
         self.step_in_episode = xp.where(done, xp.zeros_like(self.step_in_episode), self.step_in_episode)

@@ -213,6 +213,7 @@ class BatchedOpfEnv:
         self._pipe = None     # step_host's look-ahead: episode k+1 already sampled, its observation on the host
         self.test = False
         self.power_flow_available = False
+        self._results = self.engine
 
         # ---- reward function (may sample the engine for its scaling parameters) --------
         reward_function_params = reward_function_params or {}
@@ -503,15 +504,25 @@ class BatchedOpfEnv:
         if self.pf_for_obs:
             # the reference re-samples envs whose reset power flow fails (opf_env.py:209-214);
             # here such envs simply start with a NaN observation and are flagged in `converged`
-            if self.diff_objective:
-                self.engine.enable_objective_offset().zero_()
-            self.engine.pf_solve()
-            self.engine.score()
-            if self.diff_objective:      # opf_env.py:216: initial_obj = objective of the reset state
-                self.engine.objective_offset.copy_(self.engine.objective)
-            self.power_flow_available = True
+            self._reset_power_flow()
         else:
             self.engine.observe()
+
+    def _reset_power_flow(self):
+        """Power flow + scoring of the freshly reset state (opf_env.py:209-216).  It goes to the
+        engine's auxiliary result buffers without statistics: what ``step`` just returned (possibly
+        as aliases, ``copy_outputs=False``) stays intact and ``episode_statistics`` counts agent
+        steps only."""
+        e = self.engine
+        aux = e.enable_aux_results()
+        if self.diff_objective:
+            e.enable_objective_offset().zero_()
+        e.pf_solve(e.batch_aux)
+        e.score(e.batch_aux)
+        if self.diff_objective:      # opf_env.py:216: initial_obj = objective of the reset state
+            e.objective_offset.copy_(aux.objective)
+        self.power_flow_available = True
+        self._results = aux
 
     def _obs_out(self, final: bool = False):
         obs = self.engine.obs_final if final else self.engine.obs
@@ -550,10 +561,12 @@ class BatchedOpfEnv:
         self.engine.actions.copy_(act.reshape(self.engine.actions.shape))
         self.engine.step(final_obs=True)
         self.power_flow_available = True
+        self._results = e
         keep = (lambda t: t.clone()) if self.copy_outputs else (lambda t: t)
         reward = keep(e.reward)
         if self.clipped_action_penalty:
-            reward = reward - self._mean_correction(act) * self.clipped_action_penalty
+            # opf_env.py:429, 488-491: the correction is measured against the CLIPPED action
+            reward = reward - self._mean_correction(act.clamp(0.0, 1.0)) * self.clipped_action_penalty
         nc = max(len(self.constraints), 1)
         info = {"valids": e.valids[:, :nc].bool(), "violations": keep(e.violations[:, :nc]),
                 "unscaled_penalties": keep(e.penalties[:, :nc]), "cost": keep(e.cost),
@@ -662,9 +675,10 @@ class BatchedOpfEnv:
             e.actions.copy_(src, non_blocking=True)
             e.step(final_obs=True)
         self.power_flow_available = True
+        self._results = e
         reward = e.reward
         if self.clipped_action_penalty:
-            reward = reward - self._mean_correction(e.actions) * self.clipped_action_penalty
+            reward = reward - self._mean_correction(e.actions.clamp(0.0, 1.0)) * self.clipped_action_penalty
         h["reward"].copy_(reward, non_blocking=True)
         h["cost"].copy_(e.cost, non_blocking=True)
         h["converged"].copy_(e.converged, non_blocking=True)
@@ -695,11 +709,14 @@ class BatchedOpfEnv:
     # ----------------------------------------------------------------- OpfEnv-style API
     def run_power_flow(self, **kwargs):
         """opf_env.py:646-662; returns the per-environment converged mask."""
-        self.engine.assemble(apply_actions=False)   # re-scatter Sbus from the current cells
-        self.engine.pf_solve()
-        self.engine.score()
+        e = self.engine
+        e.assemble(apply_actions=False)   # re-scatter Sbus from the current cells
+        batch = e.nostats_batch()         # not an agent step: no contribution to the statistics
+        e.pf_solve(batch)
+        e.score(batch)
         self.power_flow_available = True
-        return self.engine.converged.bool()
+        self._results = e
+        return e.converged.bool()
 
     def ensure_power_flow_available(self):
         if not self.power_flow_available:
@@ -747,20 +764,21 @@ class BatchedOpfEnv:
             return self.col(table, column)[:, pos]
         return self.static(table, column)[pos]
 
+    # the getters read the results of the LAST power flow: the agent's step, or the reset power flow
     def is_state_valid(self):
         self.ensure_power_flow_available()
         nc = max(len(self.constraints), 1)
-        return self.engine.valids[:, :nc].bool().all(dim=1)
+        return self._results.valids[:, :nc].bool().all(dim=1)
 
     def get_objective(self):
         self.ensure_power_flow_available()
-        return self.engine.objective.clone()
+        return self._results.objective.clone()
 
     def calculate_violations(self):
         self.ensure_power_flow_available()
         nc = max(len(self.constraints), 1)
-        e = self.engine
-        return e.valids[:, :nc].bool(), e.violations[:, :nc], e.penalties[:, :nc]
+        r = self._results
+        return r.valids[:, :nc].bool(), r.violations[:, :nc], r.penalties[:, :nc]
 
     def sample_objective_penalty(self, num_samples: int):
         """Feeds ``reward.estimate_reward_distribution`` (reference reward.py:181-216:

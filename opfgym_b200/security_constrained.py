@@ -37,12 +37,17 @@ class SecurityConstrainedBatchedOpfEnv(BatchedOpfEnv):
         obs, reward, terminated, truncated, info = self._step_with_contingencies(actions)
         return obs, reward, terminated, truncated, info
 
+    def step_host(self, actions=None):
+        raise NotImplementedError("step_host would skip the contingency passes; use step()")
+
     def _step_with_contingencies(self, actions):
         xp, e = self.xp, self.engine
         act = xp.as_tensor(actions, device=self.device)
         e.actions.copy_(act.reshape(e.actions.shape))
         e.step(final_obs=True)
         self.power_flow_available = True
+        self._results = e
+        aux = e.enable_aux_results()      # contingency passes: scratch results, no statistics
         nc = max(len(self.constraints), 1)
         base_ok = e.converged.bool().clone()
         objective = e.objective.clone()
@@ -57,14 +62,14 @@ class SecurityConstrainedBatchedOpfEnv(BatchedOpfEnv):
                 saved = cells[:, pos].clone()
                 cells[:, pos] = 0.0
                 e.assemble(apply_actions=False)
-                e.pf_solve()
-                e.score()
-                ok = e.converged.bool()
+                e.pf_solve(e.batch_aux)
+                e.score(e.batch_aux)
+                ok = aux.converged.bool()
                 use = was_on & ok
                 fail = was_on & ~ok
-                valids = xp.where(use[:, None], valids & e.valids[:, :nc].bool(), valids)
-                violations = violations + xp.where(use[:, None], e.violations[:, :nc], 0.0)
-                penalties = penalties + xp.where(use[:, None], e.penalties[:, :nc], 0.0)
+                valids = xp.where(use[:, None], valids & aux.valids[:, :nc].bool(), valids)
+                violations = violations + xp.where(use[:, None], aux.violations[:, :nc], 0.0)
+                penalties = penalties + xp.where(use[:, None], aux.penalties[:, :nc], 0.0)
                 valids = valids & ~fail[:, None]                 # :59-64
                 violations = violations + fail[:, None] * self.not_converged_penalty
                 penalties = penalties + fail[:, None] * self.not_converged_penalty

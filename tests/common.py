@@ -28,9 +28,11 @@ class Case:
 
 
 def make_case(name="1-MV-semiurb--1-sw", n_profile_steps=672, reward=None, constraint_kwargs=None,
-              load_scaling=1.5, gen_scaling=1.3, tight=False) -> Case:
+              load_scaling=1.5, gen_scaling=1.3, tight=False, prepare=None) -> Case:
     net, _ = grids.build_simbench_net(name, n_profile_steps=n_profile_steps,
                                       load_scaling=load_scaling, gen_scaling=gen_scaling)
+    if prepare is not None:      # net tweaks before the tables are compiled (e.g. generator Q limits)
+        prepare(net)
     thr = np.sort(net.sgen.max_max_p_mw.to_numpy())[-10]
     net.sgen["controllable"] = net.sgen.max_max_p_mw >= thr
     qlim = 0.5 * net.sgen.max_max_p_mw.to_numpy()

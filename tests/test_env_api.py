@@ -397,3 +397,48 @@ def test_truncated_normal_noise_and_interpolation_samplers():
     moved = (a - b).abs() > 1e-9
     r = ((p - b) / (a - b))[:, moved]                  # data*r + next*(1-r): one r per environment
     assert torch.allclose(r, r[:, :1].expand_as(r), atol=1e-9) and r[:, 0].std() > 0.1
+
+
+def test_reset_power_flow_leaves_step_results_and_statistics_alone():
+    """Round-1 advisor finding: with a power flow in reset (add_res_obs) the auto-reset used to
+    overwrite the buffers `step` had just returned as aliases (copy_outputs=False) and to count the
+    reset-state scores in the episode statistics."""
+    outs = {}
+    for copy_outputs in (True, False):
+        env = make(add_res_obs=True, copy_outputs=copy_outputs, n=6)
+        env.reset(seed=5)
+        env.reset_statistics()
+        act = torch.rand(6, 14, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+        for _ in range(3):
+            obs, reward, term, trunc, info = env.step(act)
+        outs[copy_outputs] = (reward.clone(), info["violations"].clone(), info["cost"].clone(),
+                              info["iterations"].clone(), obs.clone())
+        stats = env.episode_statistics()
+        assert stats["steps"] == 6 * 3
+        # the getters describe the LAST power flow, which is the reset one (opf_env.py:209-216)
+        assert env.power_flow_available
+        assert not torch.equal(env.get_objective(), env.engine.objective)
+    for a, b in zip(outs[True], outs[False]):
+        assert torch.equal(a.nan_to_num(nan=-7.0), b.nan_to_num(nan=-7.0))
+
+
+def test_clipped_action_penalty_is_measured_against_the_clipped_action():
+    """opf_env.py:429, 488-491: an out-of-range action is clipped first, so it costs nothing extra."""
+    env = make(clipped_action_penalty=2.0, n=4)
+    base = make(n=4)
+    act = torch.full((4, 14), 1.5, dtype=torch.float64)
+    for e in (env, base):
+        e.reset(seed=9)
+    r1 = env.step(act)[1]
+    r0 = base.step(act)[1]
+    assert torch.allclose(r1, r0, atol=1e-12)
+
+
+def test_step_host_is_refused_where_it_would_skip_episode_logic():
+    from opfgym_b200.multi_stage import MultiStageBatchedOpfEnv
+    from opfgym_b200.security_constrained import SecurityConstrainedBatchedOpfEnv
+    assert "step_host" in MultiStageBatchedOpfEnv.__dict__ and "step_host" in SecurityConstrainedBatchedOpfEnv.__dict__
+    with pytest.raises(NotImplementedError):
+        MultiStageBatchedOpfEnv.step_host(object())
+    with pytest.raises(NotImplementedError):
+        SecurityConstrainedBatchedOpfEnv.step_host(object())
