@@ -25,7 +25,7 @@ class GridDesc(C.Structure):
                 ("branch", _dp), ("branch_cols", C.c_int32),
                 ("tol_pu", C.c_double), ("max_iter", C.c_int32), ("init_dc", C.c_int32),
                 ("enforce_q_lims", C.c_int32), ("threads_per_env", C.c_int32),
-                ("ordering", C.c_int32)]
+                ("ordering", C.c_int32), ("pf_kernel", C.c_int32)]
 
 
 class GridInfo(C.Structure):
@@ -34,7 +34,9 @@ class GridInfo(C.Structure):
                  "threads_per_env", "smem_bytes_pf", "smem_bytes_score", "n_state",
                  "n_const", "n_act", "n_obs", "n_constraints")] + \
                [(n, C.c_double) for n in
-                ("flops_per_iter", "flops_score", "lu_flops", "bytes_per_step")]
+                ("flops_per_iter", "flops_score", "lu_flops", "bytes_per_step")] + \
+               [(n, C.c_int32) for n in ("pf_lanes", "lane_max_row", "lane_warps_per_cta",
+                                         "lane_tables_staged")] + [("lane_scratch_bytes", C.c_double)]
 
 
 class AssemblyDesc(C.Structure):

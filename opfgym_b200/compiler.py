@@ -437,7 +437,7 @@ class Compiler:
 
 # ----------------------------------------------------------- ctypes marshalling
 def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_lims,
-               threads_per_env=0, ordering=0):
+               threads_per_env=0, ordering=0, pf_kernel=0):
     """Build the three ctypes descriptor structs.  Returns (grid, assembly,
     scoring, keepalive) -- ``keepalive`` holds the numpy arrays the structs point to."""
     import ctypes as C
@@ -461,7 +461,8 @@ def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_l
                        gen=dptr(ppc.gen), gen_cols=ppc.gen.shape[1], branch=dptr(ppc.branch),
                        branch_cols=ppc.branch.shape[1], tol_pu=tol_pu, max_iter=max_iter,
                        init_dc=int(init_dc), enforce_q_lims=int(enforce_q_lims),
-                       threads_per_env=threads_per_env, ordering=ordering)
+                       threads_per_env=threads_per_env, ordering=ordering,
+                       pf_kernel=pf_kernel)
     a = program.assembly
     ad = capi.AssemblyDesc(n_state=a["n_state"], n_const=len(program.consts),
                            consts=dptr(program.consts), n_act=len(a["act_slot"]),

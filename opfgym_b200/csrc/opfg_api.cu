@@ -85,6 +85,16 @@ struct OpfgGrid {
     size_t smem_pf = 0, smem_score = 0;
     int carveout_pct = -1;   // -1: leave the driver's default L1/shared split
     int envs_per_cta = 1;
+    // lane-per-environment kernel: schedule, per-warp scratch in global memory, launch shape
+    LaneSchedule lane;
+    int pf_kernel = 0;              // OpfgGridDesc.pf_kernel (after the OPFG_PF_KERNEL override)
+    bool lanes_ok = false;          // tables built (the grid qualifies)
+    double* lane_scratch = nullptr;
+    size_t lane_warp_doubles = 0;   // scratch doubles per warp (32 lanes)
+    int lane_ctas = 0, lane_warps_per_cta = 0, lane_stage = 0;
+    size_t lane_smem = 0;
+    bool lane_attr_set = false;
+    int n_sm = 148;
 
     // schedule / Ybus tables of the power-flow kernel live in ONE contiguous device arena so that a
     // multi-environment CTA can stage them in shared memory with a single cooperative copy
@@ -503,6 +513,56 @@ __global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E,
         cx.sync();
     }
 }
+// Lane-per-environment Newton-Raphson (opfg_core.h, lanes_pf_solve): persistent CTAs of W warps, a warp
+// takes 32 consecutive environments at a time.  Shared memory: the schedule tables (staged once per
+// CTA when STAGED, else read through L1) and one row buffer per warp; everything else per environment
+// sits in the warp's scratch slice in global memory at [slot][lane].
+#define OPFG_LANE_TABLES(X)                                                                   \
+    X(ln_row) X(ln_y) X(ln_diag_pos) X(ln_fill) X(ln_el) X(ln_el_uptr) X(ln_upd) X(ln_up)     \
+    X(ln_yval) X(ln_vm0) X(ln_va0) X(ln_bus_of_int) X(ln_type) X(ln_qbus) X(ln_qmin) X(ln_qmax)
+// MODE bits: 1 = tables staged in shared memory, 2 = enforce_q_lims (per-lane bus types), 4 = per-environment Ybus values
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) k_pf_lanes(GridDev g, OpfgBatch B, double* scratch, size_t warp_doubles) {
+    constexpr bool STAGED = (MODE & 1) != 0, QLIM = (MODE & 2) != 0, DYN = (MODE & 4) != 0;
+    extern __shared__ __align__(16) double sm[];
+    size_t tab_doubles = 0;
+    if (STAGED) {
+        const int4* src = reinterpret_cast<const int4*>(g.tab3_base);
+        int4* dst = reinterpret_cast<int4*>(sm);
+        for (int i = threadIdx.x; i < g.tab3_bytes / 16; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+        char* sbase = reinterpret_cast<char*>(sm);
+#define OPFG_REBASE(field) g.field = reinterpret_cast<decltype(g.field)>(sbase + (unsigned)reinterpret_cast<size_t>(g.field));
+        OPFG_LANE_TABLES(OPFG_REBASE)
+#undef OPFG_REBASE
+        tab_doubles = (size_t)g.tab3_bytes / 8;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    double* rb = sm + tab_doubles + (size_t)warp * (4 * g.ln_max_row * 32) + lane;
+    const size_t gwarp = (size_t)blockIdx.x * wpc + warp;
+    const LaneMem<32> s = lane_carve<32>(scratch + gwarp * warp_doubles + lane, rb, g.nb, g.n, g.ln_n_up);
+    const int64_t n_groups = (B.n_env + 31) / 32;
+    for (int64_t grp = gwarp; grp < n_groups; grp += (int64_t)gridDim.x * wpc) {
+        int64_t env = grp * 32 + lane;
+        const bool live = env < B.n_env;
+        if (!live) env = B.n_env - 1;          // idle lanes shadow the last environment (no stores)
+        lanes_pf_solve<32, QLIM, DYN>(g, s, B.sbus + env * (int64_t)g.nb * 2,
+                                      DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
+                                      B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env,
+                                      B.iterations + env, live);
+        __syncwarp();
+    }
+}
+static GridDev lane_view(const GridDev& d, bool staged) {
+    GridDev view = d;
+    if (staged) {
+#define OPFG_TO_OFFSET(field) view.field = reinterpret_cast<decltype(view.field)>((size_t)(reinterpret_cast<const char*>(d.field) - d.tab3_base));
+        OPFG_LANE_TABLES(OPFG_TO_OFFSET)
+#undef OPFG_TO_OFFSET
+    }
+    return view;
+}
+
 template <int T>
 __global__ void __launch_bounds__(T) k_score(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
@@ -552,6 +612,16 @@ static GridDev staged_view(const GridDev& d, int stage) {
         default: return fail("unsupported threads_per_env %d", T_);  \
     }
 #endif
+
+// Which power-flow kernel a launch uses: the lane-per-environment kernel when its tables exist (row
+// patterns of at most 255 blocks, row buffer fits shared memory) and the DC start comes from the dense
+// pre-pass; else one CTA per environment.  OpfgGridDesc.pf_kernel / OPFG_PF_KERNEL=cta|lanes override.
+static bool use_lanes(const OpfgGrid* G, const OpfgBatch* B) {
+    (void)B;
+    if (G->pf_kernel == 1) return false;
+    const GridDev& d = G->d;
+    return G->lanes_ok && G->lane_scratch && (!d.init_dc || d.dc_pre);
+}
 
 // ------------------------------------------------------------------- C ABI
 extern "C" {
@@ -632,7 +702,12 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
 
         int T = desc->threads_per_env;
         Symbolic& s = G->sym;
-        analyse(nb, type, active, desc->ordering, T > 0 ? T : 32, s);
+        // OPFG_PF_KERNEL=cta keeps the CTA-per-environment kernel (and its level-minimising ordering)
+        int pf_kernel = desc->pf_kernel;
+        if (const char* pfk = getenv("OPFG_PF_KERNEL")) pf_kernel = !strcmp(pfk, "cta") ? 1 : (!strcmp(pfk, "lanes") ? 2 : pf_kernel);
+        G->pf_kernel = pf_kernel;
+        const bool want_lanes = pf_kernel != 1;
+        analyse(nb, type, active, (desc->ordering == 0 && want_lanes) ? 3 : desc->ordering, T > 0 ? T : 32, s);
         if (T <= 0) T = s.n_blocks <= 1000 ? 64 : 128;   // measured: 64 on the MV grids (~450 blocks), 128 on HV (~1900)
         for (size_t c = 0; c < s.yc_branch.size(); ++c)
             if (s.yc_role[c] != 4) s.yc_branch[c] = active_row[s.yc_branch[c]];
@@ -774,6 +849,8 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         } else {
             d.dc_val = G->tab(dc_val); d.dc_rhs0 = G->tab(dc_rhs0);
         }
+        std::vector<int> lane_qb;
+        std::vector<double> lane_qmn, lane_qmx;
         {   // enforce_q_lims tables: one entry per PV bus with an active limit
             std::vector<int> qb;
             std::vector<double> qmn, qmx;
@@ -792,10 +869,46 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             }
             d.n_qlim = (int)qb.size();
             d.qlim_bus = G->tab(qb); d.qlim_min = G->tab(qmn); d.qlim_max = G->tab(qmx);
+            lane_qb = qb; lane_qmn = qmn; lane_qmx = qmx;
         }
         d.tab_base = G->tab_base;
         d.tab_bytes = (int)((G->tab_used + 15) & ~size_t(15));
 
+        // ---- lane-per-environment kernel: row-wise schedule in its own arena ----
+        if (want_lanes && nb < 65535 && (int)s.up_w.size() < 65535) {
+            LaneSchedule& ls = G->lane;
+            build_lane_schedule(s, ls);
+            if (ls.max_row <= 255) {
+                const int n = s.n;
+                std::vector<int> row(4 * (size_t)(n + 1));
+                for (int k = 0; k <= n; ++k) {
+                    row[4 * k] = s.y_ptr[k]; row[4 * k + 1] = ls.fill_ptr[k];
+                    row[4 * k + 2] = ls.el_ptr[k]; row[4 * k + 3] = s.up_ptr[k];
+                }
+                std::vector<uint32_t> ly(s.y_ptr[n]), el(ls.el_rpos.size()), upd(ls.upd_w.size()), up(s.up_w.size());
+                for (size_t e = 0; e < ly.size(); ++e) ly[e] = (uint32_t)s.y_col[e] | ((uint32_t)(ls.y_rpos[e] + 1) << 16);
+                for (size_t i = 0; i < el.size(); ++i) el[i] = (uint32_t)ls.el_rpos[i] | ((uint32_t)ls.el_m[i] << 16);
+                for (size_t i = 0; i < upd.size(); ++i) upd[i] = (uint32_t)ls.upd_w[i] | ((uint32_t)ls.upd_rpos[i] << 16);
+                for (size_t i = 0; i < up.size(); ++i) up[i] = (uint32_t)s.up_j[i] | ((uint32_t)ls.up_rpos[i] << 16);
+                std::vector<unsigned char> dpos(ls.diag_pos.begin(), ls.diag_pos.end()), fl(ls.fill_rpos.begin(), ls.fill_rpos.end());
+                // the arena is filled through the tab() helper of the main arena: swap the cursors
+                char* keep_base = G->tab_base; size_t keep_cap = G->tab_cap, keep_used = G->tab_used;
+                G->tab_reserve(1024 + 16 * row.size() / 4 + 4 * (ly.size() + el.size() + ls.el_uptr.size() + upd.size() + up.size()) +
+                               dpos.size() + fl.size() + 16 * ly.size() + 21 * (size_t)nb + 20 * lane_qb.size() + 16 * 20);
+                G->tab_used = 0;
+                d.tab3_base = G->tab_base;
+                d.ln_row = G->tab(row); d.ln_y = G->tab(ly); d.ln_diag_pos = G->tab(dpos); d.ln_fill = G->tab(fl);
+                d.ln_el = G->tab(el); d.ln_el_uptr = G->tab(ls.el_uptr); d.ln_upd = G->tab(upd); d.ln_up = G->tab(up);
+                d.ln_yval = G->tab(std::vector<double>(2 * ly.size(), 0.0));       // filled after the Ybus assembly below
+                d.ln_vm0 = G->tab(vm0); d.ln_va0 = G->tab(va0);
+                d.ln_bus_of_int = G->tab(s.bus_of_int); d.ln_type = G->tab(type_int);
+                d.ln_qbus = G->tab(lane_qb); d.ln_qmin = G->tab(lane_qmn); d.ln_qmax = G->tab(lane_qmx);
+                d.tab3_bytes = (int)((G->tab_used + 15) & ~size_t(15));
+                G->tab_base = keep_base; G->tab_cap = keep_cap; G->tab_used = keep_used;
+                d.ln_max_row = ls.max_row; d.ln_n_up = (int)s.up_w.size();
+                G->lanes_ok = true;
+            }
+        }
         if (const char* cv = getenv("OPFG_CARVEOUT")) G->carveout_pct = atoi(cv);
         G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
@@ -828,6 +941,40 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { delete G; return fail("Ybus assembly failed: %s", cudaGetErrorString(e)); }
 #endif
+        if (G->lanes_ok) {
+            const size_t ybytes = sizeof(double) * 2 * (size_t)s.y_ptr[s.n];
+#ifdef OPFG_HOSTSIM
+            memcpy(const_cast<double*>(d.ln_yval), y_val, ybytes);
+            G->lane_warp_doubles = lane_scratch_doubles(nb, s.n, d.ln_n_up, s.y_ptr[s.n]);
+            G->lane_scratch = (double*)dev_alloc(sizeof(double) * (G->lane_warp_doubles + 4 * (size_t)d.ln_max_row));
+            if (!G->lane_scratch) { delete G; return fail("lane scratch allocation failed"); }
+            G->allocs.push_back(G->lane_scratch);
+#else
+            cudaMemcpy(const_cast<double*>(d.ln_yval), y_val, ybytes, cudaMemcpyDeviceToDevice);
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&G->n_sm, cudaDevAttrMultiProcessorCount, dev);
+            // launch shape: W warps per CTA, one CTA per SM; shared memory = tables (if they fit) + W row buffers
+            const size_t rb_bytes = sizeof(double) * 4 * (size_t)d.ln_max_row * 32;
+            const size_t budget = 227 * 1024;
+            int W = getenv("OPFG_LANE_WARPS") ? atoi(getenv("OPFG_LANE_WARPS")) : 12;
+            W = std::max(1, std::min(W, 16));
+            bool staged = (size_t)d.tab3_bytes + rb_bytes <= budget;
+            if (const char* sv = getenv("OPFG_LANE_STAGE")) staged = staged && atoi(sv) != 0;
+            const size_t tabs = staged ? (size_t)d.tab3_bytes : 0;
+            while (W > 1 && tabs + W * rb_bytes > budget) --W;
+            if (tabs + W * rb_bytes > budget) G->lanes_ok = false;     // one row buffer does not fit: CTA kernel
+            else {
+                G->lane_warps_per_cta = W; G->lane_stage = staged; G->lane_ctas = G->n_sm;
+                G->lane_smem = tabs + W * rb_bytes;
+                G->lane_warp_doubles = lane_scratch_doubles(nb, s.n, d.ln_n_up, s.y_ptr[s.n]) * 32;
+                const size_t bytes = sizeof(double) * G->lane_warp_doubles * (size_t)W * G->lane_ctas;
+                void* p = nullptr;
+                if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); G->lanes_ok = false; }
+                else { G->lane_scratch = (double*)p; G->allocs.push_back(p); }
+            }
+#endif
+        }
         *out = G;
         return 0;
     } catch (const std::exception& ex) {
@@ -1002,6 +1149,12 @@ int opfg_grid_info(const OpfgGrid* G, OpfgGridInfo* o) {
     // algorithmic HBM bytes of one env step: read action + input state, write results, per-constraint
     // metrics, reward/objective/penalty/cost, flags and the f32 observation
     const int n_in = d.n_state - G->n_result_cells;
+    {
+        OpfgBatch none{};
+        o->pf_lanes = use_lanes(G, &none) ? 1 : 0;
+        o->lane_max_row = d.ln_max_row; o->lane_warps_per_cta = G->lane_warps_per_cta; o->lane_tables_staged = G->lane_stage;
+        o->lane_scratch_bytes = 8.0 * (double)G->lane_warp_doubles * std::max(1, G->lane_warps_per_cta * G->lane_ctas);
+    }
     o->bytes_per_step = 8.0 * (n_in + d.n_act) + 8.0 * (2.0 * d.nb + G->n_result_cells) + 17.0 * d.n_con + 8.0 * 4 + 5
                         + 4.0 * d.n_obs;
     return 0;
@@ -1110,6 +1263,21 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                 B->va[env * d.nb + d.bus_of_int[i]] = acc + d.dc_theta0[i];
             }
     }
+    if (use_lanes(G, B)) {
+        const GridDev& d = G->d;
+        const LaneMem<1> s = lane_carve<1>(G->lane_scratch, G->lane_scratch + G->lane_warp_doubles, d.nb, d.n, d.ln_n_up);
+        const bool dyn = d.n_dyn > 0 && B->yval;
+        for (int64_t env = 0; env < B->n_env; ++env) {
+            const double* sb = B->sbus + env * (int64_t)d.nb * 2;
+            const double* yv = dyn ? B->yval + env * (int64_t)d.nnz_y * 2 : nullptr;
+            double *vm = B->vm + env * (int64_t)d.nb, *va = B->va + env * (int64_t)d.nb;
+            if (d.n_qlim > 0 && dyn) lanes_pf_solve<1, true, true>(d, s, sb, yv, vm, va, B->converged + env, B->iterations + env, true);
+            else if (d.n_qlim > 0) lanes_pf_solve<1, true, false>(d, s, sb, yv, vm, va, B->converged + env, B->iterations + env, true);
+            else if (dyn) lanes_pf_solve<1, false, true>(d, s, sb, yv, vm, va, B->converged + env, B->iterations + env, true);
+            else lanes_pf_solve<1, false, false>(d, s, sb, yv, vm, va, B->converged + env, B->iterations + env, true);
+        }
+        return 0;
+    }
     for (int64_t env = 0; env < B->n_env; ++env)
         env_pf_solve(G->d, cx, sm.data(), B->sbus + env * (int64_t)G->d.nb * 2,
                      (G->d.n_dyn > 0 && B->yval) ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr, B->vm + env * (int64_t)G->d.nb,
@@ -1120,6 +1288,26 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         if (!dc_attr) { cudaFuncSetAttribute(k_dc_start, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM); dc_attr = true; }
         k_dc_start<<<dim3((unsigned)((B->n_env + DC_ENVS - 1) / DC_ENVS), (unsigned)((G->d.n + 63) / 64)), 256, DC_SMEM, (cudaStream_t)stream>>>(G->d, *B);
         ++g_launches;
+    }
+    if (use_lanes(G, B)) {
+        OpfgGrid* Gm = const_cast<OpfgGrid*>(G);
+        void (*fns[8])(GridDev, OpfgBatch, double*, size_t) = {
+            k_pf_lanes<0>, k_pf_lanes<1>, k_pf_lanes<2>, k_pf_lanes<3>, k_pf_lanes<4>, k_pf_lanes<5>, k_pf_lanes<6>, k_pf_lanes<7>};
+        if (!Gm->lane_attr_set) {      // per grid, hence per device (function attributes are per device)
+            for (auto* f : fns) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            Gm->lane_attr_set = true;
+        }
+        const GridDev view = lane_view(G->d, G->lane_stage != 0);
+        const int64_t groups = (B->n_env + 31) / 32;
+        // as many CTAs as there is work for W warps each, at most one per SM
+        const int W = G->lane_warps_per_cta;
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((groups + W - 1) / W, G->lane_ctas));
+        auto* fn = fns[(G->lane_stage ? 1 : 0) | (G->d.n_qlim > 0 ? 2 : 0) | ((G->d.n_dyn > 0 && B->yval) ? 4 : 0)];
+        fn<<<grid, 32 * W, G->lane_smem, (cudaStream_t)stream>>>(view, *B, G->lane_scratch, G->lane_warp_doubles);
+        ++g_launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("pf_solve (lanes) launch: %s", cudaGetErrorString(e));
+        return 0;
     }
     const size_t smem = G->smem_pf;
     OPFG_DISPATCH_T(G->d.threads, {

@@ -111,6 +111,24 @@ struct GridDev {
     int n_obs;
     const int* obs_ref;
     const int* obs_ptr;      // nullptr: one ref per observation
+    // ---- lane-per-environment power flow (row-wise schedule, symbolic.hpp LaneSchedule) ----
+    int ln_max_row, ln_n_up;
+    const int* ln_row;                 // [n+1][4] first Ybus entry, fill position, elimination item, upper block of row k
+    const uint32_t* ln_y;              // [nnz_y_nonref] column | (row-buffer position + 1) << 16
+    const unsigned char* ln_diag_pos;  // [n]
+    const unsigned char* ln_fill;      // row-buffer positions that start at zero
+    const uint32_t* ln_el;             // elimination items: position of L(k, m) | m << 16
+    const int* ln_el_uptr;             // their update ranges
+    const uint32_t* ln_upd;            // updates: W slot | target position << 16
+    const uint32_t* ln_up;             // upper blocks: column j | position << 16
+    const char* tab3_base;             // arena of the tables above (+ the Ybus values / start values they need)
+    int tab3_bytes;
+    const double* ln_yval;             // copies inside the lane arena
+    const double *ln_vm0, *ln_va0;
+    const int* ln_bus_of_int;
+    const unsigned char* ln_type;
+    const int* ln_qbus;                // q-limit tables (copies of qlim_*)
+    const double *ln_qmin, *ln_qmax;
     const char* tab_base;              // contiguous arena holding the power-flow tables
     int tab_bytes;
     int tab_hot_bytes;                 // prefix holding the LU schedule
@@ -710,6 +728,247 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         if (changed > 0) { converged = 0; it = 0; prev = 1.0; goto restart_after_q_limits; }
     }
     if (cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
+}
+
+// ------------------------------------------- kernels 2-4, lane-per-environment form
+// One LANE per environment: a warp walks the row-wise schedule once for 32 environments.  Every
+// index is warp-uniform (no per-lane index loads, no divergence, no barriers, no shuffles), every
+// per-environment value lives at [slot][lane] (coalesced / bank-conflict free).  The Jacobian is never
+// stored: row k is rebuilt in a small row buffer (shared memory) from V and Ybus at the moment it is
+// eliminated, and only W(k, j) = D_k^-1 U(k, j) and t_k = D_k^-1 y_k leave it, into a per-warp scratch
+// area in global memory that the backward substitution reads back (L2).  All sums run in the order of
+// the CTA-per-environment kernel above: both produce the same bits.
+template <int LANES>
+struct LaneMem {
+    double *vr, *vi, *vm, *va, *ivm;   // [nb] per lane
+    double *sp, *sq;                   // [n]  bus injection (set-point), internal order
+    double *t;                         // [2 n]
+    double *w;                         // [4 n_up]
+    double *rb;                        // [4 max_row] row buffer
+    double *qadd, *pqf;                // [n] enforce_q_lims: reactive power fixed at a limit; 1.0 = PQ bus
+    double *yv;                        // [2 nnz_y_nonref] per-environment Ybus values (tap / in-service cells)
+};
+OPFG_HHD size_t lane_scratch_doubles(int nb, int n, int n_up, int nnz_nonref) {
+    return 5 * (size_t)nb + 6 * (size_t)n + 4 * (size_t)n_up + 2 * (size_t)nnz_nonref;
+}
+template <int LANES>
+OPFG_HD LaneMem<LANES> lane_carve(double* base, double* rb, int nb, int n, int n_up) {
+    LaneMem<LANES> s;
+    s.vr = base; s.vi = s.vr + (size_t)nb * LANES; s.vm = s.vi + (size_t)nb * LANES;
+    s.va = s.vm + (size_t)nb * LANES; s.ivm = s.va + (size_t)nb * LANES;
+    s.sp = s.ivm + (size_t)nb * LANES; s.sq = s.sp + (size_t)n * LANES;
+    s.t = s.sq + (size_t)n * LANES; s.w = s.t + 2 * (size_t)n * LANES;
+    s.qadd = s.w + 4 * (size_t)n_up * LANES; s.pqf = s.qadd + (size_t)n * LANES;
+    s.yv = s.pqf + (size_t)n * LANES;
+    s.rb = rb;
+    return s;
+}
+#define OPFG_LN(p, i) (p)[(size_t)(i) * LANES]
+
+#ifdef OPFG_DEVICE_BUILD
+OPFG_HD bool lanes_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+#else
+OPFG_HD bool lanes_any(bool p) { return p; }
+#endif
+
+// Rows 0..n-1 in elimination order: power mismatch of the row (-> ||F||inf of this lane's environment)
+// and, if JAC, the row of the Jacobian, its elimination against the earlier rows, t_k and W(k, .).
+template <int LANES, bool JAC, bool QLIM, bool DYN>
+OPFG_HD double lanes_rows(const GridDev& g, const LaneMem<LANES>& s) {
+    const int n = g.n;
+    double part = 0.0;
+    bool bad = false;
+    for (int k = 0; k < n; ++k) {
+        const int* hdr = g.ln_row + 4 * k;
+        const int e0 = hdr[0], e1 = hdr[4];
+        const double vkr = OPFG_LN(s.vr, k), vki = OPFG_LN(s.vi, k);
+        const bool pq = QLIM ? OPFG_LN(s.pqf, k) != 0.0 : g.ln_type[k] == OPFG_PQ;
+        double ir = 0, ii = 0, dr = 0, di = 0;
+        for (int e = e0; e < e1; ++e) {
+            const uint32_t meta = g.ln_y[e];
+            const int j = (int)(meta & 0xffffu);
+            const double yr = DYN ? OPFG_LN(s.yv, 2 * e) : g.ln_yval[2 * e];
+            const double yi = DYN ? OPFG_LN(s.yv, 2 * e + 1) : g.ln_yval[2 * e + 1];
+            const double vjr = OPFG_LN(s.vr, j), vji = OPFG_LN(s.vi, j);
+            const double tr = fma(yr, vjr, -(yi * vji)), ti = fma(yr, vji, yi * vjr);   // Y_kj V_j
+            ir += tr; ii += ti;
+            if (e == e0) { dr = tr; di = ti; }                // the diagonal entry is first
+            else if (JAC) {
+                const int rp = (int)(meta >> 16) - 1;
+                if (rp >= 0) {                                // off-diagonal block (k, j), j not a slack bus
+                    const double ar = fma(vkr, tr, vki * ti), ai = fma(vki, tr, -(vkr * ti));   // V_k conj(Y_kj V_j)
+                    const double inv_vmj = OPFG_LN(s.ivm, j);
+                    double* b = s.rb + (size_t)(4 * rp) * LANES;
+                    b[0] = ai; b[LANES] = ar * inv_vmj;
+                    b[2 * LANES] = pq ? -ar : 0.0; b[3 * LANES] = pq ? ai * inv_vmj : 0.0;
+                }
+            }
+        }
+        const double P = fma(vkr, ir, vki * ii), Q = fma(vki, ir, -(vkr * ii));   // S_k = V_k conj(I_k)
+        double sq = OPFG_LN(s.sq, k);
+        if (QLIM) sq += OPFG_LN(s.qadd, k);
+        const double dp = P - OPFG_LN(s.sp, k), dq = pq ? Q - sq : 0.0;
+        if (dp != dp || dq != dq) bad = true;
+        else { const double a = fabs(dp), c = fabs(dq), r = a > c ? a : c; if (r > part) part = r; }
+        if (!JAC) continue;
+        // diagonal block and right-hand side of the row
+        double d00, d01, d10, d11, y0 = -dp, y1 = -dq;
+        {
+            const double ar = fma(vkr, dr, vki * di), ai = fma(vki, dr, -(vkr * di));   // V_k conj(Y_kk V_k)
+            const double inv_vmk = OPFG_LN(s.ivm, k);
+            d00 = -Q + ai; d01 = (ar + P) * inv_vmk;
+            d10 = pq ? P - ar : 0.0; d11 = pq ? (ai + Q) * inv_vmk : 1.0;
+        }
+        const int dpos = g.ln_diag_pos[k];
+        for (int f = hdr[1]; f < hdr[5]; ++f) {
+            double* b = s.rb + (size_t)(4 * g.ln_fill[f]) * LANES;
+            b[0] = 0.0; b[LANES] = 0.0; b[2 * LANES] = 0.0; b[3 * LANES] = 0.0;
+        }
+        // eliminate the earlier rows m (increasing): row_k -= L(k, m) W(m, .), y_k -= L(k, m) t_m
+        for (int it = hdr[2]; it < hdr[6]; ++it) {
+            const uint32_t el = g.ln_el[it];
+            const double* lb = s.rb + (size_t)(4 * (el & 0xffffu)) * LANES;
+            const double l00 = lb[0], l01 = lb[LANES], l10 = lb[2 * LANES], l11 = lb[3 * LANES];
+            const int m = (int)(el >> 16);
+            const double t0 = OPFG_LN(s.t, 2 * m), t1 = OPFG_LN(s.t, 2 * m + 1);
+            y0 = fma(-l01, t1, fma(-l00, t0, y0));
+            y1 = fma(-l11, t1, fma(-l10, t0, y1));
+            for (int u = g.ln_el_uptr[it]; u < g.ln_el_uptr[it + 1]; ++u) {
+                const uint32_t up = g.ln_upd[u];
+                const double* wb = s.w + (size_t)(4 * (up & 0xffffu)) * LANES;
+                const double w00 = wb[0], w01 = wb[LANES], w10 = wb[2 * LANES], w11 = wb[3 * LANES];
+                const int tp = (int)(up >> 16);
+                if (tp == dpos) {
+                    d00 = fma(-l01, w10, fma(-l00, w00, d00)); d01 = fma(-l01, w11, fma(-l00, w01, d01));
+                    d10 = fma(-l11, w10, fma(-l10, w00, d10)); d11 = fma(-l11, w11, fma(-l10, w01, d11));
+                } else {
+                    double* b = s.rb + (size_t)(4 * tp) * LANES;
+                    b[0] = fma(-l01, w10, fma(-l00, w00, b[0]));
+                    b[LANES] = fma(-l01, w11, fma(-l00, w01, b[LANES]));
+                    b[2 * LANES] = fma(-l11, w10, fma(-l10, w00, b[2 * LANES]));
+                    b[3 * LANES] = fma(-l11, w11, fma(-l10, w01, b[3 * LANES]));
+                }
+            }
+        }
+        // D_k^-1, t_k = D_k^-1 y_k, W(k, j) = D_k^-1 U(k, j)
+        const double r = 1.0 / fma(d00, d11, -(d01 * d10));
+        const double ia = d11 * r, ib = -d01 * r, ic = -d10 * r, id_ = d00 * r;
+        OPFG_LN(s.t, 2 * k) = fma(ia, y0, ib * y1);
+        OPFG_LN(s.t, 2 * k + 1) = fma(ic, y0, id_ * y1);
+        for (int p = hdr[3]; p < hdr[7]; ++p) {
+            const double* ub = s.rb + (size_t)(4 * (g.ln_up[p] >> 16)) * LANES;
+            const double u00 = ub[0], u01 = ub[LANES], u10 = ub[2 * LANES], u11 = ub[3 * LANES];
+            double* wb = s.w + (size_t)(4 * p) * LANES;
+            wb[0] = fma(ia, u00, ib * u10); wb[LANES] = fma(ia, u01, ib * u11);
+            wb[2 * LANES] = fma(ic, u00, id_ * u10); wb[3 * LANES] = fma(ic, u01, id_ * u11);
+        }
+    }
+    return bad ? NAN : part;
+}
+
+// One environment per lane: start values, Newton-Raphson to tolerance, |V|, angle, flag.  Same control
+// flow per environment as env_pf_solve (pandapower newtonpf); which pass a WARP runs
+// next (mismatch only, or mismatch + factorisation) is decided by vote and does not change any lane's result.
+template <int LANES, bool QLIM, bool DYN>
+OPFG_HD void lanes_pf_solve(const GridDev& g, const LaneMem<LANES>& s, const double* sbus, const double* yval,
+                            double* vm_out, double* va_out, uint8_t* conv_out, int32_t* iter_out, bool live) {
+    const int n = g.n, nb = g.nb;
+    for (int i = 0; i < nb; ++i) {
+        const int bus = g.ln_bus_of_int[i];
+        const double vm = g.ln_vm0[i];
+        const double va = (g.init_dc && i < n) ? va_out[bus] : g.ln_va0[i];   // DC start: written by the dense pre-pass
+        double sn, cs;
+        sincos(va, &sn, &cs);
+        OPFG_LN(s.vm, i) = vm; OPFG_LN(s.va, i) = va; OPFG_LN(s.ivm, i) = 1.0 / vm;
+        OPFG_LN(s.vr, i) = vm * cs; OPFG_LN(s.vi, i) = vm * sn;
+        if (i < n) {
+            OPFG_LN(s.sp, i) = sbus[2 * bus]; OPFG_LN(s.sq, i) = sbus[2 * bus + 1];
+            if (QLIM) { OPFG_LN(s.qadd, i) = 0.0; OPFG_LN(s.pqf, i) = g.ln_type[i] == OPFG_PQ ? 1.0 : 0.0; }
+        }
+    }
+    if (DYN)
+        for (int e = 0; e < 2 * g.nnz_y_nonref; ++e) OPFG_LN(s.yv, e) = yval[e];
+    bool active = live;
+    int it = 0, converged = 0;
+    double prev = 1.0;
+    for (;;) {
+        while (lanes_any(active)) {
+            if (!lanes_any(active && !(prev < 1e-4))) {
+                // every environment still running expects to have converged: look at the mismatch alone
+                const double nrm = lanes_rows<LANES, false, QLIM, DYN>(g, s);
+                if (active) {
+                    prev = nrm;
+                    if (nrm < g.tol) { converged = 1; active = false; }
+                    else if (it >= g.max_iter || nrm != nrm) active = false;
+                }
+                if (!lanes_any(active)) break;
+            }
+            const double nrm = lanes_rows<LANES, true, QLIM, DYN>(g, s);
+            bool step = false;
+            if (active) {
+                prev = nrm;
+                if (nrm < g.tol) { converged = 1; active = false; }
+                else if (it >= g.max_iter || nrm != nrm) active = false;
+                else { ++it; step = true; }
+            }
+            if (!lanes_any(step)) continue;
+            for (int k = n - 1; k >= 0; --k) {                       // backward substitution
+                double x0 = OPFG_LN(s.t, 2 * k), x1 = OPFG_LN(s.t, 2 * k + 1);
+                const int pe = g.ln_row[4 * k + 7];
+                for (int p = g.ln_row[4 * k + 3]; p < pe; ++p) {
+                    const double* wb = s.w + (size_t)(4 * p) * LANES;
+                    const int j = (int)(g.ln_up[p] & 0xffffu);
+                    const double xj0 = OPFG_LN(s.t, 2 * j), xj1 = OPFG_LN(s.t, 2 * j + 1);
+                    x0 = fma(-wb[LANES], xj1, fma(-wb[0], xj0, x0));
+                    x1 = fma(-wb[3 * LANES], xj1, fma(-wb[2 * LANES], xj0, x1));
+                }
+                OPFG_LN(s.t, 2 * k) = x0; OPFG_LN(s.t, 2 * k + 1) = x1;
+            }
+            for (int k = 0; k < n; ++k) {                            // polar update (newtonpf.py)
+                if (!step) continue;
+                const bool pq = QLIM ? OPFG_LN(s.pqf, k) != 0.0 : g.ln_type[k] == OPFG_PQ;
+                double va = OPFG_LN(s.va, k) + OPFG_LN(s.t, 2 * k);
+                double vm = OPFG_LN(s.vm, k) + (pq ? OPFG_LN(s.t, 2 * k + 1) : 0.0);
+                if (vm < 0) { vm = -vm; va += M_PI; }
+                if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
+                double sn, cs;
+                sincos(va, &sn, &cs);
+                OPFG_LN(s.va, k) = va; OPFG_LN(s.vm, k) = vm; OPFG_LN(s.ivm, k) = 1.0 / vm;
+                OPFG_LN(s.vr, k) = vm * cs; OPFG_LN(s.vi, k) = vm * sn;
+            }
+        }
+        if (!QLIM) break;
+        // pandapower `_run_ac_pf_with_qlims_enforced` [ext-mem], as in env_pf_solve: a voltage-controlled bus
+        // whose reactive output left [QMIN, QMAX] is fixed at the limit, becomes a PQ bus, solve again
+        bool changed = false;
+        for (int q = 0; q < g.n_qlim; ++q) {
+            const int i = g.ln_qbus[q];
+            const double vkr = OPFG_LN(s.vr, i), vki = OPFG_LN(s.vi, i);
+            double ir = 0, ii = 0;
+            for (int e = g.ln_row[4 * i]; e < g.ln_row[4 * i + 4]; ++e) {
+                const int j = (int)(g.ln_y[e] & 0xffffu);
+                const double yr = DYN ? OPFG_LN(s.yv, 2 * e) : g.ln_yval[2 * e];
+                const double yi = DYN ? OPFG_LN(s.yv, 2 * e + 1) : g.ln_yval[2 * e + 1];
+                const double vjr = OPFG_LN(s.vr, j), vji = OPFG_LN(s.vi, j);
+                ir += fma(yr, vjr, -(yi * vji));
+                ii += fma(yr, vji, yi * vjr);
+            }
+            const double qg = fma(vki, ir, -(vkr * ii)) - OPFG_LN(s.sq, i);   // generator Q, p.u.
+            if (converged && OPFG_LN(s.pqf, i) == 0.0) {
+                if (qg > g.ln_qmax[q]) { OPFG_LN(s.qadd, i) = g.ln_qmax[q]; OPFG_LN(s.pqf, i) = 1.0; changed = true; }
+                else if (qg < g.ln_qmin[q]) { OPFG_LN(s.qadd, i) = g.ln_qmin[q]; OPFG_LN(s.pqf, i) = 1.0; changed = true; }
+            }
+        }
+        if (changed) { converged = 0; it = 0; prev = 1.0; active = true; }
+        if (!lanes_any(active)) break;
+    }
+    if (live) {
+        for (int i = 0; i < nb; ++i) {
+            const int bus = g.ln_bus_of_int[i];
+            vm_out[bus] = OPFG_LN(s.vm, i); va_out[bus] = OPFG_LN(s.va, i);
+        }
+        *conv_out = (uint8_t)converged; *iter_out = it;
+    }
 }
 
 // ------------------------------------------------------------- kernel 5: scoring

@@ -184,6 +184,8 @@ void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchH
         if (a >= 0 && b >= 0) { adj[a].insert(b); adj[b].insert(a); }
     }
     std::vector<Order> cands;
+    const bool least_work = ordering == 3;     // lane-per-environment kernel: levels are irrelevant, fill is work
+    if (least_work) ordering = 0;
     if (ordering == 0 || ordering == 1) cands.push_back(make_order(adj, min_degree_sequence(adj), threads, "min_degree"));
     if (ordering == 0 || ordering == 2) {
         cands.push_back(make_order(adj, independent_set_sequence(adj, 0), threads, "independent_set"));
@@ -191,8 +193,13 @@ void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchH
     }
     if (cands.empty()) throw std::runtime_error("unknown ordering");
     const Order* best = &cands[0];
+    auto work = [](const Order& o) {           // Schur-update pairs: sum over pivots of |struct|^2
+        double w = 0;
+        for (const auto& st : o.strct) w += (double)st.size() * (double)st.size() + 2.0 * (double)st.size();
+        return w;
+    };
     for (const auto& c : cands)
-        if (c.cost < best->cost) best = &c;
+        if (least_work ? work(c) < work(*best) : c.cost < best->cost) best = &c;
     const Order& o = *best;
     s.ordering_name = o.name;
     s.est_cycles = o.cost;
@@ -356,6 +363,58 @@ void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchH
     lu += 8.0 * s.up_w.size();                             // backward substitution
     s.lu_flops = lu;
     s.flops_per_iter = 28.0 * nnz + 24.0 * nb + lu + 2.0 * n + 40.0 * nb;
+}
+
+void build_lane_schedule(const Symbolic& s, LaneSchedule& o) {
+    o = LaneSchedule();
+    const int n = s.n;
+    // lower(k): pivots m < k with a block (k, m); upper(k) = the up_* list of k
+    std::vector<std::vector<int>> lower(n);
+    for (int m = 0; m < n; ++m)
+        for (int p = s.up_ptr[m]; p < s.up_ptr[m + 1]; ++p) lower[s.up_j[p]].push_back(m);   // m ascending
+    std::set<int64_t> orig;                    // blocks fed by a Ybus entry
+    for (int r = 0; r < n; ++r)
+        for (int e = s.y_ptr[r]; e < s.y_ptr[r + 1]; ++e)
+            if (s.y_col[e] < n) orig.insert(key(r, s.y_col[e]));
+    o.y_rpos.assign(s.y_ptr[n], -1);
+    o.diag_pos.resize(n);
+    o.fill_ptr.assign(n + 1, 0);
+    o.el_ptr.assign(n + 1, 0);
+    o.up_rpos.assign(s.up_w.size(), -1);
+    o.el_uptr.push_back(0);
+    std::vector<int> pos_of(n, -1);
+    for (int k = 0; k < n; ++k) {
+        const int nl = (int)lower[k].size(), nu = s.up_ptr[k + 1] - s.up_ptr[k];
+        for (int a = 0; a < nl; ++a) pos_of[lower[k][a]] = a;
+        pos_of[k] = nl;
+        for (int a = 0; a < nu; ++a) { pos_of[s.up_j[s.up_ptr[k] + a]] = nl + 1 + a; o.up_rpos[s.up_ptr[k] + a] = nl + 1 + a; }
+        o.diag_pos[k] = nl;
+        o.max_row = std::max(o.max_row, nl + 1 + nu);
+        for (int e = s.y_ptr[k]; e < s.y_ptr[k + 1]; ++e)
+            if (s.y_col[e] < n) {
+                if (pos_of[s.y_col[e]] < 0) throw std::runtime_error("lane schedule: Ybus entry outside the filled pattern");
+                o.y_rpos[e] = pos_of[s.y_col[e]];
+            }
+        auto is_fill = [&](int c) { return !orig.count(key(k, c)); };
+        for (int m : lower[k]) if (is_fill(m)) o.fill_rpos.push_back(pos_of[m]);
+        for (int a = 0; a < nu; ++a) if (is_fill(s.up_j[s.up_ptr[k] + a])) o.fill_rpos.push_back(nl + 1 + a);
+        o.fill_ptr[k + 1] = (int)o.fill_rpos.size();
+        for (int m : lower[k]) {
+            o.el_rpos.push_back(pos_of[m]);
+            o.el_m.push_back(m);
+            for (int p = s.up_ptr[m]; p < s.up_ptr[m + 1]; ++p) {
+                const int j = s.up_j[p];
+                if (pos_of[j] < 0) throw std::runtime_error("lane schedule: update target outside the filled pattern");
+                o.upd_w.push_back(p);
+                o.upd_rpos.push_back(pos_of[j]);
+            }
+            o.el_uptr.push_back((int)o.upd_w.size());
+        }
+        o.el_ptr[k + 1] = (int)o.el_rpos.size();
+        for (int m : lower[k]) pos_of[m] = -1;
+        pos_of[k] = -1;
+        for (int a = 0; a < nu; ++a) pos_of[s.up_j[s.up_ptr[k] + a]] = -1;
+    }
 }
 
 void factor_dc(const Symbolic& s, const std::vector<BranchHost>& branches, std::vector<double>& val, bool& ok) {

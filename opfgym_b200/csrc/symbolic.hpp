@@ -53,7 +53,25 @@ struct Symbolic {
     std::string ordering_name;
 };
 
-// ordering: 0 auto (cheapest by cost model), 1 minimum degree, 2 independent-set rounds
+// Row-wise (IKJ) form of the same factorisation, for the lane-per-environment kernel: row k of the
+// filled Jacobian is built in a small row buffer -- L(k, m) for the earlier pivots m it touches,
+// the diagonal, U(k, j) for the later ones --, the rows of the earlier pivots are eliminated from it
+// in increasing m, and only W(k, j) = D_k^-1 U(k, j) and t_k leave the buffer.  Every sum runs in the
+// order of the gather lists above, so both kernels produce the same bits.
+struct LaneSchedule {
+    int max_row = 0;                          // largest row pattern, in blocks
+    std::vector<int> y_rpos;                  // per Ybus entry of the non-slack rows: row-buffer position, -1 = slack column
+    std::vector<int> diag_pos;                // [n]
+    std::vector<int> fill_ptr, fill_rpos;     // [n+1]; positions that start at zero (fill blocks)
+    std::vector<int> el_ptr;                  // [n+1] elimination items of row k (ascending m)
+    std::vector<int> el_rpos, el_m, el_uptr;  // position of L(k, m); m; its update range (el_uptr has one more entry)
+    std::vector<int> upd_w, upd_rpos;         // W slot = position in the up_* lists; target position in the row buffer
+    std::vector<int> up_rpos;                 // aligned with up_ptr / up_j: position of U(k, j)
+};
+void build_lane_schedule(const Symbolic& s, LaneSchedule& out);
+
+// ordering: 0 auto (cheapest by the CTA kernel's cost model), 1 minimum degree, 2 independent-set rounds,
+// 3 least work (fewest Schur-update pairs; what the lane-per-environment kernel wants)
 void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchHost>& branches,
              int ordering, int threads_per_env, Symbolic& out);
 

@@ -31,6 +31,7 @@ class Engine:
     def __init__(self, program: EnvProgram, num_envs: int, device=None,
                  tolerance_mva: float = 1e-8, max_iteration: int = 10, init: str = "dc",
                  enforce_q_lims: bool = True, threads_per_env: int = 0, ordering: int = 0,
+                 pf_kernel: str | int = 0,
                  obs_dtype: str = "float32", lib=None):
         self.program = program
         self.num_envs = int(num_envs)
@@ -39,7 +40,8 @@ class Engine:
         gd, ad, sd, dd, keep = fill_descs(
             capi, program, tol_pu=tolerance_mva / program.ppc.base_mva,
             max_iter=max_iteration, init_dc=(init == "dc"), enforce_q_lims=enforce_q_lims,
-            threads_per_env=threads_per_env, ordering=ordering)
+            threads_per_env=threads_per_env, ordering=ordering,
+            pf_kernel={"auto": 0, "cta": 1, "lanes": 2}.get(pf_kernel, pf_kernel))
         handle = C.c_void_p()
         capi.check(self.lib, self.lib.opfg_grid_create(C.byref(gd), C.byref(handle)))
         self.handle = handle
