@@ -82,8 +82,10 @@ typedef struct {
     int32_t threads_per_env;/* 0 = choose from grid size (32/64/128)                      */
     int32_t ordering;       /* 0 = auto, 1 = min-degree, 2 = independent-set, 3 = least fill work      */
     int32_t pf_kernel;      /* 0 = auto, 1 = one CTA per environment (level-scheduled block LU in shared
-                               memory), 2 = one LANE per environment (row-wise LU, Jacobian never stored);
-                               both produce the same bits                                               */
+                               memory), 2 = one LANE per environment (row-wise LU, Jacobian never stored,
+                               state in global scratch), 3 = fused kernel for radial grids (8-32 lanes per
+                               environment, Jacobian never stored, state in shared memory; auto picks it
+                               when the grid is radial).  All three produce the same bits.               */
 } OpfgGridDesc;
 
 typedef struct {
@@ -94,10 +96,12 @@ typedef struct {
     double flops_score;        /* FP64 flops of branch flows + scoring                                */
     double lu_flops;           /* block LU part of flops_per_iter                                     */
     double bytes_per_step;     /* algorithmic HBM bytes of one env step               */
-    int32_t pf_lanes;          /* 1: opfg_pf_solve runs the lane-per-environment kernel on this grid   */
+    int32_t pf_kernel_used;    /* what opfg_pf_solve launches on this grid: 1 CTA per environment, 2 lane
+                                  per environment, 3 fused kernel for radial grids                      */
     int32_t lane_max_row;      /* its largest row pattern (blocks) / warps per CTA / staged tables     */
     int32_t lane_warps_per_cta, lane_tables_staged;
     double lane_scratch_bytes; /* global scratch of the lane kernel (all resident warps)               */
+    int32_t radial_lanes_per_env, radial_envs_per_cta, radial_smem_bytes_per_env, reserved0;
 } OpfgGridInfo;
 
 /* action application + Sbus scatter (kernel 1) */

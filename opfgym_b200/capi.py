@@ -35,8 +35,10 @@ class GridInfo(C.Structure):
                  "n_const", "n_act", "n_obs", "n_constraints")] + \
                [(n, C.c_double) for n in
                 ("flops_per_iter", "flops_score", "lu_flops", "bytes_per_step")] + \
-               [(n, C.c_int32) for n in ("pf_lanes", "lane_max_row", "lane_warps_per_cta",
-                                         "lane_tables_staged")] + [("lane_scratch_bytes", C.c_double)]
+               [(n, C.c_int32) for n in ("pf_kernel_used", "lane_max_row", "lane_warps_per_cta",
+                                         "lane_tables_staged")] + [("lane_scratch_bytes", C.c_double)] + \
+               [(n, C.c_int32) for n in ("radial_lanes_per_env", "radial_envs_per_cta",
+                                         "radial_smem_bytes_per_env", "reserved0")]
 
 
 class AssemblyDesc(C.Structure):

@@ -95,6 +95,10 @@ struct OpfgGrid {
     size_t lane_smem = 0;
     bool lane_attr_set = false;
     int n_sm = 148;
+    // fused kernel for radial grids: lanes per environment, environments per CTA, shared memory
+    int tree_T = 0, tree_E = 0;
+    size_t tree_env_doubles = 0, tree_smem = 0;
+    bool tree_attr_set = false;
 
     // schedule / Ybus tables of the power-flow kernel live in ONE contiguous device arena so that a
     // multi-environment CTA can stage them in shared memory with a single cooperative copy
@@ -513,6 +517,43 @@ __global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E,
         cx.sync();
     }
 }
+// Fused kernel for radial grids (opfg_core.h, env_pf_tree): persistent CTAs, E environments of T lanes
+// each (32 / T environments share a warp and run in lockstep), tables staged once per CTA.
+#define OPFG_TREE_TABLES(X) X(tr_bus_of_int) X(tr_level_ptr) X(tr_y_ptr) X(tr_parent) X(tr_type) X(tr_y_ent) X(tr_y_val) X(tr_vm0) X(tr_va0)
+template <int T, bool DYN>
+__global__ void __launch_bounds__(T == 32 ? 768 : T * 32, 1) k_pf_tree(GridDev g, OpfgBatch B, int E, int env_doubles) {
+    extern __shared__ __align__(16) double sm[];
+    {
+        const int4* src = reinterpret_cast<const int4*>(g.tab4_base);
+        int4* dst = reinterpret_cast<int4*>(sm);
+        for (int i = threadIdx.x; i < g.tab4_bytes / 16; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    char* sbase = reinterpret_cast<char*>(sm);
+#define OPFG_REBASE(field) g.field = reinterpret_cast<decltype(g.field)>(sbase + (unsigned)reinterpret_cast<size_t>(g.field));
+    OPFG_TREE_TABLES(OPFG_REBASE)
+#undef OPFG_REBASE
+    const int grp = threadIdx.x / T;
+    double* mine = sm + g.tab4_bytes / 8 + (size_t)grp * env_doubles;
+    Grp<T> cx{(int)(threadIdx.x % T)};
+    for (int64_t base = (int64_t)blockIdx.x * E; base < B.n_env; base += (int64_t)gridDim.x * E) {
+        int64_t env = base + grp;
+        const bool live = env < B.n_env;
+        if (!live) env = B.n_env - 1;          // idle groups shadow the last environment (no stores)
+        env_pf_tree(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
+                    DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
+                    B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env, live);
+        __syncwarp();
+    }
+}
+static GridDev tree_view(const GridDev& d) {
+    GridDev view = d;
+#define OPFG_TO_OFFSET(field) view.field = reinterpret_cast<decltype(view.field)>((size_t)(reinterpret_cast<const char*>(d.field) - d.tab4_base));
+    OPFG_TREE_TABLES(OPFG_TO_OFFSET)
+#undef OPFG_TO_OFFSET
+    return view;
+}
+
 // Lane-per-environment Newton-Raphson (opfg_core.h, lanes_pf_solve): persistent CTAs of W warps, a warp
 // takes 32 consecutive environments at a time.  Shared memory: the schedule tables (staged once per
 // CTA when STAGED, else read through L1) and one row buffer per warp; everything else per environment
@@ -613,12 +654,19 @@ static GridDev staged_view(const GridDev& d, int stage) {
     }
 #endif
 
+// Radial grid with the dense DC pre-pass: the fused kernel (pf_kernel 0 = auto or 3 = radial)
+static bool use_tree(const OpfgGrid* G, const OpfgBatch* B) {
+    (void)B;
+    const GridDev& d = G->d;
+    return d.tr_ok && (G->pf_kernel == 0 || G->pf_kernel == 3) && (!d.init_dc || d.dc_pre);
+}
+
 // Which power-flow kernel a launch uses: the lane-per-environment kernel when its tables exist (row
 // patterns of at most 255 blocks, row buffer fits shared memory) and the DC start comes from the dense
 // pre-pass; else one CTA per environment.  OpfgGridDesc.pf_kernel / OPFG_PF_KERNEL=cta|lanes override.
 static bool use_lanes(const OpfgGrid* G, const OpfgBatch* B) {
     (void)B;
-    if (G->pf_kernel == 1) return false;
+    if (G->pf_kernel != 2) return false;
     const GridDev& d = G->d;
     return G->lanes_ok && G->lane_scratch && (!d.init_dc || d.dc_pre);
 }
@@ -704,10 +752,19 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         Symbolic& s = G->sym;
         // OPFG_PF_KERNEL=cta keeps the CTA-per-environment kernel (and its level-minimising ordering)
         int pf_kernel = desc->pf_kernel;
-        if (const char* pfk = getenv("OPFG_PF_KERNEL")) pf_kernel = !strcmp(pfk, "cta") ? 1 : (!strcmp(pfk, "lanes") ? 2 : pf_kernel);
+        if (const char* pfk = getenv("OPFG_PF_KERNEL"))
+            pf_kernel = !strcmp(pfk, "cta") ? 1 : (!strcmp(pfk, "lanes") ? 2 : (!strcmp(pfk, "radial") ? 3 : pf_kernel));
         G->pf_kernel = pf_kernel;
-        const bool want_lanes = pf_kernel != 1;
+        const bool want_lanes = pf_kernel == 2;     // measured slower than the CTA kernels on B200: opt-in
         analyse(nb, type, active, (desc->ordering == 0 && want_lanes) ? 3 : desc->ordering, T > 0 ? T : 32, s);
+        if (desc->ordering == 0 && pf_kernel != 1 && pf_kernel != 2 && s.fill_ids.size() > 0) {
+            // a radial grid has a fill-free (leaf-first) order, which is what the fused kernel needs
+            Symbolic leaf_first;
+            analyse(nb, type, active, 1, T > 0 ? T : 32, leaf_first);
+            bool forest = leaf_first.fill_ids.empty();
+            for (int k = 0; k < leaf_first.n && forest; ++k) forest = leaf_first.up_ptr[k + 1] - leaf_first.up_ptr[k] <= 1;
+            if (forest) s = leaf_first;
+        }
         if (T <= 0) T = s.n_blocks <= 1000 ? 64 : 128;   // measured: 64 on the MV grids (~450 blocks), 128 on HV (~1900)
         for (size_t c = 0; c < s.yc_branch.size(); ++c)
             if (s.yc_role[c] != 4) s.yc_branch[c] = active_row[s.yc_branch[c]];
@@ -909,6 +966,36 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                 G->lanes_ok = true;
             }
         }
+        // ---- fused kernel for radial grids: every pivot has at most one later neighbour ----
+        d.tr_ok = 0;
+        {
+            bool forest = pf_kernel != 1 && pf_kernel != 2 && d.n_qlim == 0 && nb < 65535;
+            for (int k = 0; k < s.n && forest; ++k) forest = s.up_ptr[k + 1] - s.up_ptr[k] <= 1;
+            if (forest) {
+                std::vector<int> parent(s.n, -1);
+                for (int k = 0; k < s.n; ++k)
+                    if (s.up_ptr[k + 1] > s.up_ptr[k]) parent[k] = s.up_j[s.up_ptr[k]];
+                std::vector<uint32_t> col(s.y_col.size());
+                for (int r = 0; r < nb; ++r)
+                    for (int e = s.y_ptr[r]; e < s.y_ptr[r + 1]; ++e) {
+                        const int c = s.y_col[e];
+                        const uint32_t kind = (r < s.n && c < s.n && c != r) ? (c < r ? 1u : 2u) : 0u;
+                        col[e] = (uint32_t)c | (kind << 16);
+                    }
+                char* keep_base = G->tab_base; size_t keep_cap = G->tab_cap, keep_used = G->tab_used;
+                G->tab_reserve(1024 + 4 * (size_t)(3 * nb + s.n_levels + 8) + nb + 4 * col.size() + 16 * col.size() + 16 * (size_t)nb + 16 * 12);
+                G->tab_used = 0;
+                d.tab4_base = G->tab_base;
+                d.tr_y_val = G->tab(std::vector<double>(2 * col.size(), 0.0));      // filled after the Ybus assembly
+                d.tr_vm0 = G->tab(vm0); d.tr_va0 = G->tab(va0);
+                d.tr_bus_of_int = G->tab(s.bus_of_int); d.tr_level_ptr = G->tab(s.level_ptr);
+                d.tr_y_ptr = G->tab(s.y_ptr); d.tr_parent = G->tab(parent);
+                d.tr_y_ent = G->tab(col); d.tr_type = G->tab(type_int);
+                d.tab4_bytes = (int)((G->tab_used + 15) & ~size_t(15));
+                G->tab_base = keep_base; G->tab_cap = keep_cap; G->tab_used = keep_used;
+                d.tr_ok = 1;
+            }
+        }
         if (const char* cv = getenv("OPFG_CARVEOUT")) G->carveout_pct = atoi(cv);
         G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
@@ -941,6 +1028,30 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { delete G; return fail("Ybus assembly failed: %s", cudaGetErrorString(e)); }
 #endif
+        if (d.tr_ok) {
+            const size_t ybytes = sizeof(double) * 2 * s.y_col.size();
+            G->tree_env_doubles = tree_smem_doubles(s.n, nb);
+#ifdef OPFG_HOSTSIM
+            memcpy(const_cast<double*>(d.tr_y_val), y_val, ybytes);
+#else
+            cudaMemcpy(const_cast<double*>(d.tr_y_val), y_val, ybytes, cudaMemcpyDeviceToDevice);
+            // lanes per environment: narrow levels (one pivot per feeder) leave wider groups idle; the
+            // environments that fit shared memory decide how many warps an SM gets
+            int T = getenv("OPFG_TREE_LANES") ? atoi(getenv("OPFG_TREE_LANES")) : 8;
+            if (T != 8 && T != 16 && T != 32) T = 8;
+            const size_t budget = 227 * 1024, per_env = G->tree_env_doubles * sizeof(double);
+            int E = (size_t)d.tab4_bytes < budget ? (int)((budget - d.tab4_bytes) / per_env) : 0;
+            E = std::min(E, T == 32 ? 24 : 32);          // the kernel's launch bounds
+            if (const char* ev = getenv("OPFG_TREE_ENVS")) E = std::min(E, atoi(ev));
+            E -= E % (32 / T);                         // whole warps
+            if (E < 32 / T) d.tr_ok = 0;
+            G->tree_T = T; G->tree_E = E;
+            G->tree_smem = d.tab4_bytes + (size_t)E * per_env;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&G->n_sm, cudaDevAttrMultiProcessorCount, dev);
+#endif
+        }
         if (G->lanes_ok) {
             const size_t ybytes = sizeof(double) * 2 * (size_t)s.y_ptr[s.n];
 #ifdef OPFG_HOSTSIM
@@ -1151,7 +1262,9 @@ int opfg_grid_info(const OpfgGrid* G, OpfgGridInfo* o) {
     const int n_in = d.n_state - G->n_result_cells;
     {
         OpfgBatch none{};
-        o->pf_lanes = use_lanes(G, &none) ? 1 : 0;
+        o->pf_kernel_used = use_tree(G, &none) ? 3 : (use_lanes(G, &none) ? 2 : 1);
+        o->radial_lanes_per_env = G->tree_T; o->radial_envs_per_cta = G->tree_E;
+        o->radial_smem_bytes_per_env = (int)(G->tree_env_doubles * 8);
         o->lane_max_row = d.ln_max_row; o->lane_warps_per_cta = G->lane_warps_per_cta; o->lane_tables_staged = G->lane_stage;
         o->lane_scratch_bytes = 8.0 * (double)G->lane_warp_doubles * std::max(1, G->lane_warps_per_cta * G->lane_ctas);
     }
@@ -1263,6 +1376,17 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                 B->va[env * d.nb + d.bus_of_int[i]] = acc + d.dc_theta0[i];
             }
     }
+    if (use_tree(G, B)) {
+        const GridDev& d = G->d;
+        Grp<1> gx;
+        std::vector<double> tsm(G->tree_env_doubles);
+        const bool dyn = d.n_dyn > 0 && B->yval;
+        for (int64_t env = 0; env < B->n_env; ++env)
+            env_pf_tree(d, gx, tsm.data(), B->sbus + env * (int64_t)d.nb * 2,
+                        dyn ? B->yval + env * (int64_t)d.nnz_y * 2 : nullptr, B->vm + env * (int64_t)d.nb,
+                        B->va + env * (int64_t)d.nb, B->converged + env, B->iterations + env, true);
+        return 0;
+    }
     if (use_lanes(G, B)) {
         const GridDev& d = G->d;
         const LaneMem<1> s = lane_carve<1>(G->lane_scratch, G->lane_scratch + G->lane_warp_doubles, d.nb, d.n, d.ln_n_up);
@@ -1288,6 +1412,25 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         if (!dc_attr) { cudaFuncSetAttribute(k_dc_start, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM); dc_attr = true; }
         k_dc_start<<<dim3((unsigned)((B->n_env + DC_ENVS - 1) / DC_ENVS), (unsigned)((G->d.n + 63) / 64)), 256, DC_SMEM, (cudaStream_t)stream>>>(G->d, *B);
         ++g_launches;
+    }
+    if (use_tree(G, B)) {
+        OpfgGrid* Gm = const_cast<OpfgGrid*>(G);
+        const bool dyn = G->d.n_dyn > 0 && B->yval;
+        void (*fns[6])(GridDev, OpfgBatch, int, int) = {k_pf_tree<8, false>, k_pf_tree<16, false>, k_pf_tree<32, false>,
+                                                        k_pf_tree<8, true>, k_pf_tree<16, true>, k_pf_tree<32, true>};
+        if (!Gm->tree_attr_set) {      // per grid, hence per device
+            for (auto* f : fns) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            Gm->tree_attr_set = true;
+        }
+        const int T = G->tree_T, E = G->tree_E;
+        const int64_t groups = (B->n_env + E - 1) / E;
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(groups, G->n_sm));
+        auto* fn = fns[(T == 8 ? 0 : (T == 16 ? 1 : 2)) + (dyn ? 3 : 0)];
+        fn<<<grid, T * E, G->tree_smem, (cudaStream_t)stream>>>(tree_view(G->d), *B, E, (int)G->tree_env_doubles);
+        ++g_launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail("pf_solve (radial) launch: %s", cudaGetErrorString(e));
+        return 0;
     }
     if (use_lanes(G, B)) {
         OpfgGrid* Gm = const_cast<OpfgGrid*>(G);

@@ -129,6 +129,14 @@ struct GridDev {
     const unsigned char* ln_type;
     const int* ln_qbus;                // q-limit tables (copies of qlim_*)
     const double *ln_qmin, *ln_qmax;
+    // ---- fused kernel for radial grids (every pivot has at most one later neighbour) ----
+    int tr_ok;
+    const int *tr_bus_of_int, *tr_level_ptr, *tr_y_ptr, *tr_parent;
+    const unsigned char* tr_type;
+    const uint32_t* tr_y_ent;          // per Ybus entry: column | kind << 16 (0 other, 1 child, 2 parent)
+    const double *tr_y_val, *tr_vm0, *tr_va0;
+    const char* tab4_base;
+    int tab4_bytes;
     const char* tab_base;              // contiguous arena holding the power-flow tables
     int tab_bytes;
     int tab_hot_bytes;                 // prefix holding the LU schedule
@@ -728,6 +736,213 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         if (changed > 0) { converged = 0; it = 0; prev = 1.0; goto restart_after_q_limits; }
     }
     if (cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
+}
+
+// ------------------------------------------- kernels 2-4, fused form for radial grids
+// On a radial grid (a forest once the slack bus is removed) every pivot of a leaf-first elimination
+// has ONE later neighbour, its parent: no fill, and no off-diagonal block is ever updated.  Then the
+// Jacobian need not exist in memory: the thread that eliminates pivot k computes row k of the power
+// mismatch, the diagonal block, the blocks L(k, child) it gathers with and the block U(k, parent) it
+// scales, all from V and Ybus on the spot (the loads of V_k / V_child serve mismatch and Jacobian
+// alike).  Per environment only V, 1/|V|, t and W(k, parent) live in shared memory: 8.7 KB on the
+// 122-bus grid instead of 19 KB, and one phase per level instead of three plus a row pass.  The
+// smaller footprint is spent on MORE, NARROWER environments per SM: T = 8 / 16 / 32 lanes per
+// environment, several environments per warp, synchronised by __syncwarp alone (no block barriers).
+// Every sum runs in the order of env_pf_solve: same bits.
+struct TreeSmem { double *vri, *ivm, *t, *w0, *w1; };
+OPFG_HHD size_t tree_smem_doubles(int n, int nb) {
+    size_t d = 2 * (size_t)nb + (size_t)(nb + (nb & 1)) + 6 * (size_t)n + (n & 1) * 2;
+    while (d % 16 != 4) d += 2;          // environment stride = 32 B mod 128 B: neighbours start in other banks
+    return d;
+}
+OPFG_HD TreeSmem tree_carve(double* base, int n, int nb) {
+    TreeSmem s;
+    s.vri = base; s.ivm = s.vri + 2 * (size_t)nb; s.t = s.ivm + nb + (nb & 1);
+    s.w0 = s.t + 2 * (size_t)n; s.w1 = s.w0 + 2 * (size_t)n;
+    return s;
+}
+
+#ifdef OPFG_DEVICE_BUILD
+template <int T>
+struct Grp {
+    int tid;                                   // lane within the environment's group of T lanes
+    __device__ __forceinline__ int nthreads() const { return T; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+    __device__ __forceinline__ double group_max(double v) const {   // NaN-propagating, over the T lanes
+        double bad = (v != v) ? 1.0 : 0.0;
+        v = bad > 0 ? 0.0 : v;
+#pragma unroll
+        for (int o = T / 2; o > 0; o >>= 1) {
+            v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+            bad = fmax(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+        }
+        return bad > 0 ? NAN : v;
+    }
+};
+#else
+template <int T>
+struct Grp {
+    int tid = 0;
+    int nthreads() const { return 1; }
+    void sync() const {}
+    bool any(bool p) const { return p; }
+    double group_max(double v) const { return v; }
+};
+#endif
+
+// Pivot k in ONE pass over its Ybus row: every entry feeds the row's injected current (power mismatch,
+// returned as the row's share of ||F||inf); if JAC, a child entry (an earlier pivot) also yields the
+// block L(k, child), which is multiplied with the child's W and t right away, and the parent entry is
+// remembered for U(k, parent).  After the pass: D_k = J_kk - sum L W, y_k = -F_k - sum L t, t_k = D_k^-1 y_k,
+// W_k = D_k^-1 U(k, parent).  (The sums are formed before they are subtracted from J_kk, so the last bits
+// differ from env_pf_solve, which subtracts product by product.)
+template <bool JAC>
+OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, const double* sbus, int k) {
+    const D2 sp = ldg2(sbus + 2 * g.tr_bus_of_int[k]);       // P, Q set-point (global, issued early)
+    const D2 vk = ld2(s.vri + 2 * k);
+    const bool pq = g.tr_type[k] == OPFG_PQ;
+    const int e0 = g.tr_y_ptr[k], e1 = g.tr_y_ptr[k + 1];
+    double ir = 0, ii = 0, dr = 0, di = 0;
+    double g00 = 0, g01 = 0, g10 = 0, g11 = 0, gy0 = 0, gy1 = 0, ptr = 0, pti = 0;
+    int pj = -1;
+    for (int e = e0; e < e1; ++e) {
+        const uint32_t ent = g.tr_y_ent[e];                   // column | kind << 16
+        const int j = (int)(ent & 0xffffu);
+        const D2 y = ld2(yv + 2 * e);
+        const D2 vj = ld2(s.vri + 2 * j);
+        const double tr = fma(y.x, vj.x, -(y.y * vj.y)), ti = fma(y.x, vj.y, y.y * vj.x);   // Y_kj V_j
+        ir += tr; ii += ti;
+        if (e == e0) { dr = tr; di = ti; }                    // the diagonal entry is first
+        if (JAC) {
+            const uint32_t kind = ent >> 16;
+            if (kind == 1u) {                                 // child: L(k, j) times the child's W and t
+                const double ar = fma(vk.x, tr, vk.y * ti), ai = fma(vk.y, tr, -(vk.x * ti));   // V_k conj(Y_kj V_j)
+                const double inv_vmj = s.ivm[j];
+                const double l00 = ai, l01 = ar * inv_vmj, l10 = pq ? -ar : 0.0, l11 = pq ? ai * inv_vmj : 0.0;
+                const D2 w0 = ld2(s.w0 + 2 * j), w1 = ld2(s.w1 + 2 * j), t = ld2(s.t + 2 * j);
+                g00 = fma(l01, w1.x, fma(l00, w0.x, g00));  g01 = fma(l01, w1.y, fma(l00, w0.y, g01));
+                g10 = fma(l11, w1.x, fma(l10, w0.x, g10));  g11 = fma(l11, w1.y, fma(l10, w0.y, g11));
+                gy0 = fma(l01, t.y, fma(l00, t.x, gy0));    gy1 = fma(l11, t.y, fma(l10, t.x, gy1));
+            } else if (kind == 2u) { ptr = tr; pti = ti; pj = j; }
+        }
+    }
+    const double P = fma(vk.x, ir, vk.y * ii), Q = fma(vk.y, ir, -(vk.x * ii));   // S_k = V_k conj(I_k)
+    const double dp = P - sp.x, dq = pq ? Q - sp.y : 0.0;
+    double res;
+    if (dp != dp || dq != dq) res = NAN;
+    else { const double a = fabs(dp), c = fabs(dq); res = a > c ? a : c; }
+    if (!JAC) return res;
+    const double ar = fma(vk.x, dr, vk.y * di), ai = fma(vk.y, dr, -(vk.x * di));   // V_k conj(Y_kk V_k)
+    const double inv_vmk = s.ivm[k];
+    const double d00 = (-Q + ai) - g00, d01 = (ar + P) * inv_vmk - g01;
+    const double d10 = (pq ? P - ar : 0.0) - g10, d11 = (pq ? (ai + Q) * inv_vmk : 1.0) - g11;
+    const double y0 = -dp - gy0, y1 = -dq - gy1;
+    const double r = 1.0 / fma(d00, d11, -(d01 * d10));
+    const double ia = d11 * r, ib = -d01 * r, ic = -d10 * r, id_ = d00 * r;
+    st2(s.t + 2 * k, fma(ia, y0, ib * y1), fma(ic, y0, id_ * y1));
+    if (pj >= 0) {                                            // U(k, parent) -> W_k
+        const double ur = fma(vk.x, ptr, vk.y * pti), ui = fma(vk.y, ptr, -(vk.x * pti));
+        const double inv_vmj = s.ivm[pj];
+        const double u00 = ui, u01 = ur * inv_vmj, u10 = pq ? -ur : 0.0, u11 = pq ? ui * inv_vmj : 0.0;
+        st2(s.w0 + 2 * k, fma(ia, u00, ib * u10), fma(ia, u01, ib * u11));
+        st2(s.w1 + 2 * k, fma(ic, u00, id_ * u10), fma(ic, u01, id_ * u11));
+    }
+    return res;
+}
+
+template <class C>
+OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const double* sbus, const double* yval_env,
+                         double* vm_out, double* va_out, uint8_t* conv_out, int32_t* iter_out, bool live) {
+    const int T = cx.nthreads();
+    const int n = g.n, nb = g.nb;
+    const TreeSmem s = tree_carve(smem, n, nb);
+    const double* yv = yval_env ? yval_env : g.tr_y_val;
+    for (int i = cx.tid; i < nb; i += T) {
+        const double vm = g.tr_vm0[i];
+        const int bus = g.tr_bus_of_int[i];
+        const double va = (g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i];   // DC start: the dense pre-pass wrote it
+        double sn, cs;
+        sincos(va, &sn, &cs);
+        if (live) { vm_out[bus] = vm; va_out[bus] = va; }
+        s.ivm[i] = 1.0 / vm;
+        st2(s.vri + 2 * i, vm * cs, vm * sn);
+    }
+    cx.sync();
+    bool active = live;
+    int it = 0, converged = 0;
+    double prev = 1.0;
+    while (cx.any(active)) {
+        if (!cx.any(active && !(prev < 1e-4))) {
+            // every environment of the warp that still runs expects to have converged: mismatch alone
+            double part = 0;
+            bool bad = false;
+            for (int k = cx.tid; k < n; k += T) {
+                const double r = tree_row<false>(g, s, yv, sbus, k);
+                if (r != r) bad = true; else if (r > part) part = r;
+            }
+            const double nrm = cx.group_max(bad ? NAN : part);
+            if (active) {
+                prev = nrm;
+                if (nrm < g.tol) { converged = 1; active = false; }
+                else if (it >= g.max_iter || nrm != nrm) active = false;
+            }
+            if (!cx.any(active)) break;
+        }
+        double part = 0;
+        bool bad = false;
+        for (int l = 0; l < g.n_levels; ++l) {               // leaves first: one phase per level
+            const int le = g.tr_level_ptr[l + 1];
+            for (int k = g.tr_level_ptr[l] + cx.tid; k < le; k += T) {
+                const double r = tree_row<true>(g, s, yv, sbus, k);
+                if (r != r) bad = true; else if (r > part) part = r;
+            }
+            cx.sync();
+        }
+        const double nrm = cx.group_max(bad ? NAN : part);
+        bool step = false;
+        if (active) {
+            prev = nrm;
+            if (nrm < g.tol) { converged = 1; active = false; }
+            else if (it >= g.max_iter || nrm != nrm) active = false;
+            else { ++it; step = true; }
+        }
+        if (!cx.any(step)) continue;
+        for (int l = g.n_levels - 1; l >= 0; --l) {           // x_k = t_k - W_k x_parent
+            const int le = g.tr_level_ptr[l + 1];
+            for (int k = g.tr_level_ptr[l] + cx.tid; k < le; k += T) {
+                const int p = g.tr_parent[k];
+                if (p < 0) continue;
+                D2 x = ld2(s.t + 2 * k);
+                const D2 w0 = ld2(s.w0 + 2 * k), w1 = ld2(s.w1 + 2 * k), xj = ld2(s.t + 2 * p);
+                x.x = fma(-w0.y, xj.y, fma(-w0.x, xj.x, x.x));
+                x.y = fma(-w1.y, xj.y, fma(-w1.x, xj.x, x.y));
+                st2(s.t + 2 * k, x.x, x.y);
+            }
+            cx.sync();
+        }
+        if (step) {
+            // polar update (newtonpf.py); |V| and angle live in the output buffers (L2): the next pair is
+            // fetched while the current one goes through sincos
+            double va_n = 0, vm_n = 0;
+            if (cx.tid < n) { const int b0 = g.tr_bus_of_int[cx.tid]; va_n = va_out[b0]; vm_n = vm_out[b0]; }
+            for (int k = cx.tid; k < n; k += T) {
+                const D2 dx = ld2(s.t + 2 * k);
+                const int bus = g.tr_bus_of_int[k];
+                double va = va_n + dx.x;
+                double vm = vm_n + ((g.tr_type[k] == OPFG_PQ) ? dx.y : 0.0);
+                if (k + T < n) { const int b1 = g.tr_bus_of_int[k + T]; va_n = va_out[b1]; vm_n = vm_out[b1]; }
+                if (vm < 0) { vm = -vm; va += M_PI; }
+                if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
+                double sn, cs;
+                sincos(va, &sn, &cs);
+                va_out[bus] = va; vm_out[bus] = vm; s.ivm[k] = 1.0 / vm;
+                st2(s.vri + 2 * k, vm * cs, vm * sn);
+            }
+        }
+        cx.sync();
+    }
+    if (live && cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
 }
 
 // ------------------------------------------- kernels 2-4, lane-per-environment form

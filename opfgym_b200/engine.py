@@ -41,7 +41,7 @@ class Engine:
             capi, program, tol_pu=tolerance_mva / program.ppc.base_mva,
             max_iter=max_iteration, init_dc=(init == "dc"), enforce_q_lims=enforce_q_lims,
             threads_per_env=threads_per_env, ordering=ordering,
-            pf_kernel={"auto": 0, "cta": 1, "lanes": 2}.get(pf_kernel, pf_kernel))
+            pf_kernel={"auto": 0, "cta": 1, "lanes": 2, "radial": 3}.get(pf_kernel, pf_kernel))
         handle = C.c_void_p()
         capi.check(self.lib, self.lib.opfg_grid_create(C.byref(gd), C.byref(handle)))
         self.handle = handle

@@ -14,6 +14,13 @@ def main():
     for v in variants:
         kernel, _, w = v.partition(":")
         stage = None
+        if kernel == "radial" and w:          # radial:T or radial:TxE
+            t, _, e = w.partition("x")
+            os.environ["OPFG_TREE_LANES"] = t
+            os.environ.pop("OPFG_TREE_ENVS", None)
+            if e:
+                os.environ["OPFG_TREE_ENVS"] = e
+            w = ""
         if w and "s" in w:
             w, stage = w.split("s")
         if w:
@@ -25,7 +32,8 @@ def main():
         eng.assemble()
         ms = timeit(eng.pf_solve)
         i = eng.info
-        print(f"{name} B={B} {v:10s} lanes={i['pf_lanes']} W={i['lane_warps_per_cta']} staged={i['lane_tables_staged']} "
+        print(f"{name} B={B} {v:12s} kernel={i['pf_kernel_used']} T={i['radial_lanes_per_env']} E={i['radial_envs_per_cta']} "
+              f"env_smem={i['radial_smem_bytes_per_env']} W={i['lane_warps_per_cta']} staged={i['lane_tables_staged']} "
               f"max_row={i['lane_max_row']} blocks={i['n_blocks']} levels={i['n_levels']} scratch={i['lane_scratch_bytes']/1e6:.0f} MB "
               f"pf={ms:.3f} ms -> {B/ms*1e3:.3e} env/s iters={eng.iterations.float().mean().item():.2f} "
               f"conv={eng.converged.float().mean().item():.4f}", flush=True)

@@ -7,13 +7,13 @@ import pytest
 from tests import common
 
 
-def _pair(engine_cls, name, n_env, seed, lam=None, sync=lambda: None, **kw):
+def _pair(engine_cls, name, n_env, seed, lam=None, sync=lambda: None, kernels=("cta", "lanes"), **kw):
     case = common.make_case(name)
     out = {}
-    for kernel in ("cta", "lanes"):
-        # same elimination order for both (3 = least fill work, what the lane kernel picks by itself)
-        eng = engine_cls(case.program, n_env, obs_dtype="float64", pf_kernel=kernel, ordering=3, **kw)
-        assert eng.info["pf_lanes"] == (kernel == "lanes"), eng.info
+    for kernel in kernels:
+        # same elimination order for all (1 = minimum degree: leaf-first on radial grids)
+        eng = engine_cls(case.program, n_env, obs_dtype="float64", pf_kernel=kernel, ordering=1, **kw)
+        assert eng.info["pf_kernel_used"] == {"cta": 1, "lanes": 2, "radial": 3}[kernel], eng.info
         common.randomize(case, eng, seed=seed)
         eng.assemble()
         sync()
@@ -31,7 +31,13 @@ def _pair(engine_cls, name, n_env, seed, lam=None, sync=lambda: None, **kw):
 
 
 def _same(out, mixed):
-    a, b = out["cta"], out["lanes"]
+    names = list(out)
+    for other in names[1:]:
+        # the radial kernel forms sum(L W) before subtracting it from J_kk: last bits differ
+        _same2(out[names[0]], out[other], mixed, exact=other != "radial")
+
+
+def _same2(a, b, mixed, exact=True):
     if mixed:
         assert 0.1 < a["converged"].mean() < 0.9
     else:
@@ -39,29 +45,47 @@ def _same(out, mixed):
     for k in ("converged", "iterations"):
         assert np.array_equal(a[k], b[k]), k
     ok = a["converged"].astype(bool)
+    if not exact:
+        for k, tol in (("vm", 1e-11), ("va", 1e-11), ("reward", 1e-9), ("obs", 1e-8)):
+            np.testing.assert_allclose(a[k][ok], b[k][ok], rtol=0, atol=tol, err_msg=k)
+        return
     for k in ("vm", "va", "reward", "obs"):
         assert np.array_equal(a[k][ok].view(np.int64), b[k][ok].view(np.int64)), k
     # diverging environments: the iterates agree bit for bit as well (NaN patterns included)
     assert np.array_equal(a["vm"].view(np.int64), b["vm"].view(np.int64))
 
 
-@pytest.mark.parametrize("name", ["1-MV-semiurb--1-sw", "1-HV-urban--0-sw"])
-def test_lanes_equal_cta_hostsim(name):
-    from tests.hostsim.harness import HostSimEngine
-    _same(_pair(HostSimEngine, name, 24, seed=31), mixed=False)
+ALL = ("cta", "lanes", "radial")
 
 
-def test_lanes_equal_cta_at_the_convergence_boundary_hostsim():
+@pytest.mark.parametrize("name,kernels", [("1-MV-semiurb--1-sw", ALL), ("1-MV-rural--0-sw", ALL),
+                                          ("1-HV-urban--0-sw", ("cta", "lanes"))])
+def test_kernels_agree_hostsim(name, kernels):
     from tests.hostsim.harness import HostSimEngine
-    _same(_pair(HostSimEngine, "1-MV-semiurb--1-sw", 96, seed=32, lam=(5.0, 12.0)), mixed=True)
+    _same(_pair(HostSimEngine, name, 24, seed=31, kernels=kernels), mixed=False)
+
+
+def test_kernels_agree_at_the_convergence_boundary_hostsim():
+    from tests.hostsim.harness import HostSimEngine
+    _same(_pair(HostSimEngine, "1-MV-semiurb--1-sw", 96, seed=32, lam=(5.0, 12.0), kernels=ALL), mixed=True)
+
+
+def test_auto_picks_the_radial_kernel_on_radial_grids_only():
+    from tests.hostsim.harness import HostSimEngine
+    for name, used in (("1-MV-semiurb--1-sw", 3), ("1-HV-urban--0-sw", 1)):
+        case = common.make_case(name)
+        eng = HostSimEngine(case.program, 2)
+        assert eng.info["pf_kernel_used"] == used, (name, eng.info)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,n_env,lam", [("1-MV-semiurb--1-sw", 4133, None),
-                                            ("1-MV-semiurb--1-sw", 4096, (5.0, 12.0)),
-                                            ("1-HV-urban--0-sw", 1000, None),
-                                            ("1-HV-urban--0-sw", 1024, (3.0, 9.0))])
-def test_lanes_equal_cta_cuda(cuda_lib, name, n_env, lam):
+@pytest.mark.parametrize("name,n_env,lam,kernels", [("1-MV-semiurb--1-sw", 4133, None, ALL),
+                                                    ("1-MV-semiurb--1-sw", 4096, (5.0, 12.0), ALL),
+                                                    ("1-MV-rural--0-sw", 2000, None, ALL),
+                                                    ("1-HV-urban--0-sw", 1000, None, ("cta", "lanes")),
+                                                    ("1-HV-urban--0-sw", 1024, (5.0, 14.0), ("cta", "lanes"))])
+def test_kernels_agree_cuda(cuda_lib, name, n_env, lam, kernels):
     import torch
     from opfgym_b200.engine import Engine
-    _same(_pair(Engine, name, n_env, seed=33, lam=lam, sync=torch.cuda.synchronize), mixed=lam is not None)
+    _same(_pair(Engine, name, n_env, seed=33, lam=lam, sync=torch.cuda.synchronize, kernels=kernels),
+          mixed=lam is not None)
