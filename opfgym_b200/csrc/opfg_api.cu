@@ -654,6 +654,15 @@ static GridDev staged_view(const GridDev& d, int stage) {
     }
 #endif
 
+// lanes per environment of the fused radial kernel (also the cap of its balanced levels).  Measured on
+// the 122-bus grid (B200, 32 768 environments): 8 lanes 1.27 ms, 16 lanes 1.00 ms, 32 lanes 1.26 ms --
+// the kernel is bound by the latency of its level chain, more lanes mean fewer rounds per level until
+// the idle lanes of the narrow levels cost more issue slots than the rounds save.
+static int tree_lanes() {
+    const int T = getenv("OPFG_TREE_LANES") ? atoi(getenv("OPFG_TREE_LANES")) : 16;
+    return (T == 8 || T == 16 || T == 32) ? T : 16;
+}
+
 // Radial grid with the dense DC pre-pass: the fused kernel (pf_kernel 0 = auto or 3 = radial)
 static bool use_tree(const OpfgGrid* G, const OpfgBatch* B) {
     (void)B;
@@ -760,7 +769,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         if (desc->ordering == 0 && pf_kernel != 1 && pf_kernel != 2 && s.fill_ids.size() > 0) {
             // a radial grid has a fill-free (leaf-first) order, which is what the fused kernel needs
             Symbolic leaf_first;
-            analyse(nb, type, active, 1, T > 0 ? T : 32, leaf_first);
+            analyse(nb, type, active, 1, T > 0 ? T : 32, leaf_first, tree_lanes());
             bool forest = leaf_first.fill_ids.empty();
             for (int k = 0; k < leaf_first.n && forest; ++k) forest = leaf_first.up_ptr[k + 1] - leaf_first.up_ptr[k] <= 1;
             if (forest) s = leaf_first;
@@ -1037,8 +1046,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             cudaMemcpy(const_cast<double*>(d.tr_y_val), y_val, ybytes, cudaMemcpyDeviceToDevice);
             // lanes per environment: narrow levels (one pivot per feeder) leave wider groups idle; the
             // environments that fit shared memory decide how many warps an SM gets
-            int T = getenv("OPFG_TREE_LANES") ? atoi(getenv("OPFG_TREE_LANES")) : 8;
-            if (T != 8 && T != 16 && T != 32) T = 8;
+            const int T = tree_lanes();
             const size_t budget = 227 * 1024, per_env = G->tree_env_doubles * sizeof(double);
             int E = (size_t)d.tab4_bytes < budget ? (int)((budget - d.tab4_bytes) / per_env) : 0;
             E = std::min(E, T == 32 ? 24 : 32);          // the kernel's launch bounds

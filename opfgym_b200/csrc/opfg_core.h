@@ -797,53 +797,71 @@ struct Grp {
 // remembered for U(k, parent).  After the pass: D_k = J_kk - sum L W, y_k = -F_k - sum L t, t_k = D_k^-1 y_k,
 // W_k = D_k^-1 U(k, parent).  (The sums are formed before they are subtracted from J_kk, so the last bits
 // differ from env_pf_solve, which subtracts product by product.)
+struct TreeAcc {
+    double ir, ii, g00, g01, g10, g11, gy0, gy1, ptr, pti;
+    int pj;
+};
+// one off-diagonal Ybus entry (k, j) of pivot k, its values already loaded
 template <bool JAC>
-OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, const double* sbus, int k) {
-    const D2 sp = ldg2(sbus + 2 * g.tr_bus_of_int[k]);       // P, Q set-point (global, issued early)
+OPFG_HD void tree_entry(const TreeSmem& s, TreeAcc& a, uint32_t ent, D2 y, D2 vj, D2 vk, bool pq) {
+    const double tr = fma(y.x, vj.x, -(y.y * vj.y)), ti = fma(y.x, vj.y, y.y * vj.x);   // Y_kj V_j
+    a.ir += tr; a.ii += ti;
+    if (JAC) {
+        const uint32_t kind = ent >> 16;
+        if (kind == 1u) {                                     // child: L(k, j) times the child's W and t
+            const int j = (int)(ent & 0xffffu);
+            const double ar = fma(vk.x, tr, vk.y * ti), ai = fma(vk.y, tr, -(vk.x * ti));   // V_k conj(Y_kj V_j)
+            const double inv_vmj = s.ivm[j];
+            const double l00 = ai, l01 = ar * inv_vmj, l10 = pq ? -ar : 0.0, l11 = pq ? ai * inv_vmj : 0.0;
+            const D2 w0 = ld2(s.w0 + 2 * j), w1 = ld2(s.w1 + 2 * j), t = ld2(s.t + 2 * j);
+            a.g00 = fma(l01, w1.x, fma(l00, w0.x, a.g00));  a.g01 = fma(l01, w1.y, fma(l00, w0.y, a.g01));
+            a.g10 = fma(l11, w1.x, fma(l10, w0.x, a.g10));  a.g11 = fma(l11, w1.y, fma(l10, w0.y, a.g11));
+            a.gy0 = fma(l01, t.y, fma(l00, t.x, a.gy0));    a.gy1 = fma(l11, t.y, fma(l10, t.x, a.gy1));
+        } else if (kind == 2u) { a.ptr = tr; a.pti = ti; a.pj = (int)(ent & 0xffffu); }
+    }
+}
+
+template <bool JAC>
+OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D2 sp, int k) {
     const D2 vk = ld2(s.vri + 2 * k);
     const bool pq = g.tr_type[k] == OPFG_PQ;
     const int e0 = g.tr_y_ptr[k], e1 = g.tr_y_ptr[k + 1];
-    double ir = 0, ii = 0, dr = 0, di = 0;
-    double g00 = 0, g01 = 0, g10 = 0, g11 = 0, gy0 = 0, gy1 = 0, ptr = 0, pti = 0;
-    int pj = -1;
-    for (int e = e0; e < e1; ++e) {
-        const uint32_t ent = g.tr_y_ent[e];                   // column | kind << 16
-        const int j = (int)(ent & 0xffffu);
-        const D2 y = ld2(yv + 2 * e);
-        const D2 vj = ld2(s.vri + 2 * j);
-        const double tr = fma(y.x, vj.x, -(y.y * vj.y)), ti = fma(y.x, vj.y, y.y * vj.x);   // Y_kj V_j
-        ir += tr; ii += ti;
-        if (e == e0) { dr = tr; di = ti; }                    // the diagonal entry is first
-        if (JAC) {
-            const uint32_t kind = ent >> 16;
-            if (kind == 1u) {                                 // child: L(k, j) times the child's W and t
-                const double ar = fma(vk.x, tr, vk.y * ti), ai = fma(vk.y, tr, -(vk.x * ti));   // V_k conj(Y_kj V_j)
-                const double inv_vmj = s.ivm[j];
-                const double l00 = ai, l01 = ar * inv_vmj, l10 = pq ? -ar : 0.0, l11 = pq ? ai * inv_vmj : 0.0;
-                const D2 w0 = ld2(s.w0 + 2 * j), w1 = ld2(s.w1 + 2 * j), t = ld2(s.t + 2 * j);
-                g00 = fma(l01, w1.x, fma(l00, w0.x, g00));  g01 = fma(l01, w1.y, fma(l00, w0.y, g01));
-                g10 = fma(l11, w1.x, fma(l10, w0.x, g10));  g11 = fma(l11, w1.y, fma(l10, w0.y, g11));
-                gy0 = fma(l01, t.y, fma(l00, t.x, gy0));    gy1 = fma(l11, t.y, fma(l10, t.x, gy1));
-            } else if (kind == 2u) { ptr = tr; pti = ti; pj = j; }
-        }
+    TreeAcc a{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1};
+    double dr, di;
+    {                                                         // the diagonal entry is first
+        const D2 y = ld2(yv + 2 * e0);
+        dr = fma(y.x, vk.x, -(y.y * vk.y)); di = fma(y.x, vk.y, y.y * vk.x);
+        a.ir = dr; a.ii = di;
     }
-    const double P = fma(vk.x, ir, vk.y * ii), Q = fma(vk.y, ir, -(vk.x * ii));   // S_k = V_k conj(I_k)
+    int e = e0 + 1;
+    for (; e + 1 < e1; e += 2) {                              // two entries per trip: their loads overlap
+        const uint32_t ea = g.tr_y_ent[e], eb = g.tr_y_ent[e + 1];
+        const D2 ya = ld2(yv + 2 * e), yb = ld2(yv + 2 * e + 2);
+        const D2 va = ld2(s.vri + 2 * (ea & 0xffffu)), vb = ld2(s.vri + 2 * (eb & 0xffffu));
+        tree_entry<JAC>(s, a, ea, ya, va, vk, pq);
+        tree_entry<JAC>(s, a, eb, yb, vb, vk, pq);
+    }
+    if (e < e1) {
+        const uint32_t ea = g.tr_y_ent[e];
+        tree_entry<JAC>(s, a, ea, ld2(yv + 2 * e), ld2(s.vri + 2 * (ea & 0xffffu)), vk, pq);
+    }
+    const double P = fma(vk.x, a.ir, vk.y * a.ii), Q = fma(vk.y, a.ir, -(vk.x * a.ii));   // S_k = V_k conj(I_k)
     const double dp = P - sp.x, dq = pq ? Q - sp.y : 0.0;
     double res;
     if (dp != dp || dq != dq) res = NAN;
-    else { const double a = fabs(dp), c = fabs(dq); res = a > c ? a : c; }
+    else { const double x = fabs(dp), c = fabs(dq); res = x > c ? x : c; }
     if (!JAC) return res;
     const double ar = fma(vk.x, dr, vk.y * di), ai = fma(vk.y, dr, -(vk.x * di));   // V_k conj(Y_kk V_k)
     const double inv_vmk = s.ivm[k];
-    const double d00 = (-Q + ai) - g00, d01 = (ar + P) * inv_vmk - g01;
-    const double d10 = (pq ? P - ar : 0.0) - g10, d11 = (pq ? (ai + Q) * inv_vmk : 1.0) - g11;
-    const double y0 = -dp - gy0, y1 = -dq - gy1;
+    const double d00 = (-Q + ai) - a.g00, d01 = (ar + P) * inv_vmk - a.g01;
+    const double d10 = (pq ? P - ar : 0.0) - a.g10, d11 = (pq ? (ai + Q) * inv_vmk : 1.0) - a.g11;
+    const double y0 = -dp - a.gy0, y1 = -dq - a.gy1;
     const double r = 1.0 / fma(d00, d11, -(d01 * d10));
     const double ia = d11 * r, ib = -d01 * r, ic = -d10 * r, id_ = d00 * r;
     st2(s.t + 2 * k, fma(ia, y0, ib * y1), fma(ic, y0, id_ * y1));
-    if (pj >= 0) {                                            // U(k, parent) -> W_k
-        const double ur = fma(vk.x, ptr, vk.y * pti), ui = fma(vk.y, ptr, -(vk.x * pti));
-        const double inv_vmj = s.ivm[pj];
+    if (a.pj >= 0) {                                          // U(k, parent) -> W_k
+        const double ur = fma(vk.x, a.ptr, vk.y * a.pti), ui = fma(vk.y, a.ptr, -(vk.x * a.pti));
+        const double inv_vmj = s.ivm[a.pj];
         const double u00 = ui, u01 = ur * inv_vmj, u10 = pq ? -ur : 0.0, u11 = pq ? ui * inv_vmj : 0.0;
         st2(s.w0 + 2 * k, fma(ia, u00, ib * u10), fma(ia, u01, ib * u11));
         st2(s.w1 + 2 * k, fma(ic, u00, id_ * u10), fma(ic, u01, id_ * u11));
@@ -878,7 +896,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             double part = 0;
             bool bad = false;
             for (int k = cx.tid; k < n; k += T) {
-                const double r = tree_row<false>(g, s, yv, sbus, k);
+                const double r = tree_row<false>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
                 if (r != r) bad = true; else if (r > part) part = r;
             }
             const double nrm = cx.group_max(bad ? NAN : part);
@@ -891,11 +909,25 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
         }
         double part = 0;
         bool bad = false;
-        for (int l = 0; l < g.n_levels; ++l) {               // leaves first: one phase per level
+        // leaves first, one phase per level; the set-point of the NEXT level's pivot (global memory) is
+        // requested before this level's pivot is worked on
+        D2 sp_next{0, 0};
+        { const int k0 = g.tr_level_ptr[0] + cx.tid; if (k0 < g.tr_level_ptr[1]) sp_next = ldg2(sbus + 2 * g.tr_bus_of_int[k0]); }
+        for (int l = 0; l < g.n_levels; ++l) {
             const int le = g.tr_level_ptr[l + 1];
-            for (int k = g.tr_level_ptr[l] + cx.tid; k < le; k += T) {
-                const double r = tree_row<true>(g, s, yv, sbus, k);
+            const D2 sp0 = sp_next;
+            if (l + 1 < g.n_levels) {
+                const int k1 = le + cx.tid;
+                if (k1 < g.tr_level_ptr[l + 2]) sp_next = ldg2(sbus + 2 * g.tr_bus_of_int[k1]);
+            }
+            int k = g.tr_level_ptr[l] + cx.tid;
+            if (k < le) {
+                double r = tree_row<true>(g, s, yv, sp0, k);
                 if (r != r) bad = true; else if (r > part) part = r;
+                for (k += T; k < le; k += T) {                // levels wider than the group (unbalanced schedule)
+                    r = tree_row<true>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
+                    if (r != r) bad = true; else if (r > part) part = r;
+                }
             }
             cx.sync();
         }

@@ -116,7 +116,7 @@ std::vector<int> independent_set_sequence(const std::vector<std::set<int>>& adj0
 // Turn an elimination sequence into a levelled order: level = longest dependency
 // path; pivots renumbered by (level, position in seq).
 Order make_order(const std::vector<std::set<int>>& adj0, const std::vector<int>& seq, int threads,
-                 const std::string& name) {
+                 const std::string& name, int level_cap = 0) {
     const int n = (int)adj0.size();
     auto nb_at = eliminate(adj0, seq);
     std::vector<int> pos(n);
@@ -125,6 +125,35 @@ Order make_order(const std::vector<std::set<int>>& adj0, const std::vector<int>&
     for (int i = 0; i < n; ++i) {   // seq order is a valid topological order
         int v = seq[i];
         for (int a : nb_at[v]) level[a] = std::max(level[a], level[v] + 1);
+    }
+    if (level_cap > 0) {
+        // Balanced levels: at most `level_cap` pivots per level.  A pivot may run later than its
+        // earliest level as long as everything that depends on it still fits: list scheduling by
+        // latest start (the tail of a radial feeder is a chain, its leaves have slack to spare).
+        int n_lv = 0;
+        for (int v = 0; v < n; ++v) n_lv = std::max(n_lv, level[v] + 1);
+        std::vector<int> latest(n, n_lv - 1);
+        for (int i = n - 1; i >= 0; --i) {
+            const int v = seq[i];
+            for (int a : nb_at[v]) latest[v] = std::min(latest[v], latest[a] - 1);
+        }
+        std::vector<int> pending(n, 0), assigned(n, -1);   // predecessors not yet scheduled
+        std::vector<std::vector<int>> preds(n);
+        for (int v = 0; v < n; ++v) for (int a : nb_at[v]) { preds[a].push_back(v); pending[a]++; }
+        std::vector<int> ready;
+        for (int v = 0; v < n; ++v) if (!pending[v]) ready.push_back(v);
+        int done = 0, round = 0;
+        while (done < n) {
+            std::stable_sort(ready.begin(), ready.end(), [&](int a, int b) {
+                return latest[a] != latest[b] ? latest[a] < latest[b] : pos[a] < pos[b]; });
+            const int take = std::min<int>((int)ready.size(), level_cap);
+            std::vector<int> now(ready.begin(), ready.begin() + take);
+            ready.erase(ready.begin(), ready.begin() + take);
+            for (int v : now) { assigned[v] = round; ++done; }
+            for (int v : now) for (int a : nb_at[v]) if (--pending[a] == 0) ready.push_back(a);
+            ++round;
+        }
+        level = assigned;
     }
     std::vector<int> by(n);
     for (int i = 0; i < n; ++i) by[i] = seq[i];
@@ -169,7 +198,7 @@ inline int64_t key(int i, int j) { return ((int64_t)i << 32) | (uint32_t)j; }
 }  // namespace
 
 void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchHost>& branches,
-             int ordering, int threads, Symbolic& s) {
+             int ordering, int threads, Symbolic& s, int level_cap) {
     s = Symbolic();
     s.nb = nb;
     std::vector<int> node_of_bus(nb, -1), bus_of_node;
@@ -186,7 +215,7 @@ void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchH
     std::vector<Order> cands;
     const bool least_work = ordering == 3;     // lane-per-environment kernel: levels are irrelevant, fill is work
     if (least_work) ordering = 0;
-    if (ordering == 0 || ordering == 1) cands.push_back(make_order(adj, min_degree_sequence(adj), threads, "min_degree"));
+    if (ordering == 0 || ordering == 1) cands.push_back(make_order(adj, min_degree_sequence(adj), threads, "min_degree", level_cap));
     if (ordering == 0 || ordering == 2) {
         cands.push_back(make_order(adj, independent_set_sequence(adj, 0), threads, "independent_set"));
         cands.push_back(make_order(adj, independent_set_sequence(adj, 1), threads, "independent_set+1"));

@@ -72,8 +72,9 @@ void build_lane_schedule(const Symbolic& s, LaneSchedule& out);
 
 // ordering: 0 auto (cheapest by the CTA kernel's cost model), 1 minimum degree, 2 independent-set rounds,
 // 3 least work (fewest Schur-update pairs; what the lane-per-environment kernel wants)
+// level_cap > 0 (minimum-degree order only): at most that many pivots per level (balanced levels)
 void analyse(int nb, const std::vector<int>& bus_type, const std::vector<BranchHost>& branches,
-             int ordering, int threads_per_env, Symbolic& out);
+             int ordering, int threads_per_env, Symbolic& out, int level_cap = 0);
 
 // scalar LU of the DC matrix B'[nonref, nonref] on the same schedule.
 // Outputs indexed by block id: inv_d[k] (k<n), val[id] = W for U blocks, L~ for L blocks.
