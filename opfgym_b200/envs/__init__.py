@@ -2,7 +2,7 @@
 The reference registers ``*-v0`` ids with gymnasium; the same ids are registered
 here when gymnasium is importable, and ``make(id, num_envs=...)`` works either way."""
 from .eco_dispatch import EcoDispatch
-from .load_shedding import LoadShedding
+from .load_shedding import LoadShedding, LoadSheddingReconfiguration
 from .max_renewable import MaxRenewable
 from .q_market import QMarket
 from .voltage_control import VoltageControl

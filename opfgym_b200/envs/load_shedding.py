@@ -31,9 +31,13 @@ class LoadShedding(BatchedOpfEnv):
                       ("load", "q_mvar", net.load.index), ("storage", "p_mw", free_storage)]
         act_keys = [("load", "p_mw", net.load.index[net.load.controllable]),
                     ("storage", "p_mw", net.storage.index[net.storage.controllable])]
+        act_keys += self._extra_action_keys(net)
         super().__init__(net, act_keys, obs_keys, state_keys=state_keys, profiles=profiles,
                          num_envs=num_envs, pwl_price_columns=["price_charge", "price_discharge"],
                          **kwargs)
+
+    def _extra_action_keys(self, net):
+        return []
 
     def _define_opf(self, simbench_network_name, **kwargs):
         net, profiles = build_simbench_net(simbench_network_name, **kwargs)
@@ -92,3 +96,28 @@ class LoadShedding(BatchedOpfEnv):
         self.run_row_program("ls_prices", "pwl_cost", prices)
         self.run_row_program("ls_load", "load", load_bounds)
         self.run_row_program("ls_storage", "storage", storage_bounds)
+
+
+class LoadSheddingReconfiguration(LoadShedding):
+    """BASELINE.json config 5: LoadShedding whose agent also moves the transformer tap changers and
+    switches the normally-open tie lines -- per-environment Ybus values.  The reference LoadShedding
+    has no such actuators (SURVEY.md 8d calls this an extension); their semantics are those of the
+    reference's ``examples/network_reconfiguration.py:34-35, 49-60``: ``trafo.tap_pos`` and
+    ``line.in_service`` columns with ``min_`` / ``max_`` bounds, rounded by ``_apply_actions``
+    (``opf_env.py:476-481``)."""
+
+    def __init__(self, *args, tap_range: int = 3, **kwargs):
+        self.tap_range = int(tap_range)
+        super().__init__(*args, **kwargs)
+
+    def _define_opf(self, simbench_network_name, **kwargs):
+        net, profiles = LoadShedding._define_opf(self, simbench_network_name, **kwargs)
+        net.trafo["min_tap_pos"] = -float(self.tap_range)
+        net.trafo["max_tap_pos"] = float(self.tap_range)
+        net.line["min_in_service"] = 0.0
+        net.line["max_in_service"] = 1.0
+        return net, profiles
+
+    def _extra_action_keys(self, net):
+        ties = net.line.index[~net.line.in_service]
+        return [("trafo", "tap_pos", net.trafo.index), ("line", "in_service", ties)]

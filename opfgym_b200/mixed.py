@@ -62,6 +62,27 @@ class MixedBatchEnv:
                 "cost": xp.cat([o[4]["cost"] for o in outs])}
         return obs, reward, term, trunc, info
 
+    def step_host(self, actions):
+        """Host-buffer form (``BatchedOpfEnv.step_host``): member after member, each with its own
+        look-ahead pipeline; numpy results concatenated (observations padded with NaN)."""
+        import numpy as np
+        xp = self.xp
+        act = xp.as_tensor(actions)
+        outs, row = [], 0
+        for e in self.envs:
+            a = act[row:row + e.num_envs, :e.single_action_space.shape[0]]
+            outs.append(e.step_host(a if a.is_contiguous() else a.contiguous()))
+            row += e.num_envs
+        obs = np.full((self.num_envs, self.n_obs), np.nan, dtype=outs[0][0].dtype)
+        row = 0
+        for o, e in zip(outs, self.envs):
+            obs[row:row + e.num_envs, :o[0].shape[1]] = o[0]
+            row += e.num_envs
+        cat = lambda k: np.concatenate([o[k] for o in outs])
+        info = {"cost": np.concatenate([o[4]["cost"] for o in outs]),
+                "converged": np.concatenate([o[4]["converged"] for o in outs])}
+        return obs, cat(1), cat(2), cat(3), info
+
     def episode_statistics(self, reduce=True):
         stats = [e.episode_statistics(reduce=reduce) for e in self.envs]
         steps = sum(s["steps"] for s in stats)
