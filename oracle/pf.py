@@ -26,9 +26,11 @@ import numpy as np
 import scipy.sparse as sp
 from scipy.sparse.linalg import spsolve
 
-from opfgym_b200.ppc import (BASE_KV, BR_B, BR_G, BR_R, BR_STATUS, BR_X, BS, BUS_TYPE,
-                             F_BUS, GEN_BUS, GEN_STATUS, GS, PD, PG, PQ, PV, QD, QG,
-                             QMAX, QMIN, REF, SHIFT, T_BUS, TAP, VA, VG, VM, Ppc)
+from oracle.ppc_ref import (BASE_KV, BR_B, BR_G, BR_R, BR_STATUS, BR_X, BS, BUS_TYPE,
+                            F_BUS, GEN_BUS, GEN_STATUS, GS, PD, PG, PQ, PV, QD, QG,
+                            QMAX, QMIN, REF, SHIFT, T_BUS, TAP, VA, VG, VM, RefBuilder)
+
+Ppc = object     # any namespace with base_mva / bus / gen / branch / rate_f / rate_t and the lookups
 
 
 # ------------------------------------------------------------------ admittances
@@ -218,7 +220,7 @@ def run_pf(ppc: Ppc, tolerance_mva=1e-8, max_iteration=10, enforce_q_lims=True,
     sf = v[f] * np.conj(yf @ v) * base
     st = v[t] * np.conj(yt @ v) * base
     return dict(V=v, converged=ok, iterations=total_it, Sf=sf, St=st, gen=gen, bus=bus,
-                Ybus=ybus)
+                Ybus=ybus, ppc=ppc)
 
 
 def branch_loading(ppc: Ppc, res):
@@ -238,10 +240,10 @@ def runpp(net, builder=None, enforce_q_lims=True, tolerance_mva=1e-8,
     ``LoadflowNotConverged`` (reference call site ``opfgym/opf_env.py:703``)."""
     import pandas as pd
 
-    from opfgym_b200.net import LoadflowNotConverged
-    from opfgym_b200.ppc import PpcBuilder
+    from opfgym_b200.net import LoadflowNotConverged      # the stand-in for pandapower's exception type
 
-    builder = builder or PpcBuilder(net)
+    # the oracle's OWN net -> ppc conversion (oracle/ppc_ref.py), not the product's
+    builder = builder or RefBuilder()
     ppc = builder.build(net)
     res = run_pf(ppc, tolerance_mva, max_iteration, enforce_q_lims, init)
     if not res["converged"]:

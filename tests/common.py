@@ -111,9 +111,9 @@ def oracle_env(case: Case, eng, b: int):
         k += len(idxs)
     out = {"net": net}
     try:
-        res = pf.runpp(net, case.builder)
-        out.update(converged=True, iterations=res["iterations"], vm=np.abs(res["V"]),
-                   va=np.angle(res["V"]))
+        res = pf.runpp(net)            # the oracle's own net -> ppc conversion (oracle/ppc_ref.py)
+        out.update(converged=True, iterations=res["iterations"],
+                   vm=net.res_bus.vm_pu.to_numpy(float), va=np.radians(net.res_bus.va_degree.to_numpy(float)))
         out.update(scoring.step_reward(net, case.constraints, case.reward))
         obs = [net[t].loc[idxs, c].to_numpy(float) for t, c, idxs in case.obs_keys]
         out["obs"] = np.concatenate(obs)
@@ -134,8 +134,10 @@ def compare_with_oracle(case: Case, eng, envs):
         if not o["converged"]:
             continue
         worst["iter_mismatch"] += int(_np(eng.iterations)[b] != o["iterations"])
-        worst["vm"] = max(worst["vm"], np.abs(_np(eng.vm[b]) - o["vm"]).max())
-        worst["va"] = max(worst["va"], np.abs(_np(eng.va[b]) - o["va"]).max())
+        lk = case.program.ppc.bus_lookup      # pandapower bus order on both sides (the numberings differ)
+        has = lk >= 0
+        worst["vm"] = max(worst["vm"], np.abs(_np(eng.vm[b])[lk[has]] - o["vm"][has]).max())
+        worst["va"] = max(worst["va"], np.abs(_np(eng.va[b])[lk[has]] - o["va"][has]).max())
         r = float(_np(eng.reward)[b])
         worst["reward_rel"] = max(worst["reward_rel"], abs(r - o["reward"]) / max(1e-12, abs(o["reward"])))
         worst["violation"] = max(worst["violation"], np.abs(_np(eng.violations[b]) - o["violations"]).max())

@@ -26,25 +26,36 @@ _G = {}
 
 
 def _oracle_one(b):
+    """Environment b on the ORACLE's own tables (oracle/ppc_ref.py: its own per-unit conversion and bus
+    numbering); only the injections come from the engine, carried over through the pandapower bus order."""
+    import copy
     from oracle import pf
-    ppc, sbus = _G["ppc"], _G["sbus"][b]
-    s = sbus[:, 0] + 1j * sbus[:, 1]
-    bus, gen = ppc.bus.copy(), ppc.gen
+    ref, perm, sbus = _G["ref"], _G["perm"], _G["sbus"][b]
+    if not np.isfinite(sbus).all():
+        return False, -1, None, None
+    s = np.zeros(ref.bus.shape[0], complex)
+    s[perm] = sbus[:, 0] + 1j * sbus[:, 1]
+    bus, gen = ref.bus.copy(), ref.gen
     on = gen[:, P.GEN_STATUS] > 0
     sg = np.zeros(len(bus), complex)
     np.add.at(sg, gen[on, P.GEN_BUS].astype(int), gen[on, P.PG] + 1j * gen[on, P.QG])
-    sd = sg - s * ppc.base_mva                     # makeSbus then returns exactly these injections
+    sd = sg - s * ref.base_mva                     # makeSbus then returns exactly these injections
     bus[:, P.PD], bus[:, P.QD] = sd.real, sd.imag
-    case = P.Ppc(**{**ppc.__dict__, "bus": bus})
-    if not np.isfinite(sbus).all():
-        return False, -1, None, None
+    case = copy.copy(ref)
+    case.bus = bus
     res = pf.run_pf(case, tolerance_mva=1e-8, max_iteration=10, enforce_q_lims=True, init="dc")
-    types_changed = int((res["bus"][:, P.BUS_TYPE] != ppc.bus[:, P.BUS_TYPE]).sum())
-    return bool(res["converged"]), int(res["iterations"]), np.abs(res["V"]), types_changed
+    types_changed = int((res["bus"][:, P.BUS_TYPE] != ref.bus[:, P.BUS_TYPE]).sum())
+    return bool(res["converged"]), int(res["iterations"]), np.abs(res["V"])[perm], types_changed
 
 
-def _oracle_batch(ppc, sbus, envs):
-    _G["ppc"], _G["sbus"] = ppc, sbus
+def _oracle_batch(net, ppc, sbus, envs):
+    from oracle import ppc_ref
+    ref = ppc_ref.build(net)
+    ok = ppc.bus_lookup >= 0
+    perm = np.full(ppc.bus.shape[0], -1)           # engine bus -> oracle bus
+    perm[ppc.bus_lookup[ok]] = ref.bus_lookup[ok]
+    assert (perm >= 0).all(), "stand-in grids of this test have no auxiliary buses"
+    _G["ref"], _G["perm"], _G["sbus"] = ref, perm, sbus
     n = min(len(os.sched_getaffinity(0)), 32)
     if n > 1 and len(envs) > 64:
         with mp.get_context("fork").Pool(n) as pool:
@@ -76,7 +87,7 @@ def _stress(engine_cls, name, n_env, lam, seed, sync=lambda: None, every=1):
     iters = common._np(eng.iterations)
     vm = common._np(eng.vm)
     envs = range(0, n_env, every)
-    ref = _oracle_batch(case.program.ppc, sbus, envs)
+    ref = _oracle_batch(case.net, case.program.ppc, sbus, envs)
     flag_mismatch, iter_mismatch, worst_vm, switched = [], [], 0.0, 0
     for b, (ok, it, vm_ref, types_changed) in zip(envs, ref):
         if ok != conv[b]:

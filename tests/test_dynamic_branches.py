@@ -57,7 +57,7 @@ def oracle(env, ties, b, action):
             sp = np.round(sp)
         net[table].loc[idxs, column] = sp
         k += len(idxs)
-    res = pf.runpp(net, PpcBuilder(net))        # topology changed: fresh builder
+    res = pf.runpp(net)        # topology changed: fresh builder
     out = scoring.step_reward(net, env.constraints, env.reward_function)
     return net, res, out
 
@@ -84,9 +84,11 @@ def _check(engine_kw):
     e.state.copy_(state_before)                 # oracle replays from the pre-action cells
     for b in range(n):
         net, res, out = oracle(env, ties, b, act[b].numpy())
-        lk = PpcBuilder(net).bus_lookup
-        np.testing.assert_allclose(e.vm[b].cpu().numpy(), np.abs(res["V"])[lk], atol=1e-9)
-        np.testing.assert_allclose(e.va[b].cpu().numpy(), np.angle(res["V"])[lk], atol=1e-9)
+        lk = env.program.ppc.bus_lookup          # pandapower bus order on both sides
+        has = lk >= 0
+        np.testing.assert_allclose(e.vm[b].cpu().numpy()[lk[has]], net.res_bus.vm_pu.to_numpy()[has], atol=1e-9)
+        np.testing.assert_allclose(e.va[b].cpu().numpy()[lk[has]],
+                                   np.radians(net.res_bus.va_degree.to_numpy()[has]), atol=1e-9)
     e.actions.copy_(act.to(env.device))
     e.step()
     for b in range(n):

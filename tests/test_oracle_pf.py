@@ -84,9 +84,8 @@ def test_two_bus_closed_form():
 @pytest.mark.parametrize("name", ["1-MV-rural--0-sw", "1-HV-mixed--1-sw"])
 def test_invariants_on_standin_grid(name):
     net, _ = grids.build_simbench_net(name, n_profile_steps=96)
-    builder = P.PpcBuilder(net)
-    res = pf.runpp(net, builder)
-    ppc = builder.build(net)
+    res = pf.runpp(net)
+    ppc = res["ppc"]
     v = res["V"]
     sbus = pf.make_sbus(ppc.base_mva, res["bus"], res["gen"])
     mis = v * np.conj(res["Ybus"] @ v) - sbus

@@ -47,7 +47,7 @@ def reference_loop(env, outages, b, action):
     idxs = env.act_keys[0][2]
     lo, hi = net.sgen.min_p_mw.loc[idxs].to_numpy(), net.sgen.max_p_mw.loc[idxs].to_numpy()
     net.sgen.loc[idxs, "p_mw"] = (np.clip(action, 0, 1) * (hi - lo) + lo) / net.sgen.scaling.loc[idxs].to_numpy()
-    pf.runpp(net, PpcBuilder(net))
+    pf.runpp(net)
     base = scoring.step_reward(net, env.constraints, env.reward_function)
     valids, viol, pens = base["valids"].copy(), base["violations"].copy(), base["unscaled_penalties"].copy()
     for idx in outages:
@@ -55,7 +55,7 @@ def reference_loop(env, outages, b, action):
             continue
         net.line.at[idx, "in_service"] = False
         try:
-            pf.runpp(net, PpcBuilder(net))
+            pf.runpp(net)
             m = [scoring.violation_metrics(c, net) for c in env.constraints]
             valids &= np.array([x["valid"] for x in m])
             viol += np.array([x["violation"] for x in m])
