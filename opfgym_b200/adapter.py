@@ -35,8 +35,12 @@ _RESULTS = (("res_bus", "vm_pu"), ("res_bus", "va_degree"), ("res_line", "loadin
 
 class PowerFlowSolver:
     def __init__(self, net, device=None, engine_cls=Engine, tolerance_mva=1e-8, max_iteration=10,
-                 **engine_kwargs):
-        self.builder = PpcBuilder(net)
+                 builder=None, **engine_kwargs):
+        # a real pandapower net brings its own ppc (net._ppc): read it instead of restating the conversion
+        if builder is None and type(net).__module__.startswith("pandapower"):
+            from .pandapower_adapter import from_pandapower
+            builder = from_pandapower(net)
+        self.builder = builder or PpcBuilder(net)
         comp = Compiler(net, self.builder)
         inputs = [(t, c, net[t].index) for t, c in _INPUTS if len(net[t])]
         results = [(t, c) for t, c in _RESULTS if len(net[t[4:]]) or t == "res_bus"]
