@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--config", default="vc32k", choices=sorted(CONFIGS))
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="override (single-member configs)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--host-obs-dtype", default=None, choices=[None, "float32", "float16"],
+                    help="e2e leg: dtype of the observations on the host (default: float32, the reference's Box dtype)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -224,7 +226,8 @@ def gpu_arm(args):
     for kind, n in members:
         parts.append(getattr(envs, kind)(num_envs=n, train_data="full_uniform", test_data="full_uniform",
                                          n_profile_steps=672, rank=rank, world_size=world, device=dev,
-                                         seed=1234, copy_outputs=False))
+                                         seed=1234, copy_outputs=False,
+                                         host_obs_dtype=None if args.host_obs_dtype in (None, "float32") else args.host_obs_dtype))
     env = parts[0] if len(parts) == 1 else MixedBatchEnv(parts)
     engines = [p.engine for p in parts]
     eng = engines[0]                      # the member whose power-flow kernel the roofline describes
@@ -294,7 +297,8 @@ def gpu_arm(args):
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
     h2d = sum(p.num_envs * p.single_action_space.shape[0] * 4 for p in parts)
-    d2h = sum(p.num_envs * (p.single_observation_space.shape[0] * 4 + 8 + 8 + 1) for p in parts)   # obs f32, reward, cost, flag
+    obs_bytes = 2 if args.host_obs_dtype == "float16" else 4
+    d2h = sum(p.num_envs * (p.single_observation_space.shape[0] * obs_bytes + 8 + 8 + 1) for p in parts)   # obs, reward, cost, flag
 
     # ---- FP64 peak probe (roofline denominator not in MEASURED_PEAKS.json) -----------------
     fp64_tflops = None
@@ -382,7 +386,9 @@ def gpu_arm(args):
                        "n_blocks": info["n_blocks"], "pf_kernel": info["pf_kernel_used"]},
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps,
+                    "host_obs_dtype": args.host_obs_dtype or "float32",
+                    "host_ingest_gbs_per_rank": d2h / (ms_e2e / e2e_steps * 1e-3) / 1e9},
             "gpu_launches": launches,
             "roofline": roofline, "fp64": fp64, "cpu_baseline": cpu_baseline, "single_env": single_env,
             "converged_share": sum(m["converged"] for m in member_stats) / max(sum(m["steps"] for m in member_stats), 1.0),

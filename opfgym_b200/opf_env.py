@@ -74,7 +74,7 @@ class BatchedOpfEnv:
                  device=None, rank: int = 0, world_size: int = 1, obs_dtype: str = "float32",
                  dynamic_columns=(), pwl_price_columns=None, tolerance_mva: float = 1e-8,
                  max_iteration: int = 10, engine_cls=Engine, engine_kwargs: dict | None = None,
-                 copy_outputs: bool = True, validate_actions: bool = False,
+                 copy_outputs: bool = True, validate_actions: bool = False, host_obs_dtype: str | None = None,
                  prefetch_reset: bool = True, keep_all_columns: bool = False,
                  fused_reset: bool | None = None, **kwargs):
         unknown = set(kwargs) - _SPLIT_KWARGS
@@ -93,6 +93,10 @@ class BatchedOpfEnv:
 
         self.net = net
         self.copy_outputs = copy_outputs   # False: returned tensors alias engine buffers
+        # step_host only: dtype of the observation matrix on the HOST (None = the engine's obs dtype, float32
+        # like the reference's Box).  The observation transfer is what bounds step_host on a multi-GPU box
+        # (profiles/r02_d2h_probe_8gpu.txt); "float16" halves it for agents that consume half precision anyway.
+        self.host_obs_dtype = host_obs_dtype
         # The reference asserts `not isnan(action)` (opf_env.py:382).  Checking on the host costs a
         # device sync per step; by default a NaN action simply propagates: that env comes back
         # non-converged with NaN reward/obs (its neighbours in the batch are unaffected).
@@ -593,10 +597,13 @@ class BatchedOpfEnv:
             pin = lambda *shape, dtype: (xp.empty(shape, dtype=dtype).pin_memory() if cuda
                                          else xp.empty(shape, dtype=dtype))
             n_obs = self.single_observation_space.shape[0]
+            host_dt = getattr(xp, self.host_obs_dtype) if self.host_obs_dtype else self.engine.obs.dtype
+            self._obs_cast = None if host_dt == self.engine.obs.dtype else \
+                xp.empty((B, n_obs), dtype=host_dt, device=self.device)
             self._host = dict(
                 actions=pin(B, max(self.program.n_act, 1), dtype=xp.float64),
-                obs=pin(B, n_obs, dtype=self.engine.obs.dtype),
-                obs_alt=pin(B, n_obs, dtype=self.engine.obs.dtype), reward=pin(B, dtype=xp.float64),
+                obs=pin(B, n_obs, dtype=host_dt),
+                obs_alt=pin(B, n_obs, dtype=host_dt), reward=pin(B, dtype=xp.float64),
                 cost=pin(B, dtype=xp.float64), converged=pin(B, dtype=self.engine.converged.dtype),
                 terminated=xp.ones(B, dtype=xp.bool).numpy(), truncated=xp.zeros(B, dtype=xp.bool).numpy())
             self.host_actions = self._host["actions"].numpy()
@@ -626,7 +633,11 @@ class BatchedOpfEnv:
             raise AssertionError("NaN in actions")     # opf_env.py:382
         def obs_to_host(dst):
             keep, self.copy_outputs = self.copy_outputs, False     # no device-side clone on the way out
-            dst.copy_(self._obs_out(), non_blocking=True)
+            obs = self._obs_out()
+            if self._obs_cast is not None:                         # narrower host dtype: cast on the device
+                self._obs_cast.copy_(obs)
+                obs = self._obs_cast
+            dst.copy_(obs, non_blocking=True)
             self.copy_outputs = keep
 
         main = xp.cuda.current_stream(self.device) if self.device.type == "cuda" else None

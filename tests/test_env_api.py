@@ -442,3 +442,18 @@ def test_step_host_is_refused_where_it_would_skip_episode_logic():
         MultiStageBatchedOpfEnv.step_host(object())
     with pytest.raises(NotImplementedError):
         SecurityConstrainedBatchedOpfEnv.step_host(object())
+
+
+def test_step_host_with_half_precision_host_observations():
+    """Opt-in: the observation matrix crosses to the host as float16 (the transfer that bounds
+    step_host on a multi-GPU box); values equal the float32 ones to half precision."""
+    a = make(n=5, obs_dtype="float32")
+    b = make(n=5, obs_dtype="float32", host_obs_dtype="float16")
+    act = np.random.default_rng(0).uniform(0, 1, (5, 14)).astype(np.float32)
+    for e in (a, b):
+        e.reset(seed=4)
+    oa, ra = a.step_host(act)[:2]
+    ob, rb = b.step_host(act)[:2]
+    assert ob.dtype == np.float16 and oa.dtype == np.float32
+    np.testing.assert_allclose(ob.astype(np.float32), oa, rtol=1e-3, atol=1e-3)
+    np.testing.assert_array_equal(ra, rb)
