@@ -64,8 +64,14 @@ class MultiStageBatchedOpfEnv(BatchedOpfEnv):
         cur = self.current_simbench_step
         nxt = cur + 1
         n_prof = len(next(iter(self.profiles.values())))
-        # multi_stage.py:33-41: never step from one data split into another
-        truncated = (self._split_of(nxt) != self._split_of(cur)) | (nxt >= n_prof)
+        # multi_stage.py:33-41: training never steps onto validation / test data, testing never onto
+        # training data (the rule looks at the NEXT step only -- an episode started inside the other
+        # split is truncated at once, as in the reference)
+        nxt_split = self._split_of(nxt)
+        truncated = ((nxt_split == 0) if self.test else (nxt_split > 0)) | (nxt >= n_prof)
+        # the base class already flags the last stage as truncated (opf_env.py:408-410) before
+        # multi_stage.py:43-45 adds terminated: both flags are set, as in the reference
+        truncated = truncated | (self.step_in_episode >= self.steps_per_episode)
         terminated = (self.step_in_episode >= self.steps_per_episode) | ~info["converged"]   # :43-45, opf_env.py:399
         done = terminated | truncated
         # next state: finished envs draw a fresh time step (auto-reset), the others advance by one
