@@ -274,6 +274,9 @@ typedef struct OpfgRowProgram OpfgRowProgram;
 int  opfg_row_program_create(int32_t n_rows, int32_t n_ops, const OpfgRowOp* ops /* host */,
                              int32_t n_static, const double* statics /* host */, OpfgRowProgram** out);
 void opfg_row_program_destroy(OpfgRowProgram* program);
+/* Run the program on a subset of the table's rows only (host array of row numbers): rows whose stores
+ * no kernel table ever reads need not be computed (row-level pruning by the table compiler). */
+int  opfg_row_program_select_rows(OpfgRowProgram* program, int32_t n_selected, const int32_t* rows /* host */);
 int  opfg_row_program_run(const OpfgRowProgram* program, int64_t n_env, double* state, int32_t n_state,
                           void* cuda_stream);
 

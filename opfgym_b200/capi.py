@@ -121,6 +121,7 @@ PROTOTYPES = {
     "opfg_row_program_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(RowOp), C.c_int32,
                                           _dp, C.POINTER(C.c_void_p)]),
     "opfg_row_program_destroy": (None, [C.c_void_p]),
+    "opfg_row_program_select_rows": (C.c_int, [C.c_void_p, C.c_int32, _ip]),
     "opfg_row_program_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "opfg_reset_plan_create": (C.c_int, [C.POINTER(ResetStage), C.c_int32, C.POINTER(C.c_void_p)]),
     "opfg_reset_plan_destroy": (None, [C.c_void_p]),

@@ -83,6 +83,7 @@ class EnvProgram:
     index_pos: dict = field(default_factory=dict)
     dyn_branches: dict | None = None     # OpfgDynBranchDesc arrays, if any branch cell is per-environment
     obs_segments: list | None = None     # observation entries per obs key (after bus-wise grouping)
+    read_cells: frozenset = frozenset()  # state cells that some kernel table reads (or an action overwrites)
 
 
 def _positions(net, table: str, idxs) -> np.ndarray:
@@ -105,6 +106,7 @@ class Compiler:
         self.layout = StateLayout()
         self.consts = ConstTable()
         self.referenced: set[tuple[str, str]] = set()   # columns some compiled table actually reads
+        self.read_cells: set[int] = set()               # ... and the state cells (row-level pruning of hooks)
 
     # ---------------------------------------------------------------- references
     def declare_dynamic(self, table: str, column: str):
@@ -117,7 +119,9 @@ class Compiler:
     def value_ref(self, table: str, column: str, pos: int) -> int:
         self.referenced.add((table, column))
         if self.layout.has(table, column):
-            return self.layout.columns[(table, column)][0] + int(pos)
+            cell = self.layout.columns[(table, column)][0] + int(pos)
+            self.read_cells.add(cell)
+            return cell
         if _is_res(table):
             raise KeyError(f"result column {table}.{column} was not materialised")
         v = self.net[table][column].iloc[int(pos)]
@@ -418,7 +422,7 @@ class Compiler:
                           n_act=n_act, n_obs=len(obs_ptr) - 1, constraints=list(constraints),
                           obs_segments=obs_segments,
                           act_low_refs=np.asarray(a_lo, _I32), act_high_refs=np.asarray(a_hi, _I32),
-                          dyn_branches=dyn)
+                          dyn_branches=dyn, read_cells=frozenset(self.read_cells) | frozenset(int(x) for x in a_slot))
 
     def _result_ref(self, res_table: str, column: str, pos: int) -> tuple[int, float]:
         """Reference (and multiplier) that yields ``net[res_table][column]`` of row ``pos``."""

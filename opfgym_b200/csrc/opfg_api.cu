@@ -163,11 +163,14 @@ struct OpfgGrid {
 
 struct OpfgRowProgram {
     int n_rows = 0, n_ops = 0, n_regs = 1;
+    int n_items = 0;                 // rows the program runs on (all of them, or the selected subset)
+    int32_t* rows = nullptr;         // device, [n_items] table row of every item; null = item i is row i
+    std::vector<int> host_rows;
     OpfgRowOp* ops = nullptr;        // device
     double* statics = nullptr;       // device
     std::vector<OpfgRowOp> host_ops;
     std::vector<double> host_statics;
-    ~OpfgRowProgram() { dev_free(ops); dev_free(statics); }
+    ~OpfgRowProgram() { dev_free(ops); dev_free(statics); dev_free(rows); }
 };
 
 // `r` is the program's register file, register i at r[i * rs]: a shared-memory column per thread in
@@ -204,6 +207,7 @@ struct ResetStage {
     unsigned stream_off;
     const OpfgRowOp* ops;
     int n_ops, n_rows;
+    const int32_t* rows;   // table row of every item (null: identity)
     const double* statics;
     int sync_after;      // 0: the next stage touches other cells and runs beside this one
     int item_off;        // first thread of this stage within its group (spreads the group's items)
@@ -243,7 +247,8 @@ OPFG_HD void env_reset(const GridDev& g, const C& cx, const OpfgBatch& B, int64_
             }
         } else {
             const OpfgRowOp* ops = ops_staged ? ops_staged + s.ops_smem : s.ops;
-            for (int r = first; r < s.n_rows; r += T) row_program_exec(ops, s.n_ops, s.statics, r, S, regs, reg_stride);
+            for (int r = first; r < s.n_rows; r += T)
+                row_program_exec(ops, s.n_ops, s.statics, s.rows ? s.rows[r] : r, S, regs, reg_stride);
         }
         if (s.sync_after) cx.sync();
     }
@@ -280,15 +285,15 @@ static ItemGrid item_grid(int64_t n_env, int n_items) {
     const int item = (int)(blockIdx.x << (w_log2)) + (int)(threadIdx.x & ((1u << (w_log2)) - 1u));  \
     const int64_t env_step_ = (int64_t)gridDim.y * (256 >> (w_log2));                               \
     for (int64_t env = (int64_t)blockIdx.y * (256 >> (w_log2)) + (threadIdx.x >> (w_log2)); env < (n_env_); env += env_step_)
-__global__ void k_row_program(const OpfgRowOp* ops, int n_ops, const double* statics, int n_rows, int64_t n_env,
-                              double* state, int n_state, int w_log2) {
+__global__ void k_row_program(const OpfgRowOp* ops, int n_ops, const double* statics, int n_rows, const int32_t* rows,
+                              int64_t n_env, double* state, int n_state, int w_log2) {
     extern __shared__ __align__(16) double regs[];      // [n_regs][256] register file, one column per thread
     __shared__ OpfgRowOp sops[96];
     for (int i = threadIdx.x; i < n_ops; i += blockDim.x) sops[i] = ops[i];
     __syncthreads();
     OPFG_ITEM_LOOP(row, env, n_env, w_log2)
         if (row < n_rows)
-            row_program_exec(sops, n_ops, statics, row, state + env * (int64_t)n_state, regs + threadIdx.x, 256);
+            row_program_exec(sops, n_ops, statics, rows ? rows[row] : row, state + env * (int64_t)n_state, regs + threadIdx.x, 256);
 }
 // One CTA per environment.  Dynamic shared memory: [n_row doubles: input part of the state row]
 // [n_st stages][all row-program ops][n_regs x T register file]; n_row == 0 keeps the row in global
@@ -1233,6 +1238,22 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
         for (int i = 0, n = sc->obs_ptr ? sc->obs_ptr[sc->n_obs] : sc->n_obs; i < n; ++i)
             G->obs_ref_max = std::max(G->obs_ref_max, sc->obs_ref[i]);
         d.obs_ptr = sc->obs_ptr ? G->tab2(sc->obs_ptr, sc->n_obs + 1) : nullptr;
+        d.n_obs_runs = 0; d.obs_runs = nullptr;
+        if (!sc->obs_ptr && sc->n_obs > 0) {      // runs of consecutive state cells (observation keys are whole columns)
+            std::vector<int> runs;
+            bool ok = true;
+            for (int i = 0; i < sc->n_obs && ok;) {
+                if (sc->obs_ref[i] < 0) { ok = false; break; }
+                int j = i + 1;
+                while (j < sc->n_obs && sc->obs_ref[j] == sc->obs_ref[j - 1] + 1) ++j;
+                runs.insert(runs.end(), {sc->obs_ref[i], i, j - i});
+                i = j;
+            }
+            if (ok && runs.size() / 3 <= 64 && (int)(runs.size() / 3) * 8 <= sc->n_obs && !getenv("OPFG_NO_OBS_RUNS")) {
+                d.obs_runs = G->up(runs);
+                d.n_obs_runs = (int)(runs.size() / 3);
+            }
+        }
         d.tab2_base = G->tab2_base;
         d.tab2_bytes = (int)((G->tab2_used + 15) & ~size_t(15));
         d.n_inputs = sc->n_inputs;
@@ -1600,7 +1621,7 @@ int opfg_row_program_create(int32_t n_rows, int32_t n_ops, const OpfgRowOp* ops,
         if (o.op == OPFG_OP_LOAD_STATIC && (o.a < 0 || o.a + n_rows > n_static)) return fail("row program: static out of range");
     }
     auto* P = new OpfgRowProgram();
-    P->n_rows = n_rows; P->n_ops = n_ops;
+    P->n_rows = n_rows; P->n_ops = n_ops; P->n_items = n_rows;
     for (int i = 0; i < n_ops; ++i)
         if (ops[i].op != OPFG_OP_STORE_STATE) P->n_regs = std::max(P->n_regs, ops[i].dst + 1);
     P->host_ops.assign(ops, ops + n_ops);
@@ -1615,18 +1636,31 @@ int opfg_row_program_create(int32_t n_rows, int32_t n_ops, const OpfgRowOp* ops,
 
 void opfg_row_program_destroy(OpfgRowProgram* p) { delete p; }
 
+int opfg_row_program_select_rows(OpfgRowProgram* P, int32_t n_sel, const int32_t* rows) {
+    if (!P || n_sel < 0 || (n_sel > 0 && !rows)) return fail("bad argument");
+    for (int i = 0; i < n_sel; ++i)
+        if (rows[i] < 0 || rows[i] >= P->n_rows) return fail("row program: selected row %d out of range", rows[i]);
+    dev_free(P->rows);
+    P->rows = (int32_t*)dev_alloc(sizeof(int32_t) * std::max(n_sel, 1));
+    if (!P->rows) return fail("device allocation failed");
+    dev_put(P->rows, rows, sizeof(int32_t) * n_sel);
+    P->host_rows.assign(rows, rows + n_sel);
+    P->n_items = n_sel;
+    return 0;
+}
+
 int opfg_row_program_run(const OpfgRowProgram* P, int64_t n_env, double* state, int32_t n_state, void* stream) {
     if (!P || !state || n_env < 0) return fail("bad argument");
-    if (n_env == 0 || P->n_rows == 0) return 0;
+    if (n_env == 0 || P->n_items == 0) return 0;
 #ifdef OPFG_HOSTSIM
     (void)stream;
     for (int64_t env = 0; env < n_env; ++env)
-        for (int row = 0; row < P->n_rows; ++row)
-            { double r[16]; row_program_exec(P->ops, P->n_ops, P->statics, row, state + env * (int64_t)n_state, r, 1); }
+        for (int item = 0; item < P->n_items; ++item)
+            { double r[16]; row_program_exec(P->ops, P->n_ops, P->statics, P->rows ? P->rows[item] : item, state + env * (int64_t)n_state, r, 1); }
 #else
-    const ItemGrid ig = item_grid(n_env, P->n_rows);
+    const ItemGrid ig = item_grid(n_env, P->n_items);
     k_row_program<<<ig.grid, 256, sizeof(double) * 256 * P->n_regs, (cudaStream_t)stream>>>(
-        P->ops, P->n_ops, P->statics, P->n_rows, n_env, state, n_state, ig.w_log2);
+        P->ops, P->n_ops, P->statics, P->n_items, P->rows, n_env, state, n_state, ig.w_log2);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("row program launch: %s", cudaGetErrorString(e));
@@ -1659,13 +1693,14 @@ int opfg_reset_plan_create(const OpfgResetStage* stages, int32_t n_stages, OpfgR
                 if (!a.program) return fail("reset stage %d: null row program", k);
                 const OpfgRowProgram& rp = *a.program;
                 s.ops = rp.ops; s.statics = rp.statics;   // device copies (host memory in the host build)
-                s.n_ops = rp.n_ops; s.n_rows = rp.n_rows;
+                s.n_ops = rp.n_ops; s.n_rows = rp.n_items; s.rows = rp.rows;
                 s.ops_smem = P->n_ops_total;
                 P->n_ops_total += rp.n_ops;
                 P->n_regs = std::max(P->n_regs, rp.n_regs);
                 for (const OpfgRowOp& o : rp.host_ops)
                     if (o.op == OPFG_OP_LOAD_STATE || o.op == OPFG_OP_STORE_STATE)
-                        for (int r = 0; r < rp.n_rows; ++r) (o.op == OPFG_OP_LOAD_STATE ? rd : wr).push_back(o.a + r);
+                        for (int it = 0; it < rp.n_items; ++it)
+                            (o.op == OPFG_OP_LOAD_STATE ? rd : wr).push_back(o.a + (rp.host_rows.empty() ? it : rp.host_rows[it]));
             } else return fail("reset stage %d: unknown kind %d", k, a.kind);
             for (int c : wr) { if (c < 0) return fail("reset stage %d: negative state cell", k); P->max_cell = std::max(P->max_cell, c); }
             for (int c : rd) { if (c < 0) return fail("reset stage %d: negative state cell", k); P->max_cell = std::max(P->max_cell, c); }

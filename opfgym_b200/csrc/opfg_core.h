@@ -111,6 +111,8 @@ struct GridDev {
     int n_obs;
     const int* obs_ref;
     const int* obs_ptr;      // nullptr: one ref per observation
+    int n_obs_runs;          // > 0: the observation is a few runs of consecutive state cells
+    const int* obs_runs;     // [n_obs_runs][3] first state cell, first observation entry, length
     // ---- lane-per-environment power flow (row-wise schedule, symbolic.hpp LaneSchedule) ----
     int ln_max_row, ln_n_up;
     const int* ln_row;                 // [n+1][4] first Ybus entry, fill position, elimination item, upper block of row k
@@ -289,6 +291,18 @@ OPFG_HD void gather_obs(const GridDev& g, const C& cx, const double* S, const Op
     const int T = cx.nthreads(), n = g.n_obs;
     float* o32 = B.obs_f32 ? B.obs_f32 + env * (int64_t)n : nullptr;
     double* o64 = B.obs_f64 ? B.obs_f64 + env * (int64_t)n : nullptr;
+    if (g.n_obs_runs > 0) {
+        // whole columns of the state row: coalesced copies, no reference loads in front of the data loads
+        for (int r = 0; r < g.n_obs_runs; ++r) {
+            const int src = g.obs_runs[3 * r], dst = g.obs_runs[3 * r + 1], len = g.obs_runs[3 * r + 2];
+            for (int k = cx.tid; k < len; k += T) {
+                const double v = S[src + k];
+                if (o32) o32[dst + k] = (float)v;
+                if (o64) o64[dst + k] = v;
+            }
+        }
+        return;
+    }
     int j = cx.tid;
     for (; j + 3 * T < n; j += 4 * T) {
         const double v0 = obs_value(g, S, j), v1 = obs_value(g, S, j + T), v2 = obs_value(g, S, j + 2 * T),

@@ -275,11 +275,13 @@ class BatchedOpfEnv:
             else:
                 rp = RowProgram(self, table)
                 build(rp)
-                ops, statics = rp.compile()
-                self._row_programs[key] = CompiledRowProgram(self.engine, rp.n_rows, ops, statics) \
-                    if ops else None       # every store was to a pruned (unread) column
-        prog = self._row_programs[key]
-        if prog is not None:
+                # column-level pruning happened in `store`; row-level pruning here: only the cells some
+                # kernel table reads are computed (VoltageControl: 14 of 198 sgen rows carry an action
+                # and hence need their reactive range; the rest only need `q_mvar = 0`)
+                live = self.program.read_cells if self._compile_args["prune_unused"] else None
+                self._row_programs[key] = [CompiledRowProgram(self.engine, rp.n_rows, ops, statics, rows)
+                                           for rows, ops, statics in rp.compile_groups(live)]
+        for prog in self._row_programs[key] or ():
             prog.run()
 
     # ------------------------------------------------------------------------ sampling

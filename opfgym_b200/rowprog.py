@@ -91,6 +91,38 @@ class RowProgram:
         self.stores.append((lay.columns[(self.table, column)][0], Expr.wrap(value)))
 
     # ------------------------------------------------------------------ compile
+    def compile_groups(self, live_cells):
+        """Row-level pruning: a store whose cell no kernel table reads need not happen.  Rows are grouped
+        by the set of their live stores; every group gets its own (shorter) program over its rows.
+        Returns a list of ``(rows, ops, statics)``; ``live_cells=None`` keeps everything (one group)."""
+        if live_cells is None:
+            ops, statics = self.compile()
+            return [(None, ops, statics)] if ops else []
+        # a column that the program itself reads back later counts as live for every row
+        loaded = set()
+
+        def walk(e):
+            if e.op == LOAD_STATE:
+                loaded.add(e.start)
+            for a in e.args:
+                walk(a)
+        for _, e in self.stores:
+            walk(e)
+        groups: dict[tuple, list] = {}
+        for r in range(self.n_rows):
+            sig = tuple(i for i, (start, _) in enumerate(self.stores)
+                        if (start + r) in live_cells or start in loaded)
+            if sig:
+                groups.setdefault(sig, []).append(r)
+        out = []
+        all_stores = self.stores
+        for sig, rows in groups.items():
+            self.stores = [all_stores[i] for i in sig]
+            ops, statics = self.compile()
+            out.append((None if len(rows) == self.n_rows else np.asarray(rows, np.int32), ops, statics))
+        self.stores = all_stores
+        return out
+
     def compile(self):
         uses: dict[int, int] = {}
 
@@ -140,7 +172,7 @@ class RowProgram:
 
 
 class CompiledRowProgram:
-    def __init__(self, engine, n_rows, ops, statics):
+    def __init__(self, engine, n_rows, ops, statics, rows=None):
         self.engine, self.lib = engine, engine.lib
         arr = (capi.RowOp * len(ops))(*[capi.RowOp(*o) for o in ops])
         statics = np.ascontiguousarray(statics, dtype=np.float64)
@@ -149,6 +181,12 @@ class CompiledRowProgram:
             n_rows, len(ops), arr, len(statics), statics.ctypes.data_as(C.POINTER(C.c_double)),
             C.byref(h)))
         self.handle, self.n_ops = h, len(ops)
+        self.n_items = n_rows
+        if rows is not None:
+            rows = np.ascontiguousarray(rows, dtype=np.int32)
+            capi.check(self.lib, self.lib.opfg_row_program_select_rows(
+                h, len(rows), rows.ctypes.data_as(C.POINTER(C.c_int32))))
+            self.n_items = len(rows)
 
     def run(self):
         e = self.engine
