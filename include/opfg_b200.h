@@ -68,6 +68,7 @@ typedef struct OpfgGrid OpfgGrid; /* opaque; owns device copies of all tables */
  * environments live in a constant table C[n_const].  A value reference is an
  * int32:  ref >= 0 -> S[b, ref];  ref < 0 -> C[-ref-1].                        */
 typedef int32_t opfg_ref;
+#define OPFG_NO_VM_REF ((opfg_ref)(-2147483647 - 1))
 
 typedef struct {
     int32_t nb, ng, nbr;
@@ -125,6 +126,11 @@ typedef struct {
     const opfg_ref* inj_p;           /* host [n_inj]                                   */
     const opfg_ref* inj_q;           /* host [n_inj] (ref to a 0 constant if none)     */
     const opfg_ref* inj_coef;        /* host [n_inj] sign*scaling*in_service           */
+    /* per-environment voltage set-points (gen.vm_pu / ext_grid.vm_pu as actions or sampled cells,
+       reference anchor opfgym/envs/eco_dispatch.py:83): host [nb] by ppc bus, OPFG_NO_VM_REF where the
+       bus keeps the static start value; NULL = all static.  opfg_assemble then writes the start |V| of
+       every bus into the batch's `vm` buffer and opfg_pf_solve starts (and holds PV / slack buses) there. */
+    const opfg_ref* bus_vm_ref;
 } OpfgAssemblyDesc;
 
 enum { OPFG_REWARD_SUMMATION = 0, OPFG_REWARD_REPLACEMENT = 1, OPFG_REWARD_PARAMETERIZED = 2,

@@ -47,7 +47,7 @@ class AssemblyDesc(C.Structure):
                 ("act_div", _ip), ("act_kind", _ip), ("act_clamp_lo", _ip),
                 ("act_clamp_hi", _ip), ("act_diff_step", C.c_double),
                 ("n_inj", C.c_int32), ("inj_bus", _ip), ("inj_p", _ip), ("inj_q", _ip),
-                ("inj_coef", _ip)]
+                ("inj_coef", _ip), ("bus_vm_ref", _ip)]
 
 
 class ScoringDesc(C.Structure):

@@ -274,6 +274,19 @@ class Compiler:
             inj_c.append(self.consts.ref(float(net.gen.scaling.iloc[pos])))
         # static ppc bus demand not represented by an element table (none today) is ignored
 
+        # ---- per-environment voltage set-points: gen.vm_pu / ext_grid.vm_pu as state cells ----
+        # (pandapower `_get_pf_variables_from_ppci`: V0[gen bus] = VG for generators on PV / slack buses)
+        bus_vm_ref = None
+        NO_REF = -2**31
+        for table, lookup in (("ext_grid", ppc.ext_grid_gen), ("gen", ppc.gen_gen)):
+            if not lay.has(table, "vm_pu"):
+                continue
+            if bus_vm_ref is None:
+                bus_vm_ref = np.full(ppc.bus.shape[0], NO_REF, dtype=np.int64)
+            for pos, g in enumerate(lookup):
+                if g >= 0 and ppc.bus[int(ppc.gen[g, P.GEN_BUS]), P.BUS_TYPE] != P.PQ:
+                    bus_vm_ref[int(ppc.gen[g, P.GEN_BUS])] = self.value_ref(table, "vm_pu", pos)
+
         assembly = dict(
             n_state=lay.n, act_slot=np.asarray(a_slot, _I32), act_lo=np.asarray(a_lo, _I32),
             act_hi=np.asarray(a_hi, _I32), act_div=np.asarray(a_div, _I32),
@@ -282,7 +295,8 @@ class Compiler:
             act_clamp_hi=np.asarray(a_chi, _I32) if a_chi else None,
             act_diff_step=float(diff_action_step_size or 0.0),
             inj_bus=np.asarray(inj_bus, _I32), inj_p=np.asarray(inj_p, _I32),
-            inj_q=np.asarray(inj_q, _I32), inj_coef=np.asarray(inj_c, _I32))
+            inj_q=np.asarray(inj_q, _I32), inj_coef=np.asarray(inj_c, _I32),
+            bus_vm_ref=None if bus_vm_ref is None else bus_vm_ref.astype(_I32))
 
         # ---- constraints (constraints.py:70-128) ------------------------------
         con_ptr = [0]
@@ -476,7 +490,8 @@ def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_l
                            act_clamp_hi=iptr(a["act_clamp_hi"]), act_diff_step=a["act_diff_step"],
                            n_inj=len(a["inj_bus"]),
                            inj_bus=iptr(a["inj_bus"]), inj_p=iptr(a["inj_p"]),
-                           inj_q=iptr(a["inj_q"]), inj_coef=iptr(a["inj_coef"]))
+                           inj_q=iptr(a["inj_q"]), inj_coef=iptr(a["inj_coef"]),
+                           bus_vm_ref=iptr(a.get("bus_vm_ref")))
     s = program.scoring
     r = s["reward"]
     sd = capi.ScoringDesc(

@@ -78,6 +78,7 @@ struct OpfgGrid {
     std::vector<void*> allocs;
     std::vector<int> gen_bus_host;
     std::vector<double> gen_q_share_host;
+    std::vector<double> vm_bus_host;       // start |V| by ppc bus (set-point at generator buses)
     int n_result_cells = 0;
     double flops_score = 0;
     bool has_assembly = false, has_scoring = false;
@@ -445,7 +446,8 @@ __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                  B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
                  B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
-                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0);
+                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0,
+                 B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
 }
 // One warp per environment, W environments per CTA (lifts the 32-CTAs-per-SM limit on resident envs).
 __global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) {
@@ -455,7 +457,8 @@ __global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) 
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                  B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
                  B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
-                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0);
+                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0,
+                 B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
 }
 __global__ void __launch_bounds__(128) k_score_warps(GridDev g, OpfgBatch B, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
@@ -733,6 +736,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             G->gen_bus_host[gI] = bus;
             if (row[OPFG_GEN_STATUS] > 0 && type[bus] != 1) { vm_bus[bus] = row[OPFG_VG]; vgens[bus]++; }
         }
+        G->vm_bus_host = vm_bus;
         G->gen_q_share_host.resize(ng);
         for (int gI = 0; gI < ng; ++gI) {
             const int bus = G->gen_bus_host[gI];
@@ -1108,6 +1112,14 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
 
 void opfg_grid_destroy(OpfgGrid* grid) { delete grid; }
 
+static void check_ref_vm(const OpfgAssemblyDesc* a, int nb) {
+    for (int b = 0; b < nb; ++b) {
+        const int r = a->bus_vm_ref[b];
+        if (r != OPFG_NO_REF && (r >= a->n_state || -r - 1 >= a->n_const))
+            throw std::runtime_error("reference out of range in bus_vm_ref");
+    }
+}
+
 int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
     if (!G || !a) return fail("null argument");
     try {
@@ -1152,6 +1164,14 @@ int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
         for (int b = 0; b < d.nb; ++b) order[b] = b;
         std::stable_sort(order.begin(), order.end(), [&](int a_, int b_) { return ptr[a_ + 1] - ptr[a_] > ptr[b_ + 1] - ptr[b_]; });
         d.inj_order = G->up(order);
+        d.vm_from_state = 0; d.bus_vm_ref = nullptr; d.vm0_bus = nullptr;
+        if (a->bus_vm_ref) {
+            check_ref_vm(a, d.nb);
+            std::vector<double> vm0_bus(d.nb);
+            for (int b = 0; b < d.nb; ++b) vm0_bus[b] = G->vm_bus_host[b];
+            d.bus_vm_ref = G->up(a->bus_vm_ref, d.nb); d.vm0_bus = G->up(vm0_bus);
+            d.vm_from_state = 1;
+        }
         G->has_assembly = true;
         return 0;
     } catch (const std::exception& ex) {
@@ -1366,6 +1386,7 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (!G->has_assembly) return fail("opfg_set_assembly was not called");
     if (!B->state || (!B->sbus && !B->actions)) return fail("opfg_assemble needs state and at least one of actions / sbus");
     if (G->d.n_dyn > 0 && B->sbus && (!B->yval || !B->bry)) return fail("grid has dynamic branches: batch needs yval and bry");
+    if (G->d.vm_from_state && B->sbus && !B->vm) return fail("grid has per-environment voltage set-points: batch needs vm");
     if (B->n_env <= 0) return 0;
 #ifdef OPFG_HOSTSIM
     (void)stream;
@@ -1374,7 +1395,8 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         env_assemble(G->d, cx, B->actions ? B->actions + env * G->d.n_act : nullptr,
                      B->state + env * (int64_t)G->d.n_state, B->sbus ? B->sbus + env * (int64_t)G->d.nb * 2 : nullptr,
                      B->yval ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr,
-                     B->bry ? B->bry + env * (int64_t)G->d.n_dyn * 8 : nullptr, B->absolute_actions != 0);
+                     B->bry ? B->bry + env * (int64_t)G->d.n_dyn * 8 : nullptr, B->absolute_actions != 0,
+                     B->vm ? B->vm + env * (int64_t)G->d.nb : nullptr);
 #else
     {
         static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;

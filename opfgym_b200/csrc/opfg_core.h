@@ -90,6 +90,11 @@ struct GridDev {
     const int* inj_ptr;                // [nb+1] CSR by ppc bus
     const int* inj_order;              // [nb] buses sorted by descending entry count
     const int *inj_p, *inj_q, *inj_coef;
+    // per-environment voltage set-points (gen.vm_pu / ext_grid.vm_pu as state cells): kernel 1 writes the
+    // start |V| of every bus into the `vm` buffer, the power-flow kernels start from there
+    int vm_from_state;
+    const int* bus_vm_ref;             // [nb] ppc bus -> value reference, or OPFG_NO_REF
+    const double* vm0_bus;             // [nb] default start |V| by ppc bus
     // ---- scoring (kernel 5) ----
     int n_pp_bus, res_vm_slot, res_va_slot;
     const int* pp_lookup;
@@ -243,6 +248,8 @@ OPFG_HD double ref_val(const GridDev& g, const double* S, int r) {
     return *p;
 }
 
+constexpr int OPFG_NO_REF = -2147483647 - 1;
+
 // ------------------------------------------------- kernel 1a: branch -> Ybus values
 // Admittances of one branch from its ppc row (pypower makeYbus.py [ext-mem]).
 OPFG_HD void branch_admittance(const double* p, double* y) {
@@ -320,7 +327,8 @@ OPFG_HD void gather_obs(const GridDev& g, const C& cx, const double* S, const Op
 // --------------------------------------- kernel 1b: actions -> set-points -> Sbus
 template <class C>
 OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, double* S, double* sbus,
-                          double* yval_env = nullptr, double* bry_env = nullptr, bool absolute = false) {
+                          double* yval_env = nullptr, double* bry_env = nullptr, bool absolute = false,
+                          double* vm_out = nullptr) {
     const int T = cx.nthreads();
     for (int j = cx.tid; act != nullptr && j < g.n_act; j += T) {
         double a = act[j];
@@ -366,6 +374,11 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
 #endif
         for (int e = cx.tid; e < g.nnz_y; e += T) ybus_entry(g, g.br_y, e, yval_env + 2 * (size_t)e, bry_env);
     }
+    if (g.vm_from_state && vm_out)       // start |V| / set-point of every bus (pandapower: V0[gen bus] = VG)
+        for (int bus = cx.tid; bus < g.nb; bus += T) {
+            const int r = g.bus_vm_ref[bus];
+            vm_out[bus] = r == OPFG_NO_REF ? g.vm0_bus[bus] : ref_val(g, S, r);
+        }
     const double inv_base = 1.0 / g.base_mva;
     // buses in descending order of their entry count: the lanes of one round carry equal work
     for (int k = cx.tid; k < g.nb; k += T) {
@@ -630,8 +643,8 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
     // |V| and angle are touched only by their owner lane, once per iteration: they live in the
     // output buffers (L2) instead of shared memory, which buys one more resident environment per SM
     for (int i = cx.tid; i < nb; i += T) {
-        const double vm = g.vm0_int[i];
         const int bus = g.bus_of_int[i];
+        const double vm = g.vm_from_state ? vm_out[bus] : g.vm0_int[i];
         const double va = (g.init_dc && i < n) ? (g.dc_pre ? va_out[bus] : s.rhs[i]) : g.va0_int[i];
         double sn, cs;
         sincos(va, &sn, &cs);
@@ -891,8 +904,8 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
     const TreeSmem s = tree_carve(smem, n, nb);
     const double* yv = yval_env ? yval_env : g.tr_y_val;
     for (int i = cx.tid; i < nb; i += T) {
-        const double vm = g.tr_vm0[i];
         const int bus = g.tr_bus_of_int[i];
+        const double vm = g.vm_from_state ? vm_out[bus] : g.tr_vm0[i];
         const double va = (g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i];   // DC start: the dense pre-pass wrote it
         double sn, cs;
         sincos(va, &sn, &cs);
@@ -1136,7 +1149,7 @@ OPFG_HD void lanes_pf_solve(const GridDev& g, const LaneMem<LANES>& s, const dou
     const int n = g.n, nb = g.nb;
     for (int i = 0; i < nb; ++i) {
         const int bus = g.ln_bus_of_int[i];
-        const double vm = g.ln_vm0[i];
+        const double vm = g.vm_from_state ? vm_out[bus] : g.ln_vm0[i];
         const double va = (g.init_dc && i < n) ? va_out[bus] : g.ln_va0[i];   // DC start: written by the dense pre-pass
         double sn, cs;
         sincos(va, &sn, &cs);
