@@ -21,6 +21,7 @@
  *                         opfgym/reward.py:61-98, OpfEnv._get_obs opf_env.py:532-549
  *   opfg_philox_uniform   np_random.uniform in OpfEnv._sample_from_range  opf_env.py:278
  *   opfg_sample_uniform   OpfEnv._sample_uniform / _sample_from_range      opf_env.py:253-284
+ *   opfg_sample_profiles  OpfEnv._set_simbench_state (profile row, noise, clip)    opf_env.py:317-372
  *   opfg_assemble         OpfEnv._apply_actions + makeSbus (kernel 1)
  *   opfg_pf_solve         pp.runpp(net, enforce_q_lims=True)  opf_env.py:696-709
  *                         (kernels 2-4: mismatch SpMV, Jacobian, batched sparse LU)
@@ -257,6 +258,18 @@ int opfg_philox_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id,
 int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env,
                         int32_t n_cols, const int32_t* slots, const double* lo, const double* hi,
                         const double* div, double* state, int32_t n_state, void* cuda_stream);
+
+/* OpfEnv._set_simbench_state (opf_env.py:317-372; the reference's DEFAULT sampler, train_data='simbench'):
+ * S[b, slots[j]] = clip(noise(table[step[b], j] (optionally interpolated towards step + 1 with interp_r[b])),
+ * pmin[j], pmax[j]).  noise_kind 0 none, 1 uniform (value * U(1 - f, 1 + f)), 2 normal (value + |value| f N(0,1)).
+ * table: device [n_steps, n_cols] row-major (one profile table = one element table's column); step: device
+ * int64 [n_env]; random numbers are Philox rows keyed like opfg_philox_uniform (uniform: n_cols wide,
+ * normal: 2 n_cols wide). */
+int  opfg_sample_profiles(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env, int32_t n_cols,
+                          const int32_t* slots, const double* table, int32_t n_steps, const int64_t* step,
+                          const double* interp_r /* device [n_env] or NULL */, const double* pmin,
+                          const double* pmax, double noise_factor, int32_t noise_kind, double* state,
+                          int32_t n_state, void* cuda_stream);
 
 int opfg_assemble(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 int opfg_pf_solve(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);

@@ -200,6 +200,32 @@ OPFG_HHD void row_program_exec(const OpfgRowOp* ops, int n_ops, const double* st
     }
 }
 
+// OpfEnv._set_simbench_state for one cell (opf_env.py:317-372): profile row of the environment's time
+// step, optional interpolation towards the next step, multiplicative uniform or additive normal
+// noise, clipped to the profile's range.  Random numbers: element j of the Philox row of this
+// environment (uniform noise: row of n_cols; normal noise: row of 2 n_cols, Box-Muller of j and n_cols + j).
+OPFG_HD double profile_value(uint64_t seed, uint64_t env, uint64_t stream, int j, int n_cols, const double* table,
+                              int n_steps, int64_t step, const double* r, const double* pmin, const double* pmax,
+                              double noise_factor, int noise_kind) {
+    double v = table[step * (int64_t)n_cols + j];
+    if (r) {
+        const int64_t nxt = step + 1 < n_steps ? step + 1 : n_steps - 1;
+        v = v * r[0] + table[nxt * (int64_t)n_cols + j] * (1.0 - r[0]);
+    }
+    if (noise_kind == 1) {
+        double u[2];
+        philox_two_doubles(seed, env, stream, (uint32_t)(j >> 1), &u[0], &u[1]);
+        v = v * (u[j & 1] * (2.0 * noise_factor) + (1.0 - noise_factor));
+    } else if (noise_kind == 2) {
+        double a[2], c[2];
+        philox_two_doubles(seed, env, stream, (uint32_t)(j >> 1), &a[0], &a[1]);
+        philox_two_doubles(seed, env, stream, (uint32_t)((n_cols + j) >> 1), &c[0], &c[1]);
+        const double z = sqrt(-2.0 * log1p(-a[j & 1])) * cos(2.0 * M_PI * c[(n_cols + j) & 1]);
+        v = v + fabs(v) * noise_factor * z;
+    }
+    return fmin(fmax(v, pmin[j]), pmax[j]);
+}
+
 // one stage of a fused episode reset (device form of OpfgResetStage)
 struct ResetStage {
     int kind, n_cols;
@@ -437,6 +463,17 @@ __global__ void k_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t str
         double* row = state + b * (int64_t)n_state;
         row[s0] = (lo0 + w0 * u0) / d0;
         if (two) row[s1] = (lo1 + w1 * u1) / d1;
+    }
+}
+__global__ void k_sample_profiles(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols,
+                                  const int* slots, const double* table, int n_steps, const int64_t* step,
+                                  const double* interp_r, const double* pmin, const double* pmax, double noise_factor,
+                                  int noise_kind, double* state, int n_state, int w_log2) {
+    OPFG_ITEM_LOOP(j, b, n_env, w_log2) {
+        if (j >= n_cols) break;
+        state[b * (int64_t)n_state + slots[j]] = profile_value(seed, first_env + (uint64_t)b, stream, j, n_cols, table, n_steps,
+                                                               step[b], interp_r ? interp_r + b : nullptr, pmin, pmax,
+                                                               noise_factor, noise_kind);
     }
 }
 template <int T>
@@ -1377,6 +1414,33 @@ int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("sample launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_sample_profiles(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env, int32_t n_cols,
+                         const int32_t* slots, const double* table, int32_t n_steps, const int64_t* step,
+                         const double* interp_r, const double* pmin, const double* pmax, double noise_factor,
+                         int32_t noise_kind, double* state, int32_t n_state, void* cuda_stream) {
+    if (!slots || !table || !step || !pmin || !pmax || !state || n_env < 0 || n_cols < 0 || n_steps <= 0 ||
+        noise_kind < 0 || noise_kind > 2)
+        return fail("bad argument");
+    if (n_env == 0 || n_cols == 0) return 0;
+#ifdef OPFG_HOSTSIM
+    (void)cuda_stream;
+    for (int64_t b = 0; b < n_env; ++b)
+        for (int j = 0; j < n_cols; ++j)
+            state[b * (int64_t)n_state + slots[j]] = profile_value(seed, first_env + (uint64_t)b, stream_id, j, n_cols, table,
+                                                                   n_steps, step[b], interp_r ? interp_r + b : nullptr,
+                                                                   pmin, pmax, noise_factor, noise_kind);
+#else
+    const ItemGrid ig = item_grid(n_env, n_cols);
+    k_sample_profiles<<<ig.grid, 256, 0, (cudaStream_t)cuda_stream>>>(
+        seed, first_env, stream_id, n_env, n_cols, slots, table, n_steps, step, interp_r, pmin, pmax, noise_factor,
+        noise_kind, state, n_state, ig.w_log2);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("profile sampler launch: %s", cudaGetErrorString(e));
 #endif
     return 0;
 }

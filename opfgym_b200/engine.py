@@ -230,6 +230,15 @@ class Engine:
             self._ptr(hi), self._ptr(div), self._ptr(self.state), self.program.layout.n,
             self._stream()))
 
+    def sample_profiles(self, slots, table, step, interp_r, pmin, pmax, noise_factor: float, noise_kind: int,
+                        seed: int, first_env: int, stream_id: int):
+        """ONE launch per profile table: row gather, interpolation, noise, clip (opf_env.py:317-372)."""
+        capi.check(self.lib, self.lib.opfg_sample_profiles(
+            seed, first_env, stream_id, self.num_envs, int(slots.shape[0]), self._ptr(slots), self._ptr(table),
+            int(table.shape[0]), self._ptr(step), self._ptr(interp_r) if interp_r is not None else None,
+            self._ptr(pmin), self._ptr(pmax), float(noise_factor), int(noise_kind), self._ptr(self.state),
+            self.program.layout.n, self._stream()))
+
     def philox_uniform(self, out, seed: int, first_env: int, stream_id: int):
         capi.check(self.lib, self.lib.opfg_philox_uniform(
             seed, first_env, stream_id, out.shape[0], out.shape[1], self._ptr(out), self._stream()))

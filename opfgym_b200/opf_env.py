@@ -382,9 +382,13 @@ class BatchedOpfEnv:
                     continue
                 unit_type, column = key
                 cols = df[self.net[unit_type].index].to_numpy(float)
+                slots = None
+                if self.program.layout.has(unit_type, column):
+                    start = self.program.layout.columns[(unit_type, column)][0]
+                    slots = self.engine._from_numpy(np.arange(start, start + cols.shape[1], dtype=np.int32))
                 self._prof_dev[key] = (self.engine._from_numpy(cols),
                                        self.engine._from_numpy(cols.min(axis=0)),
-                                       self.engine._from_numpy(cols.max(axis=0)))
+                                       self.engine._from_numpy(cols.max(axis=0)), slots)
             n_prof = len(next(iter(self.profiles.values())))
             self._steps_dev = {name: self.engine._from_numpy(
                 np.asarray(v, dtype=np.int64)[np.asarray(v, dtype=np.int64) < n_prof])
@@ -400,28 +404,18 @@ class BatchedOpfEnv:
             step_idx = xp.as_tensor(step, device=self.device).long()
             step_idx = step_idx.expand(B) if step_idx.dim() == 0 else step_idx
         self.current_simbench_step = step_idx
-        for key, (table, pmin, pmax) in self._prof_dev.items():
-            unit_type, column = key
-            if not self.program.layout.has(unit_type, column):
+        step_idx = step_idx.contiguous()
+        r = None
+        if interpolate_steps:                          # :349-353 random point between two profile steps
+            r = xp.empty((B, 1), dtype=xp.float64, device=self.device)
+            self.engine.philox_uniform(r, self.seed, self.first_env, self._next_stream())
+        kind = 0 if not noise_factor else (1 if noise_distribution == "uniform" else 2)
+        for key, (table, pmin, pmax, slots) in self._prof_dev.items():
+            if slots is None:
                 continue
-            values = table[step_idx]
-            if interpolate_steps:                      # :349-353 random point between two profile steps
-                nxt = table[(step_idx + 1).clamp(max=table.shape[0] - 1)]
-                if "r" not in locals():
-                    r = xp.empty((B, 1), dtype=xp.float64, device=self.device)
-                    self.engine.philox_uniform(r, self.seed, self.first_env, self._next_stream())
-                values = values * r + nxt * (1.0 - r)
-            if noise_factor and noise_distribution == "uniform":
-                u = xp.empty(values.shape, dtype=xp.float64, device=self.device)
-                self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
-                values = values * (u * (2.0 * noise_factor) + (1.0 - noise_factor))
-            elif noise_factor:                         # :360-363 N(data, |data| * noise_factor)
-                n = values.shape[1]
-                u = xp.empty((B, 2 * n), dtype=xp.float64, device=self.device)
-                self.engine.philox_uniform(u, self.seed, self.first_env, self._next_stream())
-                z = xp.sqrt(-2.0 * xp.log1p(-u[:, :n])) * xp.cos(2.0 * np.pi * u[:, n:])
-                values = values + values.abs() * noise_factor * z
-            self.col(unit_type, column).copy_(xp.minimum(xp.maximum(values, pmin), pmax))
+            # one launch per profile table: gather + interpolation + noise (:355-363) + clip (:365-370)
+            self.engine.sample_profiles(slots, table, step_idx, r, pmin, pmax, float(noise_factor or 0.0), kind,
+                                        self.seed, self.first_env, self._next_stream() if kind else 0)
 
     def _sampling(self, step=None, test=False, sample_new=True, **kwargs):
         """opf_env.py:222-251 (dispatch on the data distribution)."""

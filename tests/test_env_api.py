@@ -462,3 +462,40 @@ def test_step_host_with_half_precision_host_observations():
     assert ob.dtype == np.float16 and oa.dtype == np.float32
     np.testing.assert_allclose(ob.astype(np.float32), oa, rtol=1e-3, atol=1e-3)
     np.testing.assert_array_equal(ra, rb)
+
+
+@pytest.mark.parametrize("mode", [dict(noise_factor=0.0), dict(noise_factor=0.1), dict(noise_factor=0.2, noise_distribution="normal"),
+                                  dict(noise_factor=0.1, interpolate_steps=True)])
+def test_profile_sampler_kernel_equals_the_tensor_formula(mode):
+    """opfg_sample_profiles (one launch per profile table) against opf_env.py:317-372 written with
+    tensor ops on the same Philox rows."""
+    env = make(n=7, train_data="noisy_simbench", test_data="simbench", sampling_params=mode, n_profile_steps=4 * 672)
+    env.reset(seed=9)
+    env._episode, env._stream_in_episode = 40, 0
+    env._set_simbench_state(**mode)
+    got = {k: env.col(*k).clone() for k in env._prof_dev if env.program.layout.has(*k)}
+    steps = env.current_simbench_step
+    # the same draws, by hand
+    env._stream_in_episode = 1                      # stream 1 chose the time steps
+    B = env.num_envs
+    r = None
+    if mode.get("interpolate_steps"):
+        r = torch.empty(B, 1, dtype=torch.float64)
+        env.engine.philox_uniform(r, env.seed, env.first_env, env._next_stream())
+    for key, (table, pmin, pmax, slots) in env._prof_dev.items():
+        if slots is None:
+            continue
+        v = table[steps]
+        if r is not None:
+            v = v * r + table[(steps + 1).clamp(max=table.shape[0] - 1)] * (1.0 - r)
+        nf, n = mode["noise_factor"], v.shape[1]
+        if nf and mode.get("noise_distribution", "uniform") == "uniform":
+            u = torch.empty(B, n, dtype=torch.float64)
+            env.engine.philox_uniform(u, env.seed, env.first_env, env._next_stream())
+            v = v * (u * 2 * nf + (1 - nf))
+        elif nf:
+            u = torch.empty(B, 2 * n, dtype=torch.float64)
+            env.engine.philox_uniform(u, env.seed, env.first_env, env._next_stream())
+            v = v + v.abs() * nf * torch.sqrt(-2.0 * torch.log1p(-u[:, :n])) * torch.cos(2.0 * np.pi * u[:, n:])
+        want = torch.minimum(torch.maximum(v, pmin), pmax)
+        torch.testing.assert_close(got[key], want, rtol=1e-13, atol=1e-15)
