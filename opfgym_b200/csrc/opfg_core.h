@@ -792,6 +792,7 @@ OPFG_HD TreeSmem tree_carve(double* base, int n, int nb) {
 #ifdef OPFG_DEVICE_BUILD
 template <int T>
 struct Grp {
+    static constexpr int OWN_ROUNDS = 128 / T;
     int tid;                                   // lane within the environment's group of T lanes
     __device__ __forceinline__ int nthreads() const { return T; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -810,6 +811,7 @@ struct Grp {
 #else
 template <int T>
 struct Grp {
+    static constexpr int OWN_ROUNDS = 8;
     int tid = 0;
     int nthreads() const { return 1; }
     void sync() const {}
@@ -903,10 +905,30 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
     const int n = g.n, nb = g.nb;
     const TreeSmem s = tree_carve(smem, n, nb);
     const double* yv = yval_env ? yval_env : g.tr_y_val;
-    for (int i = cx.tid; i < nb; i += T) {
+    // |V| and angle of the buses a lane owns (bus tid + r T) stay in ITS REGISTERS for the whole solve:
+    // the polar update then needs no round trip to the output buffers in L2 (11 % of the kernel's stall
+    // samples before).  Buses beyond OWN rounds (large grids) keep using the output buffers.
+    constexpr int OWN = C::OWN_ROUNDS;       // 128 / T on the device: grids up to 128 buses stay in registers
+    double vm_own[OWN], va_own[OWN];
+#pragma unroll
+    for (int r = 0; r < OWN; ++r) {
+        const int i = cx.tid + r * T;
+        vm_own[r] = va_own[r] = 0.0;
+        if (i < nb) {
+            const int bus = g.tr_bus_of_int[i];
+            const double vm = g.vm_from_state ? vm_out[bus] : g.tr_vm0[i];
+            const double va = (g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i];   // DC start: the dense pre-pass wrote it
+            double sn, cs;
+            sincos(va, &sn, &cs);
+            vm_own[r] = vm; va_own[r] = va;
+            s.ivm[i] = 1.0 / vm;
+            st2(s.vri + 2 * i, vm * cs, vm * sn);
+        }
+    }
+    for (int i = cx.tid + OWN * T; i < nb; i += T) {
         const int bus = g.tr_bus_of_int[i];
         const double vm = g.vm_from_state ? vm_out[bus] : g.tr_vm0[i];
-        const double va = (g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i];   // DC start: the dense pre-pass wrote it
+        const double va = (g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i];
         double sn, cs;
         sincos(va, &sn, &cs);
         if (live) { vm_out[bus] = vm; va_out[bus] = va; }
@@ -980,17 +1002,27 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             }
             cx.sync();
         }
-        if (step) {
-            // polar update (newtonpf.py); |V| and angle live in the output buffers (L2): the next pair is
-            // fetched while the current one goes through sincos
-            double va_n = 0, vm_n = 0;
-            if (cx.tid < n) { const int b0 = g.tr_bus_of_int[cx.tid]; va_n = va_out[b0]; vm_n = vm_out[b0]; }
-            for (int k = cx.tid; k < n; k += T) {
+        if (step) {                                              // polar update (newtonpf.py)
+#pragma unroll
+            for (int r = 0; r < OWN; ++r) {
+                const int k = cx.tid + r * T;
+                if (k < n) {
+                    const D2 dx = ld2(s.t + 2 * k);
+                    double va = va_own[r] + dx.x;
+                    double vm = vm_own[r] + ((g.tr_type[k] == OPFG_PQ) ? dx.y : 0.0);
+                    if (vm < 0) { vm = -vm; va += M_PI; }
+                    if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
+                    double sn, cs;
+                    sincos(va, &sn, &cs);
+                    va_own[r] = va; vm_own[r] = vm; s.ivm[k] = 1.0 / vm;
+                    st2(s.vri + 2 * k, vm * cs, vm * sn);
+                }
+            }
+            for (int k = cx.tid + OWN * T; k < n; k += T) {
                 const D2 dx = ld2(s.t + 2 * k);
                 const int bus = g.tr_bus_of_int[k];
-                double va = va_n + dx.x;
-                double vm = vm_n + ((g.tr_type[k] == OPFG_PQ) ? dx.y : 0.0);
-                if (k + T < n) { const int b1 = g.tr_bus_of_int[k + T]; va_n = va_out[b1]; vm_n = vm_out[b1]; }
+                double va = va_out[bus] + dx.x;
+                double vm = vm_out[bus] + ((g.tr_type[k] == OPFG_PQ) ? dx.y : 0.0);
                 if (vm < 0) { vm = -vm; va += M_PI; }
                 if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
                 double sn, cs;
@@ -1000,6 +1032,13 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             }
         }
         cx.sync();
+    }
+    if (live) {
+#pragma unroll
+        for (int r = 0; r < OWN; ++r) {
+            const int i = cx.tid + r * T;
+            if (i < nb) { const int bus = g.tr_bus_of_int[i]; vm_out[bus] = vm_own[r]; va_out[bus] = va_own[r]; }
+        }
     }
     if (live && cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
 }

@@ -18,4 +18,26 @@ for cls, n in ((envs.VoltageControl, 40), (envs.EcoDispatch, 12), (envs.LoadShed
         out = env.step_host(torch.rand(n, env.single_action_space.shape[0]).numpy())
     assert out[4]["converged"].all()
     env.close()
+# the other power-flow kernels on the radial grid (auto = fused radial kernel above), per-environment
+# Ybus values, per-environment voltage set-points, the profile sampler
+from tests import common
+from opfgym_b200.engine import Engine
+case = common.make_case("1-MV-semiurb--1-sw")
+for kernel in ("cta", "lanes", "radial"):
+    eng = Engine(case.program, 70, obs_dtype="float64", pf_kernel=kernel, ordering=1)
+    common.randomize(case, eng, seed=1)
+    eng.step()
+    torch.cuda.synchronize()
+    assert eng.converged.all()
+    eng.close()
+env = envs.LoadSheddingReconfiguration(num_envs=24, **kw)
+env.reset(seed=3)
+env.step(torch.rand(24, env.single_action_space.shape[0], device="cuda", dtype=torch.float64))
+env.close()
+env = envs.VoltageControl(num_envs=33, train_data="noisy_simbench", test_data="simbench", n_profile_steps=4 * 672,
+                          sampling_params=dict(noise_factor=0.1, interpolate_steps=True))
+env.reset(seed=4)
+env.step(torch.rand(33, 14, device="cuda", dtype=torch.float64))
+torch.cuda.synchronize()
+env.close()
 print("sanitizer run ok")
