@@ -83,11 +83,18 @@ class BatchedOpfEnv:
         if add_time_obs:
             raise NotImplementedError("add_time_obs raises TypeError in the reference itself "
                                       "(opf_env.py:545-546 vs time_observation.py:4)")
-        if objective_function is not None or power_flow_solver is not None:
-            raise NotImplementedError(
-                "Python callables cannot run inside the batched kernels; costs are taken from "
-                "net.poly_cost / net.pwl_cost and the power flow is the CUDA engine. Use "
-                "opfgym_b200.adapter.power_flow_solver to plug the engine into a single-env OpfEnv.")
+        # The reference's plug-in points (opf_env.py:52-53, 70-84) in BATCHED form: the callables get the
+        # env (all environments at once, device tensors) instead of one pandapower net.
+        #   power_flow_solver(env)   -- replaces kernels 2-4: read env.engine.sbus [B, nb, 2] (and .yval),
+        #                               fill env.engine.vm / .va [B, nb], .converged [B] u8, .iterations [B] i32
+        #   objective_function(env)  -- replaces the poly / pwl costs of kernel 5: return the COSTS as a
+        #                               tensor [B] or [B, k] (the objective is minus their sum, opf_env.py:493-500);
+        #                               result columns are read with env.col("res_bus", "vm_pu") etc.
+        for name, fn in (("objective_function", objective_function), ("power_flow_solver", power_flow_solver)):
+            if fn is not None and not callable(fn):
+                raise TypeError(f"{name} must be callable: {name}(env) on batched device tensors")
+        self._custom_solver = power_flow_solver
+        self._custom_objective = objective_function
         if steps_per_episode != 1 and not getattr(self, "_multi_step_ok", False):
             raise NotImplementedError("multi-step episodes: use opfgym_b200.multi_stage.MultiStageBatchedOpfEnv")
 
@@ -524,6 +531,23 @@ class BatchedOpfEnv:
         self.power_flow_available = True
         self._results = aux
 
+    def _apply_custom_objective(self):
+        """``objective_function=`` plug-in: costs from the callable, reward / cost recombined with the
+        constraint results of kernel 5 (reward.py:61-98)."""
+        e, xp = self.engine, self.xp
+        costs = xp.as_tensor(self._custom_objective(self), device=self.device).to(xp.float64)
+        objective = -(costs.reshape(self.num_envs, -1).sum(dim=1))
+        if e.objective_offset is not None:
+            objective = objective - e.objective_offset
+        nc = max(len(self.constraints), 1)
+        ok = e.converged.bool()
+        valid = e.valids[:, :nc].bool().all(dim=1)
+        penalty = e.penalties[:, :nc].sum(dim=1)
+        nan = xp.full_like(objective, float("nan"))
+        e.objective.copy_(xp.where(ok, objective, nan))
+        e.reward.copy_(xp.where(ok, self.reward_function.batched(objective, penalty, valid), nan))
+        e.cost.copy_(xp.where(ok, self.reward_function.batched_cost(penalty, valid), nan))
+
     def _obs_out(self, final: bool = False):
         obs = self.engine.obs_final if final else self.engine.obs
         if self.add_mean_obs:
@@ -559,10 +583,17 @@ class BatchedOpfEnv:
                 self._side_done.record(self._side)
             e.select(cur)
         self.engine.actions.copy_(act.reshape(self.engine.actions.shape))
-        self.engine.step(final_obs=True)
+        if self._custom_solver is None:
+            self.engine.step(final_obs=True)
+        else:                                         # plug-in power flow between kernel 1 and kernel 5
+            e.assemble()
+            self._custom_solver(self)
+            e.score(e.batch_final)
         self.power_flow_available = True
         self._results = e
         keep = (lambda t: t.clone()) if self.copy_outputs else (lambda t: t)
+        if self._custom_objective is not None:
+            self._apply_custom_objective()
         reward = keep(e.reward)
         if self.clipped_action_penalty:
             # opf_env.py:429, 488-491: the correction is measured against the CLIPPED action
@@ -616,6 +647,9 @@ class BatchedOpfEnv:
         device->host transfer (the bulk of the bytes) overlaps kernel 3/4; only the small per-env
         results (reward, cost, converged) are copied after kernel 5."""
         xp, e = self.xp, self.engine
+        if self._custom_solver is not None or self._custom_objective is not None:
+            raise NotImplementedError("step_host pipelines the built-in kernels; with a plug-in power flow or "
+                                      "objective use step()")
         h = self.enable_host_io()
         src = h["actions"]
         if actions is not None:

@@ -168,8 +168,8 @@ def test_unknown_kwargs_and_unsupported_modes_raise():
         make(penalty_weight=0.3)        # reference silently swallows this (A.6 quirk 12)
     with pytest.raises(NotImplementedError):
         make(add_time_obs=True)
-    with pytest.raises(NotImplementedError):
-        make(power_flow_solver=lambda net: None)
+    with pytest.raises(TypeError):
+        make(power_flow_solver="runpp")     # must be a callable on the batched env (see test_batched_plugin_callables)
 
 
 def test_episode_statistics_accumulate():
@@ -499,3 +499,60 @@ def test_profile_sampler_kernel_equals_the_tensor_formula(mode):
             v = v + v.abs() * nf * torch.sqrt(-2.0 * torch.log1p(-u[:, :n])) * torch.cos(2.0 * np.pi * u[:, n:])
         want = torch.minimum(torch.maximum(v, pmin), pmax)
         torch.testing.assert_close(got[key], want, rtol=1e-13, atol=1e-15)
+
+
+def test_batched_plugin_callables():
+    """`power_flow_solver=` / `objective_function=` of the reference (opf_env.py:52-53, 70-84) in batched
+    form: the callables receive the env (device tensors for all environments)."""
+    calls = {"pf": 0, "obj": 0}
+
+    def solver(env):                       # delegate to the built-in kernels, count the calls
+        calls["pf"] += 1
+        env.engine.pf_solve()
+
+    def objective(env):                    # the built-in objective of VoltageControl: loss costs 0.03 eur/MW
+        calls["obj"] += 1
+        ext = env.col("res_ext_grid", "p_mw").sum(dim=1)
+        ctrl_s = env.positions("sgen", env.net.poly_cost.element[env.net.poly_cost.et == "sgen"].to_numpy())
+        ctrl_t = env.positions("storage", env.net.poly_cost.element[env.net.poly_cost.et == "storage"].to_numpy())
+        sg = (env.col("sgen", "p_mw") * env.static("sgen", "scaling"))[:, ctrl_s].sum(dim=1)
+        st = (env.col("storage", "p_mw") * env.static("storage", "scaling"))[:, ctrl_t].sum(dim=1)
+        return 0.03 * (ext + sg - st)
+
+    a = make(n=6)
+    b = make(n=6, power_flow_solver=solver, objective_function=objective)
+    act = torch.rand(6, 14, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    for e in (a, b):
+        e.reset(seed=8)
+    ra, rb = a.step(act), b.step(act)
+    assert calls == {"pf": 1, "obj": 1}
+    torch.testing.assert_close(rb[1], ra[1], rtol=1e-9, atol=1e-12)          # reward
+    torch.testing.assert_close(rb[4]["cost"], ra[4]["cost"], rtol=1e-9, atol=1e-12)
+    torch.testing.assert_close(rb[4]["final_obs"], ra[4]["final_obs"])
+    with pytest.raises(TypeError):
+        make(n=2, objective_function="costs")
+    with pytest.raises(NotImplementedError):
+        b.step_host(act.numpy())
+
+
+@pytest.mark.parametrize("cls", [envs.VoltageControl, envs.EcoDispatch, envs.LoadShedding])
+def test_tensor_objective_module_equals_kernel_objective(cls):
+    """opfgym_b200.objective.get_pandapower_costs (tensor ops, the plug-in building block) against the
+    objective kernel 5 computes -- poly and pwl costs, sampled prices, reference ordering."""
+    from opfgym_b200 import objective as O
+    env = make(cls, n=5)
+    env.reset(seed=6)
+    n_act = env.single_action_space.shape[0]
+    e = env.engine
+    e.actions.copy_(torch.rand(5, n_act, dtype=torch.float64, generator=torch.Generator().manual_seed(1)))
+    e.step()
+    costs = O.get_pandapower_costs(env)
+    assert costs.shape == (5, 2 * len(env.net.poly_cost) + len(env.net.pwl_cost))
+    assert len(O.cost_vector_layout(env.net)) == costs.shape[1]
+    torch.testing.assert_close(-costs.sum(dim=1), e.objective, rtol=1e-12, atol=1e-12)
+    plug = make(cls, n=5, objective_function=O.get_pandapower_costs)
+    plug.reset(seed=6)
+    act = torch.rand(5, n_act, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    base = make(cls, n=5)
+    base.reset(seed=6)
+    torch.testing.assert_close(plug.step(act)[1], base.step(act)[1], rtol=1e-10, atol=1e-12)
