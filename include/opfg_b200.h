@@ -275,6 +275,18 @@ int opfg_assemble(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_strea
 int opfg_pf_solve(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 int opfg_score(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 /* observation gather only (OpfEnv._get_obs after reset, opf_env.py:218): obs[b, j] = value(obs_ref[j]) */
+/* ---- mixed batch (BASELINE.json configs[3]: "MaxRenewable + QMarket mixed batch, fused constraint /
+ * objective / reward kernel"): environments of SEVERAL grids scored by ONE launch of kernel 5 (and assembled by
+ * one launch of kernel 1).  Every CTA picks its member's descriptor and batch from a device table by its
+ * block index.  The power flows in between stay per member (opfg_pf_solve; different kernels per grid size).
+ * Reference hooks the single launch carries: envs/max_renewable.py:93-105, envs/voltage_control.py:105-133. */
+typedef struct OpfgMixed OpfgMixed;
+int  opfg_mixed_create(int32_t n_members, const OpfgGrid* const* grids, const OpfgBatch* batches /* host [n] */,
+                       OpfgMixed** out);
+void opfg_mixed_destroy(OpfgMixed* mixed);
+int  opfg_assemble_mixed(OpfgMixed* mixed, const OpfgBatch* batches /* host [n], re-read every call */, void* cuda_stream);
+int  opfg_score_mixed(OpfgMixed* mixed, const OpfgBatch* batches /* host [n] */, void* cuda_stream);
+
 int opfg_observe(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);
 /* assemble -> pf_solve -> score, back to back on the stream */
 int opfg_step(const OpfgGrid* grid, const OpfgBatch* batch, void* cuda_stream);

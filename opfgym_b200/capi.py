@@ -120,6 +120,10 @@ PROTOTYPES = {
     "opfg_pf_solve": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_score": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_observe": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "opfg_mixed_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(Batch), C.POINTER(C.c_void_p)]),
+    "opfg_mixed_destroy": (None, [C.c_void_p]),
+    "opfg_assemble_mixed": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "opfg_score_mixed": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_step": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "opfg_row_program_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(RowOp), C.c_int32,
                                           _dp, C.POINTER(C.c_void_p)]),

@@ -293,6 +293,16 @@ OPFG_HD void env_reset(const GridDev& g, const C& cx, const OpfgBatch& B, int64_
     gather_obs(g, cx, S, B, env);
 }
 
+// one member of a mixed batch (several grids scored by one launch, see k_score_mixed)
+struct MixedMember {
+    GridDev g;
+    OpfgBatch B;
+    int cta_begin, cta_end;     // CTAs of this member
+    int score_threads;          // 32: one warp per environment (4 per CTA); 128: the whole CTA
+    int score_env_doubles;
+};
+constexpr int OPFG_MAX_MEMBERS = 8;
+
 // ------------------------------------------------------------------- kernels
 #ifndef OPFG_HOSTSIM
 // Elementwise kernels.  A 256-thread block is split into 256/W environment lanes of W item lanes
@@ -506,6 +516,47 @@ __global__ void __launch_bounds__(128) k_score_warps(GridDev g, OpfgBatch B, int
     env_score(g, cx, mine, B, env, (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
               B.state + env * (int64_t)g.n_state);
 }
+// Mixed batch (BASELINE config 4): ONE launch of kernel 1 / kernel 5 over several grids.  Every CTA looks
+// up its member (grid descriptor + batch, in device memory) from its block index; environments of
+// different grids therefore run side by side in one grid of CTAs, each with its own tables.
+__global__ void __launch_bounds__(128) k_assemble_mixed(const MixedMember* members, int n_members) {
+    int m = 0;
+    while (m + 1 < n_members && (int)blockIdx.x >= members[m].cta_end) ++m;
+    const MixedMember& mm = members[m];
+    const GridDev& g = mm.g;
+    const OpfgBatch& B = mm.B;
+    const int64_t env = (int64_t)(blockIdx.x - mm.cta_begin) * 4 + (threadIdx.x >> 5);
+    if (env >= B.n_env) return;
+    Ctx<32> cx{(int)(threadIdx.x & 31), nullptr, 0};
+    env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
+                 B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
+                 B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+                 B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0,
+                 B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
+}
+__global__ void __launch_bounds__(128) k_score_mixed(const MixedMember* members, int n_members) {
+    extern __shared__ __align__(16) double sm[];
+    int m = 0;
+    while (m + 1 < n_members && (int)blockIdx.x >= members[m].cta_end) ++m;
+    const MixedMember& mm = members[m];
+    const GridDev& g = mm.g;
+    const OpfgBatch& B = mm.B;
+    if (mm.score_threads == 32) {
+        const int64_t env = (int64_t)(blockIdx.x - mm.cta_begin) * 4 + (threadIdx.x >> 5);
+        if (env >= B.n_env) return;
+        double* mine = sm + (size_t)(threadIdx.x >> 5) * mm.score_env_doubles;
+        Ctx<32> cx{(int)(threadIdx.x & 31), mine + score_smem_doubles(g.nb, g.nbr, 32) - 4, 0};
+        env_score(g, cx, mine, B, env, (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+                  B.state + env * (int64_t)g.n_state);
+    } else {
+        const int64_t env = blockIdx.x - mm.cta_begin;
+        if (env >= B.n_env) return;
+        Ctx<128> cx{(int)threadIdx.x, sm + score_smem_doubles(g.nb, g.nbr, 128) - 2 * (128 / 32 + 1), 0};
+        env_score(g, cx, sm, B, env, (g.n_dyn > 0 && B.yval) ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
+                  B.state + env * (int64_t)g.n_state);
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
     extern __shared__ __align__(16) double sm[];
@@ -1659,6 +1710,88 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
 #endif
     return 0;
 }
+
+// ---- mixed batch: kernel 1 / kernel 5 of several grids in one launch each ----
+struct OpfgMixed {
+    int n = 0;
+    std::vector<const OpfgGrid*> grids;
+    std::vector<MixedMember> host;
+    void* dev = nullptr;
+    int ctas_assemble = 0, ctas_score = 0;
+    size_t smem_score = 0;
+    ~OpfgMixed() { dev_free(dev); }
+};
+
+int opfg_mixed_create(int32_t n_members, const OpfgGrid* const* grids, const OpfgBatch* batches, OpfgMixed** out) {
+    if (!out || !grids || !batches || n_members <= 0 || n_members > OPFG_MAX_MEMBERS) return fail("bad argument (1..8 members)");
+    *out = nullptr;
+    auto M = std::make_unique<OpfgMixed>();
+    M->n = n_members;
+    for (int m = 0; m < n_members; ++m) {
+        const OpfgGrid* G = grids[m];
+        if (!G || !G->has_assembly || !G->has_scoring) return fail("member %d: opfg_set_assembly / opfg_set_scoring missing", m);
+        const OpfgBatch& B = batches[m];
+        if (!B.state || !B.sbus || !B.vm || !B.va || !B.converged) return fail("member %d: batch needs state, sbus, vm, va, converged", m);
+        if (G->d.n_dyn > 0 && (!B.yval || !B.bry)) return fail("member %d: grid has dynamic branches: batch needs yval and bry", m);
+        M->grids.push_back(G);
+        MixedMember mm{};
+        mm.g = G->d; mm.B = B;
+        mm.score_threads = G->score_threads == 32 ? 32 : 128;
+        if (G->score_threads != 32 && G->score_threads != 128) return fail("member %d: scoring with %d threads per environment cannot join a mixed launch", m, G->score_threads);
+        const size_t per_env = (score_smem_doubles(G->d.nb, G->d.nbr, mm.score_threads) * sizeof(double) + 15) & ~size_t(15);
+        mm.score_env_doubles = (int)(per_env / 8);
+        M->smem_score = std::max(M->smem_score, mm.score_threads == 32 ? 4 * per_env : per_env);
+        M->host.push_back(mm);
+    }
+    M->dev = dev_alloc(sizeof(MixedMember) * n_members);
+    if (!M->dev) return fail("device allocation failed");
+    *out = M.release();
+    return 0;
+}
+
+void opfg_mixed_destroy(OpfgMixed* mixed) { delete mixed; }
+
+// which = 0: kernel 1 (opfg_assemble of every member), 1: kernel 5 (opfg_score of every member); the
+// batches are re-read at every call (state double-buffering moves the pointers)
+static int mixed_launch(OpfgMixed* M, const OpfgBatch* batches, int which, void* stream) {
+    if (!M || !batches) return fail("null argument");
+    int cta = 0;
+    for (int m = 0; m < M->n; ++m) {
+        MixedMember& mm = M->host[m];
+        mm.B = batches[m];
+        const int per_cta = (which == 0 || mm.score_threads == 32) ? 4 : 1;
+        mm.cta_begin = cta;
+        cta += (int)((mm.B.n_env + per_cta - 1) / per_cta);
+        mm.cta_end = cta;
+    }
+    if (cta == 0) return 0;
+#ifdef OPFG_HOSTSIM
+    (void)stream;
+    for (int m = 0; m < M->n; ++m) {
+        const int rc = which == 0 ? opfg_assemble(M->grids[m], &M->host[m].B, nullptr) : opfg_score(M->grids[m], &M->host[m].B, nullptr);
+        if (rc) return rc;
+    }
+#else
+    // the member table travels on the same stream as the launch (a few KB)
+    cudaMemcpyAsync(M->dev, M->host.data(), sizeof(MixedMember) * M->n, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (which == 0) {
+        k_assemble_mixed<<<cta, 128, 0, (cudaStream_t)stream>>>((const MixedMember*)M->dev, M->n);
+    } else {
+        static size_t attr = 48 * 1024;      // raised per process; the kernel is the same on every device of the process
+        if (M->smem_score > attr) {
+            cudaFuncSetAttribute(k_score_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M->smem_score);
+        }
+        k_score_mixed<<<cta, 128, M->smem_score, (cudaStream_t)stream>>>((const MixedMember*)M->dev, M->n);
+    }
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail("mixed launch: %s", cudaGetErrorString(e));
+#endif
+    return 0;
+}
+
+int opfg_assemble_mixed(OpfgMixed* mixed, const OpfgBatch* batches, void* stream) { return mixed_launch(mixed, batches, 0, stream); }
+int opfg_score_mixed(OpfgMixed* mixed, const OpfgBatch* batches, void* stream) { return mixed_launch(mixed, batches, 1, stream); }
 
 int opfg_observe(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (!G || !B) return fail("null argument");

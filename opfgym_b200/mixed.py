@@ -1,14 +1,26 @@
 """Several batched envs of different grids stepped as one batch (BASELINE config 4:
-"MaxRenewable + QMarket mixed batch").  Each member keeps its own compiled grid; the
-members' launches go to separate CUDA streams so that their kernels overlap on the
-device, and the outputs are concatenated along the env axis (observations are padded to
-the widest member).  Episode statistics add up across members."""
+"MaxRenewable + QMarket mixed batch, fused constraint/objective/reward kernel").  Each member keeps
+its own compiled grid and buffers.  ``step`` runs kernel 1 of ALL members as one launch, the members'
+power flows (different kernels per grid size) on separate streams, and kernel 5 -- constraints,
+objective, reward, observation -- of ALL members as one launch (``opfg_assemble_mixed`` /
+``opfg_score_mixed``: every CTA picks its member's descriptor from a device table).  Outputs are
+concatenated along the env axis (observations padded to the widest member); episode statistics add up.
+``fused_launches=False`` steps the members independently on their streams instead."""
 from __future__ import annotations
+
+import ctypes as C
+
+from . import capi
+from .opf_env import BatchedOpfEnv
 
 
 class MixedBatchEnv:
-    def __init__(self, envs):
+    def __init__(self, envs, fused_launches: bool = True):
         self.envs = list(envs)
+        self.fused_launches = bool(fused_launches) and all(
+            e._custom_solver is None and e._custom_objective is None and type(e).step is BatchedOpfEnv.step
+            for e in self.envs)       # subclasses with their own step (multi-stage, N-1) are stepped member by member
+        self._mixed = None
         self.num_envs = sum(e.num_envs for e in self.envs)
         self.xp = self.envs[0].xp
         self.device = self.envs[0].device
@@ -50,12 +62,39 @@ class MixedBatchEnv:
         outs = self._each(lambda i, e: e.reset(seed=seed, options=options))
         return self._pad([o[0] for o in outs]), {}
 
+    def _mixed_handle(self):
+        if self._mixed is None:
+            lib = self.envs[0].engine.lib
+            n = len(self.envs)
+            grids = (C.c_void_p * n)(*[e.engine.handle for e in self.envs])
+            batches = (capi.Batch * n)(*[e.engine.batch_final for e in self.envs])
+            h = C.c_void_p()
+            capi.check(lib, lib.opfg_mixed_create(n, grids, batches, C.byref(h)))
+            self._mixed = (lib, h)
+        return self._mixed
+
+    def _step_fused(self, parts):
+        """kernel 1 of all members: one launch; power flows per member (own streams); kernel 5 of all
+        members: one launch."""
+        lib, h = self._mixed_handle()
+        n = len(self.envs)
+        acts = [e._step_begin(parts[i][:, :e.single_action_space.shape[0]]) for i, e in enumerate(self.envs)]
+        batches = (capi.Batch * n)(*[e.engine.batch_final for e in self.envs])
+        stream = self.envs[0].engine._stream()
+        capi.check(lib, lib.opfg_assemble_mixed(h, batches, stream))
+        self._each(lambda i, e: e.engine.pf_solve(e.engine.batch_final))
+        capi.check(lib, lib.opfg_score_mixed(h, batches, stream))
+        return [e._step_end(a) for e, a in zip(self.envs, acts)]
+
     def step(self, actions):
         """``actions[num_envs, n_act]``: member i reads its rows and its first n_act_i columns."""
         xp = self.xp
         act = xp.as_tensor(actions, device=self.device)
         parts = act.split(self.splits, dim=0)
-        outs = self._each(lambda i, e: e.step(parts[i][:, :e.single_action_space.shape[0]]))
+        if self.fused_launches:
+            outs = self._step_fused(parts)
+        else:
+            outs = self._each(lambda i, e: e.step(parts[i][:, :e.single_action_space.shape[0]]))
         obs = self._pad([o[0] for o in outs])
         reward, term, trunc = (xp.cat([o[k] for o in outs]) for k in (1, 2, 3))
         info = {"member": outs, "converged": xp.cat([o[4]["converged"] for o in outs]),
@@ -93,5 +132,8 @@ class MixedBatchEnv:
                 "members": stats}
 
     def close(self):
+        if self._mixed is not None:
+            self._mixed[0].opfg_mixed_destroy(self._mixed[1])
+            self._mixed = None
         for e in self.envs:
             e.close()

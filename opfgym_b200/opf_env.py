@@ -564,6 +564,19 @@ class BatchedOpfEnv:
         batched power flow, score, auto-reset.  Returns torch tensors on the device:
         ``(obs, reward, terminated, truncated, info)``; ``info['final_obs']`` holds the
         observation of the finished episode."""
+        act = self._step_begin(actions)
+        e = self.engine
+        if self._custom_solver is None:
+            e.step(final_obs=True)
+        else:                                         # plug-in power flow between kernel 1 and kernel 5
+            e.assemble()
+            self._custom_solver(self)
+            e.score(e.batch_final)
+        return self._step_end(act)
+
+    # step() in three parts, so that a mixed batch (opfgym_b200.mixed) can run the kernels of several
+    # envs as shared launches between the parts
+    def _step_begin(self, actions):
         xp = self.xp
         act = xp.as_tensor(actions, device=self.device)
         if self.validate_actions and xp.isnan(act).any():   # host sync; off by default
@@ -582,13 +595,12 @@ class BatchedOpfEnv:
                 self._begin_episode()
                 self._side_done.record(self._side)
             e.select(cur)
+            self._next_buffer = nxt
         self.engine.actions.copy_(act.reshape(self.engine.actions.shape))
-        if self._custom_solver is None:
-            self.engine.step(final_obs=True)
-        else:                                         # plug-in power flow between kernel 1 and kernel 5
-            e.assemble()
-            self._custom_solver(self)
-            e.score(e.batch_final)
+        return act
+
+    def _step_end(self, act):
+        xp, e = self.xp, self.engine
         self.power_flow_available = True
         self._results = e
         keep = (lambda t: t.clone()) if self.copy_outputs else (lambda t: t)
@@ -609,7 +621,7 @@ class BatchedOpfEnv:
         terminated, truncated = (keep(self._flags[0]), keep(self._flags[1]))
         if self._prefetch:
             xp.cuda.current_stream(self.device).wait_event(self._side_done)
-            e.select(nxt)                             # the prefetched episode becomes the current one
+            e.select(self._next_buffer)               # the prefetched episode becomes the current one
         else:
             self._begin_episode()
         return self._obs_out(), reward, terminated, truncated, info

@@ -31,23 +31,41 @@ def test_multi_stage_cuda_equals_host_build(cuda_lib):
         np.testing.assert_allclose(rg[0].cpu().numpy(), rc[0].numpy(), rtol=1e-9, atol=1e-12)
 
 
-def test_mixed_batch_on_cuda_equals_members_alone(cuda_lib):
+@pytest.mark.parametrize("fused", [True, False])
+def test_mixed_batch_on_cuda_equals_members_alone(cuda_lib, fused):
+    """BASELINE config 4: kernel 1 and kernel 5 of BOTH grids as one launch each (fused=True) -- every
+    output bit equals the members stepped alone, and the launch counter shows the shared launches."""
     import torch
     from opfgym_b200 import envs
     from opfgym_b200.mixed import MixedBatchEnv
     kw = dict(n_profile_steps=672, obs_dtype="float64", train_data="full_uniform", test_data="full_uniform", seed=3)
 
     def members():
-        return [envs.MaxRenewable(num_envs=24, **kw), envs.QMarket(num_envs=40, **kw)]
-    mixed, alone = MixedBatchEnv(members()), members()
+        return [envs.MaxRenewable(num_envs=27, **kw), envs.QMarket(num_envs=41, **kw)]
+    mixed, alone = MixedBatchEnv(members(), fused_launches=fused), members()
+    assert mixed.fused_launches == fused
     obs, _ = mixed.reset(seed=9)
     ref = [e.reset(seed=9)[0] for e in alone]
-    assert torch.equal(obs[:24, :172], ref[0]) and torch.equal(obs[24:], ref[1])
-    act = torch.rand(64, 18, dtype=torch.float64, device="cuda")
-    obs, reward, term, trunc, info = mixed.step(act)
-    r0, r1 = alone[0].step(act[:24, :18]), alone[1].step(act[24:, :10])
-    assert torch.equal(reward, torch.cat([r0[1], r1[1]])) and term.all() and info["converged"].all()
-    assert mixed.episode_statistics()["steps"] == 64
+    assert torch.equal(obs[:27, :172], ref[0]) and torch.equal(obs[27:], ref[1])
+    act = torch.rand(68, 18, dtype=torch.float64, device="cuda")
+    eng = mixed.envs[0].engine
+    for k in range(3):
+        torch.cuda.synchronize()
+        before = eng.launch_count()
+        obs, reward, term, trunc, info = mixed.step(act)
+        torch.cuda.synchronize()
+        launches = eng.launch_count() - before
+        r0, r1 = alone[0].step(act[:27, :18]), alone[1].step(act[27:, :10])
+        assert torch.equal(reward, torch.cat([r0[1], r1[1]])) and term.all() and info["converged"].all()
+        assert torch.equal(obs[:27, :172], r0[0]) and torch.equal(obs[27:], r1[0])
+        assert torch.equal(info["cost"], torch.cat([r0[4]["cost"], r1[4]["cost"]]))
+    assert mixed.episode_statistics()["steps"] == 68 * 3
+    if fused:      # 1 assemble + 1 score for both grids (instead of 2 + 2); power flows and resets stay per member
+        torch.cuda.synchronize()
+        before = eng.launch_count()
+        alone[0].step(act[:27, :18]); alone[1].step(act[27:, :10])
+        torch.cuda.synchronize()
+        assert launches == (eng.launch_count() - before) - 2
 
 
 def test_wrapper_and_samplers_on_cuda(cuda_lib):

@@ -31,10 +31,15 @@ def test_stochastic_observation_noise_and_clipping():
     assert env.num_envs == 16 and env.single_action_space.shape == (10,)      # attribute pass-through
 
 
-def test_mixed_batch_equals_members_stepped_alone():
+import pytest
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_mixed_batch_equals_members_stepped_alone(fused):
     def members():
         return [envs.MaxRenewable(num_envs=6, **KW), envs.QMarket(num_envs=10, **KW)]
-    mixed = MixedBatchEnv(members())
+    mixed = MixedBatchEnv(members(), fused_launches=fused)
+    assert mixed.fused_launches == fused
     alone = members()
     assert mixed.num_envs == 16 and mixed.n_obs == 305 and mixed.n_act == 18
     obs, _ = mixed.reset(seed=9)
@@ -46,4 +51,8 @@ def test_mixed_batch_equals_members_stepped_alone():
     r0 = alone[0].step(act[:6, :18])
     r1 = alone[1].step(act[6:, :10])
     assert torch.equal(reward, torch.cat([r0[1], r1[1]])) and term.all() and info["converged"].all()
+    assert torch.equal(obs[:6, :172], r0[0]) and torch.equal(obs[6:], r1[0])
+    assert torch.equal(info["cost"], torch.cat([r0[4]["cost"], r1[4]["cost"]]))
     assert mixed.episode_statistics()["steps"] == 16
+    obs2, reward2 = mixed.step(act)[:2]                 # second step: buffers were switched
+    assert torch.equal(reward2, torch.cat([alone[0].step(act[:6, :18])[1], alone[1].step(act[6:, :10])[1]]))
