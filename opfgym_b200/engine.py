@@ -259,7 +259,16 @@ class Engine:
         capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(batch), self._stream()))
 
     def pf_solve(self, batch=None):
+        """Kernels 2-4.  With ``self.pf_events`` set to a list, CUDA events bracketing the launch(es) on the
+        launching stream are appended to it (bench.py's roofline)."""
+        if self.pf_events is not None:
+            e0 = self.torch.cuda.Event(enable_timing=True)
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e0.record()
         capi.check(self.lib, self.lib.opfg_pf_solve(self.handle, C.byref(batch or self.batch), self._stream()))
+        if self.pf_events is not None:
+            e1.record()
+            self.pf_events.append((e0, e1))
 
     def score(self, batch=None):
         capi.check(self.lib, self.lib.opfg_score(self.handle, C.byref(batch or self.batch), self._stream()))
@@ -277,13 +286,8 @@ class Engine:
             capi.check(self.lib, self.lib.opfg_step(self.handle, C.byref(batch), self._stream()))
             return
         self.assemble()
-        e0 = self.torch.cuda.Event(enable_timing=True)
-        e1 = self.torch.cuda.Event(enable_timing=True)
-        e0.record()
         self.pf_solve()
-        e1.record()
         capi.check(self.lib, self.lib.opfg_score(self.handle, C.byref(batch), self._stream()))
-        self.pf_events.append((e0, e1))
 
     pf_events = None
 
