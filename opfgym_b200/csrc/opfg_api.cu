@@ -1347,6 +1347,7 @@ int opfg_set_scoring(OpfgGrid* G, const OpfgScoringDesc* sc) {
             G->obs_ref_max = std::max(G->obs_ref_max, sc->obs_ref[i]);
         d.obs_ptr = sc->obs_ptr ? G->tab2(sc->obs_ptr, sc->n_obs + 1) : nullptr;
         d.n_obs_runs = 0; d.obs_runs = nullptr;
+        d.score_prefetch = getenv("OPFG_SCORE_PREFETCH") ? atoi(getenv("OPFG_SCORE_PREFETCH")) : 2;
         if (!sc->obs_ptr && sc->n_obs > 0) {      // runs of consecutive state cells (observation keys are whole columns)
             std::vector<int> runs;
             bool ok = true;

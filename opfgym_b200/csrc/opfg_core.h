@@ -116,6 +116,7 @@ struct GridDev {
     int n_obs;
     const int* obs_ref;
     const int* obs_ptr;      // nullptr: one ref per observation
+    int score_prefetch;      // kernel 5: 0 no prefetch of the state row, 1 whole row, 2 observation runs only
     int n_obs_runs;          // > 0: the observation is a few runs of consecutive state cells
     const int* obs_runs;     // [n_obs_runs][3] first state cell, first observation entry, length
     // ---- lane-per-environment power flow (row-wise schedule, symbolic.hpp LaneSchedule) ----
@@ -1357,9 +1358,20 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     }
 
 #ifdef OPFG_DEVICE_BUILD
-    // the row is read piecemeal through references below: pull it towards the SM now
-    for (int off = cx.tid * 128; off < g.n_state * 8; off += T * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S) + off));
+    // the row is read piecemeal through references below: pull what will be read towards the SM now --
+    // the observation runs if the observation is made of runs (the whole 10 KB row used to be fetched:
+    // 348 MB per launch of 32 768 environments, two thirds of it never read), else the whole row
+    if (g.score_prefetch == 2 && g.n_obs_runs > 0) {
+        for (int r = 0; r < g.n_obs_runs; ++r) {
+            const char* p0 = reinterpret_cast<const char*>(S + g.obs_runs[3 * r]);
+            const int bytes = g.obs_runs[3 * r + 2] * 8;
+            for (int off = cx.tid * 128; off < bytes + 127; off += T * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (off < bytes ? off : bytes - 1)));
+        }
+    } else if (g.score_prefetch != 0) {
+        for (int off = cx.tid * 128; off < g.n_state * 8; off += T * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S) + off));
+    }
 #endif
     for (int i = cx.tid; i < nb; i += T) {
         double sn, cs;
