@@ -186,7 +186,10 @@ typedef struct {
  * branches get their admittances -- and Ybus its values -- recomputed per environment by
  * opfg_assemble (kernel 1), in the fixed sparsity pattern of the nominal topology.
  * Replaces pandapower's per-call `_calc_branch_values_from_trafo_df` / `_calc_line_parameter` +
- * makeYbus for those branches (reached from opfgym/opf_env.py:476-483, 703). */
+ * makeYbus for those branches (reached from opfgym/opf_env.py:476-483, 703).
+ * Islands: if a cleared in-service cell cuts buses off every reference bus, opfg_assemble finds them per
+ * environment (pandapower pd2ppc `_check_connectivity`: such buses are dropped from the power flow) and
+ * opfg_pf_solve solves the rest; `vm` / `va` of a dropped bus come back NaN, `converged` stays 1. */
 typedef struct {
     int32_t n_dyn;
     const int32_t* branch;          /* host [n_dyn] ppc branch row                                        */

@@ -68,6 +68,14 @@ void dev_put(void* dst, const void* src, size_t bytes) {
     cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
 #endif
 }
+void dev_get(void* dst, const void* src, size_t bytes) {
+    if (!bytes) return;
+#ifdef OPFG_HOSTSIM
+    memcpy(dst, src, bytes);
+#else
+    cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+#endif
+}
 
 }  // namespace
 
@@ -79,6 +87,8 @@ struct OpfgGrid {
     std::vector<int> gen_bus_host;
     std::vector<double> gen_q_share_host;
     std::vector<double> vm_bus_host;       // start |V| by ppc bus (set-point at generator buses)
+    std::vector<int> br_f_host, br_t_host, type_host;     // ppc branch ends / bus types (island analysis)
+    std::vector<unsigned char> br_on_host;                // static branch status
     int n_result_cells = 0;
     double flops_score = 0;
     bool has_assembly = false, has_scoring = false;
@@ -636,7 +646,7 @@ __global__ void __launch_bounds__(T == 32 ? 768 : T * 32, 1) k_pf_tree(GridDev g
         int64_t env = base + grp;
         const bool live = env < B.n_env;
         if (!live) env = B.n_env - 1;          // idle groups shadow the last environment (no stores)
-        env_pf_tree(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
+        env_pf_tree<Grp<T>, DYN>(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
                     DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
                     B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env, live);
         __syncwarp();
@@ -773,7 +783,7 @@ static bool use_lanes(const OpfgGrid* G, const OpfgBatch* B) {
     (void)B;
     if (G->pf_kernel != 2) return false;
     const GridDev& d = G->d;
-    return G->lanes_ok && G->lane_scratch && (!d.init_dc || d.dc_pre);
+    return G->lanes_ok && G->lane_scratch && (!d.init_dc || d.dc_pre) && !d.isl;   // the lane kernel has no island handling
 }
 
 // ------------------------------------------------------------------- C ABI
@@ -849,6 +859,9 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             if (on) active.push_back(bh);
             else { p[0] = 1e300; p[1] = 0; p[2] = 0; p[3] = 0; }   // open branch: zero admittance
         }
+        G->br_f_host = br_f; G->br_t_host = br_t; G->type_host = type;
+        G->br_on_host.resize(nbr);
+        for (int l = 0; l < nbr; ++l) G->br_on_host[l] = desc->branch[(size_t)l * desc->branch_cols + OPFG_BR_STATUS] != 0.0;
         // map active branches back to ppc rows for Ybus contributions
         std::vector<int> active_row;
         for (int l = 0; l < nbr; ++l)
@@ -1289,6 +1302,74 @@ int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
         d.dyn_neutral = G->up(dd->tap_neutral, dd->n_dyn);
         d.dyn_step = G->up(dd->tap_step_percent, dd->n_dyn);
         d.dyn_ratio0 = G->up(dd->ratio_neutral, dd->n_dyn);
+        // Islands.  Spanning forest of the static grid from the slack buses, branches WITHOUT an in-service
+        // cell first: a dynamic branch that still becomes a tree edge is "critical" -- only when one of those
+        // is out can an environment lose buses, and only then does kernel 1 walk the grid (open ties that
+        // merely close loops never trigger the walk).
+        d.isl = 0; d.dyn_crit = nullptr; d.isl_ptr = d.isl_adj = d.isl_br = nullptr;
+        bool any_switchable = false;
+        std::vector<unsigned char> switchable(d.nbr, 0);
+        for (int i = 0; i < dd->n_dyn; ++i) {
+            const int r = dd->in_service[i];
+            // a reference to a constant that is not 0 means "always in service"
+            bool fixed_on = false;
+            if (r < 0) {
+                double c;
+                dev_get(&c, d.consts + (-r - 1), sizeof(double));
+                fixed_on = c != 0.0;
+            }
+            if (!fixed_on && G->br_on_host[dd->branch[i]]) { switchable[dd->branch[i]] = 1; any_switchable = true; }
+        }
+        if (any_switchable) {
+            const int nb = d.nb, nbr = d.nbr;
+            std::vector<int> ptr(nb + 1, 0), adj, brs;
+            for (int l = 0; l < nbr; ++l)
+                if (G->br_on_host[l] && G->br_f_host[l] != G->br_t_host[l]) { ptr[G->br_f_host[l] + 1]++; ptr[G->br_t_host[l] + 1]++; }
+            for (int b = 0; b < nb; ++b) ptr[b + 1] += ptr[b];
+            adj.resize(ptr[nb]); brs.resize(ptr[nb]);
+            std::vector<int> fillp(ptr.begin(), ptr.end() - 1);
+            for (int pass = 0; pass < 2; ++pass)          // fixed branches first: the walk meets them first, too
+                for (int l = 0; l < nbr; ++l) {
+                    if (!G->br_on_host[l] || G->br_f_host[l] == G->br_t_host[l] || (int)switchable[l] != pass) continue;
+                    const int f = G->br_f_host[l], t = G->br_t_host[l];
+                    adj[fillp[f]] = t; brs[fillp[f]++] = l;
+                    adj[fillp[t]] = f; brs[fillp[t]++] = l;
+                }
+            // forest: breadth-first over the fixed branches, then extended through switchable ones
+            std::vector<char> seen(nb, 0);
+            std::vector<unsigned char> crit(dd->n_dyn, 0);
+            std::vector<int> queue;
+            for (int b = 0; b < nb; ++b) if (G->type_host[b] == 3) { seen[b] = 1; queue.push_back(b); }
+            size_t head = 0;
+            for (;;) {
+                for (; head < queue.size(); ++head) {
+                    const int a = queue[head];
+                    for (int e = ptr[a]; e < ptr[a + 1]; ++e)
+                        if (!switchable[brs[e]] && !seen[adj[e]]) { seen[adj[e]] = 1; queue.push_back(adj[e]); }
+                }
+                bool grown = false;                        // one switchable edge out of the reached set, then go on
+                for (size_t q = 0; q < queue.size() && !grown; ++q) {
+                    const int a = queue[q];
+                    for (int e = ptr[a]; e < ptr[a + 1] && !grown; ++e)
+                        if (switchable[brs[e]] && !seen[adj[e]]) {
+                            seen[adj[e]] = 1; queue.push_back(adj[e]);
+                            crit[of[brs[e]]] = 1; grown = true;
+                        }
+                }
+                if (!grown) break;
+            }
+            bool any_crit = false;
+            for (unsigned char c : crit) any_crit |= c != 0;
+            if (any_crit) {
+                d.dyn_crit = G->up(crit); d.isl_ptr = G->up(ptr); d.isl_adj = G->up(adj); d.isl_br = G->up(brs);
+                d.isl = 1;
+                if (!d.vm_from_state) {                    // kernel 1 writes every start |V|: the mark of a dropped bus is 0
+                    std::vector<int> no_ref(nb, OPFG_NO_REF);
+                    d.bus_vm_ref = G->up(no_ref); d.vm0_bus = G->up(G->vm_bus_host);
+                    d.vm_from_state = 1;
+                }
+            }
+        }
         return 0;
     } catch (const std::exception& ex) {
         return fail("opfg_set_dynamic_branches: %s", ex.what());
@@ -1549,7 +1630,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         std::vector<double> tsm(G->tree_env_doubles);
         const bool dyn = d.n_dyn > 0 && B->yval;
         for (int64_t env = 0; env < B->n_env; ++env)
-            env_pf_tree(d, gx, tsm.data(), B->sbus + env * (int64_t)d.nb * 2,
+            env_pf_tree<Grp<1>, true>(d, gx, tsm.data(), B->sbus + env * (int64_t)d.nb * 2,
                         dyn ? B->yval + env * (int64_t)d.nnz_y * 2 : nullptr, B->vm + env * (int64_t)d.nb,
                         B->va + env * (int64_t)d.nb, B->converged + env, B->iterations + env, true);
         return 0;

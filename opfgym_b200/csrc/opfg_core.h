@@ -78,6 +78,14 @@ struct GridDev {
     const int* dyn_of_branch;          // [nbr] index into the dynamic list or -1
     const int *dyn_tap_ref, *dyn_svc_ref;
     const double *dyn_neutral, *dyn_step, *dyn_ratio0;
+    // islands: an in-service cell that is 0 can cut buses off every slack bus.  pandapower drops them
+    // (pd2ppc.py _check_connectivity [ext-mem]: bus type NONE, results NaN) and solves the rest.  Kernel 1
+    // finds them per environment -- only when a branch of the static grid's spanning tree is out, `dyn_crit` --
+    // and marks them with a start |V| of exactly 0; the power-flow kernels keep such a bus at V = 0 behind
+    // identity Jacobian rows (same linear system as the reduced grid) and report NaN for it.
+    int isl;
+    const unsigned char* dyn_crit;     // [n_dyn] 1: the branch is a spanning-tree edge
+    const int *isl_ptr, *isl_adj, *isl_br;   // CSR by ppc bus over the branches that can be in service: neighbour bus, branch row
     // DC start
     const double* dc_val;              // [n_blocks] scalar factor on the same schedule
     const double* dc_rhs0;             // [n]
@@ -375,11 +383,48 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
 #endif
         for (int e = cx.tid; e < g.nnz_y; e += T) ybus_entry(g, g.br_y, e, yval_env + 2 * (size_t)e, bry_env);
     }
-    if (g.vm_from_state && vm_out)       // start |V| / set-point of every bus (pandapower: V0[gen bus] = VG)
+    if (g.vm_from_state && vm_out) {     // start |V| / set-point of every bus (pandapower: V0[gen bus] = VG)
+        bool islands = false;
+        if (g.isl && bry_env) {          // is a spanning-tree branch out of service in this environment?
+            double out = 0.0;
+            for (int d = cx.tid; d < g.n_dyn; d += T)
+                if (g.dyn_crit[d] && ref_val(g, S, g.dyn_svc_ref[d]) == 0.0) out = 1.0;
+            islands = cx.block_max(out) > 0.0;
+        }
         for (int bus = cx.tid; bus < g.nb; bus += T) {
             const int r = g.bus_vm_ref[bus];
-            vm_out[bus] = r == OPFG_NO_REF ? g.vm0_bus[bus] : ref_val(g, S, r);
+            const double vm = r == OPFG_NO_REF ? g.vm0_bus[bus] : ref_val(g, S, r);
+            // while the walk below runs, a NEGATIVE start value means "not reached yet"; slack buses are the seeds
+            vm_out[bus] = (islands && g.type_int[g.int_of_bus[bus]] != OPFG_REF) ? -vm : vm;
         }
+        if (islands) {
+#ifdef OPFG_DEVICE_BUILD
+            volatile double* lab = vm_out;      // labels change under the readers' feet (monotonically): no caching
+#else
+            double* lab = vm_out;
+#endif
+            for (;;) {
+                cx.sync();
+#ifdef OPFG_DEVICE_BUILD
+                __threadfence_block();
+#endif
+                double changed = 0.0;
+                for (int bus = cx.tid; bus < g.nb; bus += T) {
+                    if (lab[bus] > 0.0) continue;
+                    bool hit = false;
+                    for (int e = g.isl_ptr[bus]; e < g.isl_ptr[bus + 1] && !hit; ++e) {
+                        const int d = g.dyn_of_branch[g.isl_br[e]];
+                        if (d >= 0 && ref_val(g, S, g.dyn_svc_ref[d]) == 0.0) continue;
+                        hit = lab[g.isl_adj[e]] > 0.0;
+                    }
+                    if (hit) { lab[bus] = -lab[bus]; changed = 1.0; }
+                }
+                if (!(cx.block_max(changed) > 0.0)) break;
+            }
+            for (int bus = cx.tid; bus < g.nb; bus += T)
+                if (!(lab[bus] > 0.0)) lab[bus] = 0.0;             // cut off: dropped from this power flow
+        }
+    }
     const double inv_base = 1.0 / g.base_mva;
     // buses in descending order of their entry count: the lanes of one round carry equal work
     for (int k = cx.tid; k < g.nb; k += T) {
@@ -458,6 +503,11 @@ OPFG_HD double row_mismatch(const GridDev& g, const PfSmem& s, const double* yv,
         if (e == e0) { dr = tr; di = ti; }                    // the diagonal entry is first
     }
     const double P = fma(vi.x, ir, vi.y * ii), Q = fma(vi.y, ir, -(vi.x * ii));   // S_i = V_i conj(I_i)
+    if (g.isl && vi.x == 0.0 && vi.y == 0.0) {               // bus cut off from every slack: identity rows, no mismatch
+        if (jac) { st2(s.lu + 2 * i, 1.0, 0.0); st2(s.lu1 + 2 * i, 0.0, 1.0); }
+        st2(s.rhs + 2 * i, 0.0, 0.0);
+        return 0.0;
+    }
     if (jac) {
         const double ar = fma(vi.x, dr, vi.y * di), ai = fma(vi.y, dr, -(vi.x * di));   // V_i conj(Y_ii V_i)
         const double inv_vmi = s.ivm[i];
@@ -646,10 +696,11 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
     for (int i = cx.tid; i < nb; i += T) {
         const int bus = g.bus_of_int[i];
         const double vm = g.vm_from_state ? vm_out[bus] : g.vm0_int[i];
-        const double va = (g.init_dc && i < n) ? (g.dc_pre ? va_out[bus] : s.rhs[i]) : g.va0_int[i];
+        const bool dead = g.isl && vm == 0.0;                 // kernel 1 found the bus cut off from every slack
+        const double va = dead ? 0.0 : ((g.init_dc && i < n) ? (g.dc_pre ? va_out[bus] : s.rhs[i]) : g.va0_int[i]);
         double sn, cs;
         sincos(va, &sn, &cs);
-        vm_out[bus] = vm; va_out[bus] = va; s.ivm[i] = 1.0 / vm;
+        vm_out[bus] = vm; va_out[bus] = va; s.ivm[i] = dead ? 0.0 : 1.0 / vm;
         st2(s.vri + 2 * i, vm * cs, vm * sn);
     }
     cx.sync();
@@ -733,7 +784,7 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
             if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
             double sn, cs;
             sincos(va, &sn, &cs);
-            va_out[bus] = va; vm_out[bus] = vm; s.ivm[k] = 1.0 / vm;
+            va_out[bus] = va; vm_out[bus] = vm; s.ivm[k] = (g.isl && vm == 0.0) ? 0.0 : 1.0 / vm;
             st2(s.vri + 2 * k, vm * cs, vm * sn);
         }
         cx.sync();
@@ -748,6 +799,7 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
             const int i = g.qlim_bus[q];
             if (s.type[i] != OPFG_PV) continue;
             const D2 vi = ld2(s.vri + 2 * i);
+            if (g.isl && vi.x == 0.0 && vi.y == 0.0) continue;
             double ir = 0, ii = 0;
             for (int e = g.y_ptr[i]; e < g.y_ptr[i + 1]; ++e) {
                 const D2 y = ld2(yv + 2 * e);
@@ -763,6 +815,12 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
         cx.sync();
         if (changed > 0) { converged = 0; it = 0; prev = 1.0; goto restart_after_q_limits; }
     }
+    if (g.isl)                         // pandapower reports NaN for the buses it dropped
+        for (int k = cx.tid; k < n; k += T)
+            if (s.vri[2 * k] == 0.0 && s.vri[2 * k + 1] == 0.0) {
+                const int bus = g.bus_of_int[k];
+                vm_out[bus] = NAN; va_out[bus] = NAN;
+            }
     if (cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
 }
 
@@ -851,9 +909,10 @@ OPFG_HD void tree_entry(const TreeSmem& s, TreeAcc& a, uint32_t ent, D2 y, D2 vj
     }
 }
 
-template <bool JAC>
+template <bool JAC, bool ISL = false>
 OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D2 sp, int k) {
     const D2 vk = ld2(s.vri + 2 * k);
+    const bool dead = ISL && vk.x == 0.0 && vk.y == 0.0;      // cut off from every slack (kernel 1): V stays 0
     const bool pq = g.tr_type[k] == OPFG_PQ;
     const int e0 = g.tr_y_ptr[k], e1 = g.tr_y_ptr[k + 1];
     TreeAcc a{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, -1};
@@ -876,15 +935,15 @@ OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D
         tree_entry<JAC>(s, a, ea, ld2(yv + 2 * e), ld2(s.vri + 2 * (ea & 0xffffu)), vk, pq);
     }
     const double P = fma(vk.x, a.ir, vk.y * a.ii), Q = fma(vk.y, a.ir, -(vk.x * a.ii));   // S_k = V_k conj(I_k)
-    const double dp = P - sp.x, dq = pq ? Q - sp.y : 0.0;
+    const double dp = dead ? 0.0 : P - sp.x, dq = (pq && !dead) ? Q - sp.y : 0.0;
     double res;
     if (dp != dp || dq != dq) res = NAN;
     else { const double x = fabs(dp), c = fabs(dq); res = x > c ? x : c; }
     if (!JAC) return res;
     const double ar = fma(vk.x, dr, vk.y * di), ai = fma(vk.y, dr, -(vk.x * di));   // V_k conj(Y_kk V_k)
     const double inv_vmk = s.ivm[k];
-    const double d00 = (-Q + ai) - a.g00, d01 = (ar + P) * inv_vmk - a.g01;
-    const double d10 = (pq ? P - ar : 0.0) - a.g10, d11 = (pq ? (ai + Q) * inv_vmk : 1.0) - a.g11;
+    const double d00 = dead ? 1.0 : (-Q + ai) - a.g00, d01 = (ar + P) * inv_vmk - a.g01;
+    const double d10 = (pq ? P - ar : 0.0) - a.g10, d11 = dead ? 1.0 : (pq ? (ai + Q) * inv_vmk : 1.0) - a.g11;
     const double y0 = -dp - a.gy0, y1 = -dq - a.gy1;
     const double r = 1.0 / fma(d00, d11, -(d01 * d10));
     const double ia = d11 * r, ib = -d01 * r, ic = -d10 * r, id_ = d00 * r;
@@ -899,7 +958,7 @@ OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D
     return res;
 }
 
-template <class C>
+template <class C, bool ISL_T = false>
 OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const double* sbus, const double* yval_env,
                          double* vm_out, double* va_out, uint8_t* conv_out, int32_t* iter_out, bool live) {
     const int T = cx.nthreads();
@@ -918,22 +977,24 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
         if (i < nb) {
             const int bus = g.tr_bus_of_int[i];
             const double vm = g.vm_from_state ? vm_out[bus] : g.tr_vm0[i];
-            const double va = (g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i];   // DC start: the dense pre-pass wrote it
+            const bool dead = ISL_T && g.isl && vm == 0.0;      // kernel 1 found the bus cut off from every slack
+            const double va = dead ? 0.0 : ((g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i]);   // DC start: the dense pre-pass wrote it
             double sn, cs;
             sincos(va, &sn, &cs);
             vm_own[r] = vm; va_own[r] = va;
-            s.ivm[i] = 1.0 / vm;
+            s.ivm[i] = dead ? 0.0 : 1.0 / vm;
             st2(s.vri + 2 * i, vm * cs, vm * sn);
         }
     }
     for (int i = cx.tid + OWN * T; i < nb; i += T) {
         const int bus = g.tr_bus_of_int[i];
         const double vm = g.vm_from_state ? vm_out[bus] : g.tr_vm0[i];
-        const double va = (g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i];
+        const bool dead = ISL_T && g.isl && vm == 0.0;
+        const double va = dead ? 0.0 : ((g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i]);
         double sn, cs;
         sincos(va, &sn, &cs);
         if (live) { vm_out[bus] = vm; va_out[bus] = va; }
-        s.ivm[i] = 1.0 / vm;
+        s.ivm[i] = dead ? 0.0 : 1.0 / vm;
         st2(s.vri + 2 * i, vm * cs, vm * sn);
     }
     cx.sync();
@@ -946,7 +1007,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             double part = 0;
             bool bad = false;
             for (int k = cx.tid; k < n; k += T) {
-                const double r = tree_row<false>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
+                const double r = tree_row<false, ISL_T>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
                 if (r != r) bad = true; else if (r > part) part = r;
             }
             const double nrm = cx.group_max(bad ? NAN : part);
@@ -972,10 +1033,10 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             }
             int k = g.tr_level_ptr[l] + cx.tid;
             if (k < le) {
-                double r = tree_row<true>(g, s, yv, sp0, k);
+                double r = tree_row<true, ISL_T>(g, s, yv, sp0, k);
                 if (r != r) bad = true; else if (r > part) part = r;
                 for (k += T; k < le; k += T) {                // levels wider than the group (unbalanced schedule)
-                    r = tree_row<true>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
+                    r = tree_row<true, ISL_T>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
                     if (r != r) bad = true; else if (r > part) part = r;
                 }
             }
@@ -1015,7 +1076,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
                     if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
                     double sn, cs;
                     sincos(va, &sn, &cs);
-                    va_own[r] = va; vm_own[r] = vm; s.ivm[k] = 1.0 / vm;
+                    va_own[r] = va; vm_own[r] = vm; s.ivm[k] = (ISL_T && vm == 0.0) ? 0.0 : 1.0 / vm;
                     st2(s.vri + 2 * k, vm * cs, vm * sn);
                 }
             }
@@ -1028,7 +1089,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
                 if (va > M_PI || va <= -M_PI) va -= 2.0 * M_PI * floor((va + M_PI) / (2.0 * M_PI));
                 double sn, cs;
                 sincos(va, &sn, &cs);
-                va_out[bus] = va; vm_out[bus] = vm; s.ivm[k] = 1.0 / vm;
+                va_out[bus] = va; vm_out[bus] = vm; s.ivm[k] = (ISL_T && vm == 0.0) ? 0.0 : 1.0 / vm;
                 st2(s.vri + 2 * k, vm * cs, vm * sn);
             }
         }
@@ -1038,8 +1099,17 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
 #pragma unroll
         for (int r = 0; r < OWN; ++r) {
             const int i = cx.tid + r * T;
-            if (i < nb) { const int bus = g.tr_bus_of_int[i]; vm_out[bus] = vm_own[r]; va_out[bus] = va_own[r]; }
+            if (i < nb) {
+                const int bus = g.tr_bus_of_int[i];
+                const bool dead = ISL_T && g.isl && vm_own[r] == 0.0;   // pandapower reports NaN for the buses it dropped
+                vm_out[bus] = dead ? NAN : vm_own[r]; va_out[bus] = dead ? NAN : va_own[r];
+            }
         }
+        if (ISL_T && g.isl)
+            for (int i = cx.tid + OWN * T; i < nb; i += T) {
+                const int bus = g.tr_bus_of_int[i];
+                if (vm_out[bus] == 0.0) { vm_out[bus] = NAN; va_out[bus] = NAN; }
+            }
     }
     if (live && cx.tid == 0) { *conv_out = (uint8_t)converged; *iter_out = it; }
 }
@@ -1375,10 +1445,11 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
 #endif
     for (int i = cx.tid; i < nb; i += T) {
         double sn, cs;
-        sincos(va[i], &sn, &cs);
+        const bool dead = g.isl && vm[i] != vm[i];          // dropped bus (island): V = 0 towards its neighbours, NaN results
+        sincos(dead ? 0.0 : va[i], &sn, &cs);
         s.vm[i] = vm[i];
-        s.vr[i] = vm[i] * cs;
-        s.vi[i] = vm[i] * sn;
+        s.vr[i] = dead ? 0.0 : vm[i] * cs;
+        s.vi[i] = dead ? 0.0 : vm[i] * sn;
     }
     cx.sync();
     // branch flows and loading (pfsoln + results_branch.py [ext-mem])
@@ -1424,7 +1495,8 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
             ir += yv[2 * e] * s.vr[j] - yv[2 * e + 1] * s.vi[j];
             ii += yv[2 * e] * s.vi[j] + yv[2 * e + 1] * s.vr[j];
         }
-        const double P = s.vr[bus] * ir + s.vi[bus] * ii, Q = s.vi[bus] * ir - s.vr[bus] * ii;
+        double P = s.vr[bus] * ir + s.vi[bus] * ii, Q = s.vi[bus] * ir - s.vr[bus] * ii;
+        if (g.isl && s.vm[bus] != s.vm[bus]) P = Q = NAN;     // generator on a dropped bus
         if (ps >= 0) S[ps] = (P - sbus[2 * bus]) * base;
         if (qs >= 0) S[qs] = (Q - sbus[2 * bus + 1]) * base * g.gen_q_share[gi];
     }

@@ -9,9 +9,10 @@ of kernels 1/2-4/5 over the whole batch with the element's ``in_service`` cell
 cleared (per-environment branch parameters, see ``opfg_set_dynamic_branches``);
 the base case and all contingencies reuse the same compiled grid.
 
-Limit: an outage that islands part of the grid makes the
-Jacobian singular, so that environment reports a failed contingency, whereas
-pandapower would drop the island and solve the rest.
+An outage that islands part of the grid (every line outage on a radial feeder does) is handled the way
+pandapower handles it: kernel 1 finds the buses cut off from every slack bus per environment, the power
+flow solves the rest, the dropped buses and their branches report NaN and violate nothing
+(``tests/test_islands.py``).
 """
 from __future__ import annotations
 
