@@ -198,7 +198,16 @@ typedef struct {
     const double* tap_step_percent; /* host [n_dyn]                                                        */
     const double* ratio_neutral;    /* host [n_dyn] off-nominal ratio at the neutral tap (HV-side changer) */
     const opfg_ref* in_service;     /* host [n_dyn] 0/1 cell (ref to constant 1: always in service)        */
+    /* optional, NULL = absent.  Switches at the branch ends (`switch.closed` of line-bus / trafo-bus switches,
+     * opfgym/examples/network_reconfiguration.py:34, security_constrained.py:31): a transformer with an open
+     * switch is out of service; a line that is open at ONE end stays energised from the other end (pandapower
+     * inserts an auxiliary bus there; here that bus is eliminated analytically), open at both ends it is out. */
+    const opfg_ref* closed_from;    /* host [n_dyn] 0/1 cell of the switch at the from / hv end (ref to constant 1: none) */
+    const opfg_ref* closed_to;      /* host [n_dyn] ... at the to / lv end                                  */
+    const int32_t* flags;           /* host [n_dyn] OPFG_DYN_* bits                                        */
 } OpfgDynBranchDesc;
+enum { OPFG_DYN_TAP_LV = 1,         /* tap changer on the LV side: ratio / t, series impedance * t^2, magnetising branch / t^2 */
+       OPFG_DYN_TRAFO = 2 };        /* transformer: any open switch takes it out of service                 */
 
 /* device buffers of one batch (any pointer may be NULL if the stage that needs it is not run) */
 typedef struct {

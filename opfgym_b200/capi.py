@@ -75,7 +75,8 @@ class ScoringDesc(C.Structure):
 
 class DynBranchDesc(C.Structure):
     _fields_ = [("n_dyn", C.c_int32), ("branch", _ip), ("tap_pos", _ip), ("tap_neutral", _dp),
-                ("tap_step_percent", _dp), ("ratio_neutral", _dp), ("in_service", _ip)]
+                ("tap_step_percent", _dp), ("ratio_neutral", _dp), ("in_service", _ip),
+                ("closed_from", _ip), ("closed_to", _ip), ("flags", _ip)]
 
 
 class RowOp(C.Structure):

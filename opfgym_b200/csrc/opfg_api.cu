@@ -89,6 +89,7 @@ struct OpfgGrid {
     std::vector<double> vm_bus_host;       // start |V| by ppc bus (set-point at generator buses)
     std::vector<int> br_f_host, br_t_host, type_host;     // ppc branch ends / bus types (island analysis)
     std::vector<unsigned char> br_on_host;                // static branch status
+    std::vector<double> br_tap_host;                      // static off-nominal ratio
     int n_result_cells = 0;
     double flops_score = 0;
     bool has_assembly = false, has_scoring = false;
@@ -616,7 +617,10 @@ __global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E,
     const int e_local = threadIdx.x / T;
     double* mine = sm + g.tab_staged_bytes / 8 + (size_t)e_local * env_doubles;
     Ctx<T> cx{(int)(threadIdx.x % T), mine + pf_smem_doubles(g.n_blocks, g.n, g.nb, T) - 2 * (T / 32 + 1) - 2, 1 + e_local};
-    for (int64_t env = (int64_t)blockIdx.x * E + e_local; env < B.n_env; env += (int64_t)gridDim.x * E) {
+    // every CTA owns a contiguous share of the batch: the last, partial round is then spread over ALL SMs (a few
+    // environments each, running faster for the lack of competition) instead of filling a quarter of them
+    const int64_t lo = B.n_env * (int64_t)blockIdx.x / gridDim.x, hi = B.n_env * ((int64_t)blockIdx.x + 1) / gridDim.x;
+    for (int64_t env = lo + e_local; env < hi; env += E) {
         env_pf_solve(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
                      DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
                      B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env);
@@ -625,9 +629,10 @@ __global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E,
 }
 // Fused kernel for radial grids (opfg_core.h, env_pf_tree): persistent CTAs, E environments of T lanes
 // each (32 / T environments share a warp and run in lockstep), tables staged once per CTA.
-#define OPFG_TREE_TABLES(X) X(tr_bus_of_int) X(tr_level_ptr) X(tr_y_ptr) X(tr_parent) X(tr_type) X(tr_y_ent) X(tr_y_val) X(tr_vm0) X(tr_va0)
-template <int T, bool DYN>
-__global__ void __launch_bounds__(T == 32 ? 768 : T * 32, 1) k_pf_tree(GridDev g, OpfgBatch B, int E, int env_doubles) {
+#define OPFG_TREE_TABLES(X) X(tr_bus_of_int) X(tr_level_ptr) X(tr_y_ptr) X(tr_parent) X(tr_type) X(tr_y_ent) X(tr_y_val) X(tr_vm0) X(tr_va0) \
+    X(tr_dc_inv) X(tr_dc_w) X(tr_dc_rhs0)
+template <int T, bool DYN, int MAX_THREADS = (T == 32 ? 768 : T * 32)>
+__global__ void __launch_bounds__(MAX_THREADS, 1) k_pf_tree(GridDev g, OpfgBatch B, int E, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
     {
         const int4* src = reinterpret_cast<const int4*>(g.tab4_base);
@@ -642,10 +647,14 @@ __global__ void __launch_bounds__(T == 32 ? 768 : T * 32, 1) k_pf_tree(GridDev g
     const int grp = threadIdx.x / T;
     double* mine = sm + g.tab4_bytes / 8 + (size_t)grp * env_doubles;
     Grp<T> cx{(int)(threadIdx.x % T)};
-    for (int64_t base = (int64_t)blockIdx.x * E; base < B.n_env; base += (int64_t)gridDim.x * E) {
+    // every CTA owns a contiguous share of the batch: the last, partial round is then spread over ALL SMs (a few
+    // environments each, running faster for the lack of competition) instead of filling a quarter of them
+    const int64_t lo = B.n_env * (int64_t)blockIdx.x / gridDim.x, hi = B.n_env * ((int64_t)blockIdx.x + 1) / gridDim.x;
+    for (int64_t base = lo; base < hi; base += E) {
+        if (base + (grp & ~(32 / T - 1)) >= hi) break;   // no environment left for this warp (the solve only uses __syncwarp)
         int64_t env = base + grp;
-        const bool live = env < B.n_env;
-        if (!live) env = B.n_env - 1;          // idle groups shadow the last environment (no stores)
+        const bool live = env < hi;
+        if (!live) env = hi - 1;               // an idle group shadows its warp's last environment (no stores)
         env_pf_tree<Grp<T>, DYN>(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
                     DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
                     B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env, live);
@@ -773,7 +782,7 @@ static int tree_lanes() {
 static bool use_tree(const OpfgGrid* G, const OpfgBatch* B) {
     (void)B;
     const GridDev& d = G->d;
-    return d.tr_ok && (G->pf_kernel == 0 || G->pf_kernel == 3) && (!d.init_dc || d.dc_pre);
+    return d.tr_ok && (G->pf_kernel == 0 || G->pf_kernel == 3) && (!d.init_dc || d.dc_pre || d.tr_dc);
 }
 
 // Which power-flow kernel a launch uses: the lane-per-environment kernel when its tables exist (row
@@ -860,8 +869,11 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             else { p[0] = 1e300; p[1] = 0; p[2] = 0; p[3] = 0; }   // open branch: zero admittance
         }
         G->br_f_host = br_f; G->br_t_host = br_t; G->type_host = type;
-        G->br_on_host.resize(nbr);
-        for (int l = 0; l < nbr; ++l) G->br_on_host[l] = desc->branch[(size_t)l * desc->branch_cols + OPFG_BR_STATUS] != 0.0;
+        G->br_on_host.resize(nbr); G->br_tap_host.resize(nbr);
+        for (int l = 0; l < nbr; ++l) {
+            G->br_on_host[l] = desc->branch[(size_t)l * desc->branch_cols + OPFG_BR_STATUS] != 0.0;
+            G->br_tap_host[l] = desc->branch[(size_t)l * desc->branch_cols + OPFG_TAP];
+        }
         // map active branches back to ppc rows for Ybus contributions
         std::vector<int> active_row;
         for (int l = 0; l < nbr; ++l)
@@ -1102,7 +1114,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                         col[e] = (uint32_t)c | (kind << 16);
                     }
                 char* keep_base = G->tab_base; size_t keep_cap = G->tab_cap, keep_used = G->tab_used;
-                G->tab_reserve(1024 + 4 * (size_t)(3 * nb + s.n_levels + 8) + nb + 4 * col.size() + 16 * col.size() + 16 * (size_t)nb + 16 * 12);
+                G->tab_reserve(1024 + 4 * (size_t)(3 * nb + s.n_levels + 8) + nb + 4 * col.size() + 16 * col.size() + 40 * (size_t)nb + 16 * 16);
                 G->tab_used = 0;
                 d.tab4_base = G->tab_base;
                 d.tr_y_val = G->tab(std::vector<double>(2 * col.size(), 0.0));      // filled after the Ybus assembly
@@ -1110,6 +1122,18 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                 d.tr_bus_of_int = G->tab(s.bus_of_int); d.tr_level_ptr = G->tab(s.level_ptr);
                 d.tr_y_ptr = G->tab(s.y_ptr); d.tr_parent = G->tab(parent);
                 d.tr_y_ent = G->tab(col); d.tr_type = G->tab(type_int);
+                // DC start inside the kernel: 1 / d_k and W_k = B'_kp / d_k of the leaf-first factor of B'
+                d.tr_dc = 0; d.tr_dc_inv = d.tr_dc_w = d.tr_dc_rhs0 = d.tr_vm0;
+                const bool dc_in_tree = getenv("OPFG_TREE_DC") ? atoi(getenv("OPFG_TREE_DC")) != 0 : true;
+                if (desc->init_dc && dc_ok && dc_in_tree) {
+                    std::vector<double> inv(s.n), w(s.n, 0.0);
+                    for (int k = 0; k < s.n; ++k) {
+                        inv[k] = dc_val[k];
+                        if (s.up_ptr[k + 1] > s.up_ptr[k]) w[k] = dc_val[s.up_w[s.up_ptr[k]]];
+                    }
+                    d.tr_dc_inv = G->tab(inv); d.tr_dc_w = G->tab(w); d.tr_dc_rhs0 = G->tab(dc_rhs0);
+                    d.tr_dc = 1;
+                }
                 d.tab4_bytes = (int)((G->tab_used + 15) & ~size_t(15));
                 G->tab_base = keep_base; G->tab_cap = keep_cap; G->tab_used = keep_used;
                 d.tr_ok = 1;
@@ -1291,8 +1315,33 @@ int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
             if (br < 0 || br >= d.nbr) throw std::runtime_error("dynamic branch out of range");
             if (of[br] >= 0) throw std::runtime_error("branch listed twice");
             of[br] = i;
-            for (const int* r : {dd->tap_pos + i, dd->in_service + i})
-                if (*r >= d.n_state || -*r - 1 >= d.n_const) throw std::runtime_error("reference out of range");
+            for (const int* r : {dd->tap_pos + i, dd->in_service + i, dd->closed_from ? dd->closed_from + i : nullptr,
+                                 dd->closed_to ? dd->closed_to + i : nullptr})
+                if (r && (*r >= d.n_state || -*r - 1 >= d.n_const)) throw std::runtime_error("reference out of range");
+        }
+        // optional arrays: no switches (the in-service reference stands in: same value, "closed" wherever the
+        // branch is in service at all would be wrong for a cleared cell, so point at a constant that is not 0)
+        std::vector<int> cf(dd->n_dyn), ct(dd->n_dyn), flags(dd->n_dyn, 0);
+        std::vector<double> lv_scale(dd->n_dyn, 1.0);
+        int one_ref = 0;
+        {
+            std::vector<double> cs(d.n_const);
+            dev_get(cs.data(), d.consts, sizeof(double) * d.n_const);
+            int found = -1;
+            for (int c = 0; c < d.n_const && found < 0; ++c) if (cs[c] == 1.0) found = c;
+            if (found < 0 && (!dd->closed_from || !dd->closed_to)) throw std::runtime_error("constant table holds no 1.0");
+            one_ref = -found - 1;
+        }
+        for (int i = 0; i < dd->n_dyn; ++i) {
+            cf[i] = dd->closed_from ? dd->closed_from[i] : one_ref;
+            ct[i] = dd->closed_to ? dd->closed_to[i] : one_ref;
+            flags[i] = dd->flags ? dd->flags[i] : 0;
+            if (flags[i] & OPFG_DYN_TAP_LV) {
+                // the ppc row carries the parameters at the static tap t0 = ratio_neutral / ratio_static
+                const double ratio_static = G->br_tap_host[dd->branch[i]] == 0.0 ? 1.0 : G->br_tap_host[dd->branch[i]];
+                const double t0 = dd->ratio_neutral[i] / ratio_static;
+                lv_scale[i] = 1.0 / (t0 * t0);
+            }
         }
         d.n_dyn = dd->n_dyn;
         d.dyn_branch = G->up(dd->branch, dd->n_dyn);
@@ -1302,6 +1351,7 @@ int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
         d.dyn_neutral = G->up(dd->tap_neutral, dd->n_dyn);
         d.dyn_step = G->up(dd->tap_step_percent, dd->n_dyn);
         d.dyn_ratio0 = G->up(dd->ratio_neutral, dd->n_dyn);
+        d.dyn_cf_ref = G->up(cf); d.dyn_ct_ref = G->up(ct); d.dyn_flags = G->up(flags); d.dyn_lv_scale = G->up(lv_scale);
         // Islands.  Spanning forest of the static grid from the slack buses, branches WITHOUT an in-service
         // cell first: a dynamic branch that still becomes a tree edge is "critical" -- only when one of those
         // is out can an environment lose buses, and only then does kernel 1 walk the grid (open ties that
@@ -1310,13 +1360,13 @@ int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
         bool any_switchable = false;
         std::vector<unsigned char> switchable(d.nbr, 0);
         for (int i = 0; i < dd->n_dyn; ++i) {
-            const int r = dd->in_service[i];
-            // a reference to a constant that is not 0 means "always in service"
-            bool fixed_on = false;
-            if (r < 0) {
+            // references to constants that are not 0 mean "always in service / closed"
+            bool fixed_on = true;
+            for (int r : {dd->in_service[i], cf[i], ct[i]}) {
+                if (r >= 0) { fixed_on = false; continue; }
                 double c;
                 dev_get(&c, d.consts + (-r - 1), sizeof(double));
-                fixed_on = c != 0.0;
+                fixed_on = fixed_on && c != 0.0;
             }
             if (!fixed_on && G->br_on_host[dd->branch[i]]) { switchable[dd->branch[i]] = 1; any_switchable = true; }
         }
@@ -1614,7 +1664,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     (void)stream;
     Ctx<1> cx;
     std::vector<double> sm(pf_smem_doubles(G->d.n_blocks, G->d.n, G->d.nb, 32, G->d.n_qlim));
-    if (G->d.dc_pre) {   // the dense DC pre-pass, as a plain loop
+    if (G->d.dc_pre && !(use_tree(G, B) && G->d.tr_dc)) {   // the dense DC pre-pass, as a plain loop (the radial kernel has its own DC start)
         const GridDev& d = G->d;
         for (int64_t env = 0; env < B->n_env; ++env)
             for (int i = 0; i < d.n; ++i) {
@@ -1655,7 +1705,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                      (G->d.n_dyn > 0 && B->yval) ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr, B->vm + env * (int64_t)G->d.nb,
                      B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);
 #else
-    if (G->d.dc_pre) {
+    if (G->d.dc_pre && !(use_tree(G, B) && G->d.tr_dc)) {   // the radial kernel has its own DC start
         static bool dc_attr = false;
         if (!dc_attr) { cudaFuncSetAttribute(k_dc_start, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM); dc_attr = true; }
         k_dc_start<<<dim3((unsigned)((B->n_env + DC_ENVS - 1) / DC_ENVS), (unsigned)((G->d.n + 63) / 64)), 256, DC_SMEM, (cudaStream_t)stream>>>(G->d, *B);
@@ -1664,8 +1714,10 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     if (use_tree(G, B)) {
         OpfgGrid* Gm = const_cast<OpfgGrid*>(G);
         const bool dyn = G->d.n_dyn > 0 && B->yval;
-        void (*fns[6])(GridDev, OpfgBatch, int, int) = {k_pf_tree<8, false>, k_pf_tree<16, false>, k_pf_tree<32, false>,
-                                                        k_pf_tree<8, true>, k_pf_tree<16, true>, k_pf_tree<32, true>};
+        // the last two: 16 lanes x at most 24 environments with the register cap of 384 threads (155 instead of 128)
+        void (*fns[8])(GridDev, OpfgBatch, int, int) = {k_pf_tree<8, false>, k_pf_tree<16, false>, k_pf_tree<32, false>,
+                                                        k_pf_tree<8, true>, k_pf_tree<16, true>, k_pf_tree<32, true>,
+                                                        k_pf_tree<16, false, 384>, k_pf_tree<16, true, 384>};
         if (!Gm->tree_attr_set) {      // per grid, hence per device
             for (auto* f : fns) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             Gm->tree_attr_set = true;
@@ -1674,6 +1726,10 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         const int64_t groups = (B->n_env + E - 1) / E;
         const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(groups, G->n_sm));
         auto* fn = fns[(T == 8 ? 0 : (T == 16 ? 1 : 2)) + (dyn ? 3 : 0)];
+        // measured on B200 (122-bus grid, 32 768 environments): 0.80 instead of 0.90 ms -- under the 128-register cap
+        // the staged-table base addresses were recomputed at their use sites
+        static const bool wide_regs = getenv("OPFG_TREE_WIDE_REGS") ? atoi(getenv("OPFG_TREE_WIDE_REGS")) != 0 : true;
+        if (wide_regs && T == 16 && E <= 24) fn = fns[dyn ? 7 : 6];
         fn<<<grid, T * E, G->tree_smem, (cudaStream_t)stream>>>(tree_view(G->d), *B, E, (int)G->tree_env_doubles);
         ++g_launches;
         cudaError_t e = cudaGetLastError();

@@ -77,7 +77,10 @@ struct GridDev {
     const int* dyn_branch;             // [n_dyn] ppc branch row
     const int* dyn_of_branch;          // [nbr] index into the dynamic list or -1
     const int *dyn_tap_ref, *dyn_svc_ref;
+    const int *dyn_cf_ref, *dyn_ct_ref;          // switches at the from / to end (reference to constant 1: none)
+    const int* dyn_flags;                        // OPFG_DYN_* bits
     const double *dyn_neutral, *dyn_step, *dyn_ratio0;
+    const double* dyn_lv_scale;                  // LV-side tap changers: 1 / t0^2 (the branch row was built at the static tap t0)
     // islands: an in-service cell that is 0 can cut buses off every slack bus.  pandapower drops them
     // (pd2ppc.py _check_connectivity [ext-mem]: bus type NONE, results NaN) and solves the rest.  Kernel 1
     // finds them per environment -- only when a branch of the static grid's spanning tree is out, `dyn_crit` --
@@ -151,6 +154,10 @@ struct GridDev {
     const unsigned char* tr_type;
     const uint32_t* tr_y_ent;          // per Ybus entry: column | kind << 16 (0 other, 1 child, 2 parent)
     const double *tr_y_val, *tr_vm0, *tr_va0;
+    // DC start inside the radial kernel (B' of a tree: one upward and one downward sweep of scalars):
+    // y_k = P_k + rhs0_k - sum_children W_c y_c;  theta_k = y_k / d_k - W_k theta_parent,  W_k = B'_kp / d_k
+    int tr_dc;
+    const double *tr_dc_inv, *tr_dc_w, *tr_dc_rhs0;
     const char* tab4_base;
     int tab4_bytes;
     const char* tab_base;              // contiguous arena holding the power-flow tables
@@ -372,10 +379,37 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
             double p[6];
             const double* src = g.br_param + 6 * (size_t)g.dyn_branch[d];
             for (int k = 0; k < 6; ++k) p[k] = src[k];
+            const int fl = g.dyn_flags[d];
             const double pos = ref_val(g, S, g.dyn_tap_ref[d]);
-            if (pos == pos) p[4] = g.dyn_ratio0[d] * (1.0 + (pos - g.dyn_neutral[d]) * g.dyn_step[d] / 100.0);
-            if (ref_val(g, S, g.dyn_svc_ref[d]) == 0.0) { p[0] = 1e300; p[1] = 0; p[2] = 0; p[3] = 0; }
-            branch_admittance(p, bry_env + 8 * (size_t)d);
+            if (pos == pos) {
+                if (fl & OPFG_DYN_TAP_LV) {
+                    // pandapower _calc_tap_from_dataframe / _calc_r_x_y_from_dataframe [ext-mem]: the LV voltage is
+                    // the tapped one, so the ratio falls with t while the impedances (referred to the LV side) rise with t^2
+                    const double t = 1.0 + (pos - g.dyn_neutral[d]) * g.dyn_step[d] / 100.0;
+                    const double t2 = t * t * g.dyn_lv_scale[d];
+                    p[4] = g.dyn_ratio0[d] / t;
+                    p[0] *= t2; p[1] *= t2; p[2] /= t2; p[3] /= t2;
+                } else {
+                    p[4] = g.dyn_ratio0[d] * (1.0 + (pos - g.dyn_neutral[d]) * g.dyn_step[d] / 100.0);
+                }
+            }
+            const bool cf = ref_val(g, S, g.dyn_cf_ref[d]) != 0.0, ct = ref_val(g, S, g.dyn_ct_ref[d]) != 0.0;
+            bool on = ref_val(g, S, g.dyn_svc_ref[d]) != 0.0;
+            on = on && ((fl & OPFG_DYN_TRAFO) ? (cf && ct) : (cf || ct));
+            if (!on) { p[0] = 1e300; p[1] = 0; p[2] = 0; p[3] = 0; }
+            double* y = bry_env + 8 * (size_t)d;
+            branch_admittance(p, y);
+            if (on && !(cf && ct)) {
+                // line open at one end: pandapower hangs it from an auxiliary bus (PQ, no injection); eliminating
+                // that bus leaves a shunt at the closed end: Y' = Y_cc - Y_co Y_oc / Y_oo
+                const double nr = y[2] * y[4] - y[3] * y[5], ni = y[2] * y[5] + y[3] * y[4];   // Yft Ytf
+                const double* o = cf ? y + 6 : y;             // Y_oo: the open end's self admittance
+                const double m2 = o[0] * o[0] + o[1] * o[1];
+                const double qr = (nr * o[0] + ni * o[1]) / m2, qi = (ni * o[0] - nr * o[1]) / m2;
+                const double cr = (cf ? y[0] : y[6]) - qr, ci = (cf ? y[1] : y[7]) - qi;
+                for (int k = 0; k < 8; ++k) y[k] = 0.0;
+                y[cf ? 0 : 6] = cr; y[cf ? 1 : 7] = ci;
+            }
         }
         cx.sync();
 #ifdef OPFG_DEVICE_BUILD
@@ -387,8 +421,8 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
         bool islands = false;
         if (g.isl && bry_env) {          // is a spanning-tree branch out of service in this environment?
             double out = 0.0;
-            for (int d = cx.tid; d < g.n_dyn; d += T)
-                if (g.dyn_crit[d] && ref_val(g, S, g.dyn_svc_ref[d]) == 0.0) out = 1.0;
+            for (int d = cx.tid; d < g.n_dyn; d += T)     // connects nothing: its Yft is zero (kernel 1a above)
+                if (g.dyn_crit[d] && bry_env[8 * (size_t)d + 2] == 0.0 && bry_env[8 * (size_t)d + 3] == 0.0) out = 1.0;
             islands = cx.block_max(out) > 0.0;
         }
         for (int bus = cx.tid; bus < g.nb; bus += T) {
@@ -414,7 +448,7 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
                     bool hit = false;
                     for (int e = g.isl_ptr[bus]; e < g.isl_ptr[bus + 1] && !hit; ++e) {
                         const int d = g.dyn_of_branch[g.isl_br[e]];
-                        if (d >= 0 && ref_val(g, S, g.dyn_svc_ref[d]) == 0.0) continue;
+                        if (d >= 0 && bry_env[8 * (size_t)d + 2] == 0.0 && bry_env[8 * (size_t)d + 3] == 0.0) continue;
                         hit = lab[g.isl_adj[e]] > 0.0;
                     }
                     if (hit) { lab[bus] = -lab[bus]; changed = 1.0; }
@@ -970,6 +1004,36 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
     // samples before).  Buses beyond OWN rounds (large grids) keep using the output buffers.
     constexpr int OWN = C::OWN_ROUNDS;       // 128 / T on the device: grids up to 128 buses stay in registers
     double vm_own[OWN], va_own[OWN];
+    const bool dc_here = g.init_dc && g.tr_dc;
+    if (dc_here) {
+        // pandapower init='dc' on a tree: B' theta = P needs no fill, so it is 2 x levels phases of a few scalar
+        // operations here instead of a dense GEMM launch of its own (k_dc_start) plus a round trip of the
+        // angles through HBM; the angles are left in s.t[2k]
+        for (int k = cx.tid; k < n; k += T) s.t[2 * k] = sbus[2 * g.tr_bus_of_int[k]] + g.tr_dc_rhs0[k];
+        cx.sync();
+        for (int l = 0; l < g.n_levels; ++l) {
+            const int le = g.tr_level_ptr[l + 1];
+            for (int k = g.tr_level_ptr[l] + cx.tid; k < le; k += T) {
+                double y = s.t[2 * k];
+                for (int e = g.tr_y_ptr[k] + 1; e < g.tr_y_ptr[k + 1]; ++e) {
+                    const uint32_t ent = g.tr_y_ent[e];
+                    if ((ent >> 16) == 1u) { const int j = (int)(ent & 0xffffu); y = fma(-g.tr_dc_w[j], s.t[2 * j], y); }
+                }
+                s.t[2 * k] = y;
+            }
+            cx.sync();
+        }
+        for (int l = g.n_levels - 1; l >= 0; --l) {
+            const int le = g.tr_level_ptr[l + 1];
+            for (int k = g.tr_level_ptr[l] + cx.tid; k < le; k += T) {
+                const int p = g.tr_parent[k];
+                double x = s.t[2 * k] * g.tr_dc_inv[k];
+                if (p >= 0) x = fma(-g.tr_dc_w[k], s.t[2 * p], x);
+                s.t[2 * k] = x;
+            }
+            cx.sync();
+        }
+    }
 #pragma unroll
     for (int r = 0; r < OWN; ++r) {
         const int i = cx.tid + r * T;
@@ -978,7 +1042,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             const int bus = g.tr_bus_of_int[i];
             const double vm = g.vm_from_state ? vm_out[bus] : g.tr_vm0[i];
             const bool dead = ISL_T && g.isl && vm == 0.0;      // kernel 1 found the bus cut off from every slack
-            const double va = dead ? 0.0 : ((g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i]);   // DC start: the dense pre-pass wrote it
+            const double va = dead ? 0.0 : ((g.init_dc && i < n) ? (dc_here ? s.t[2 * i] : va_out[bus]) : g.tr_va0[i]);   // DC start: above, or the dense pre-pass wrote it
             double sn, cs;
             sincos(va, &sn, &cs);
             vm_own[r] = vm; va_own[r] = va;
@@ -990,7 +1054,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
         const int bus = g.tr_bus_of_int[i];
         const double vm = g.vm_from_state ? vm_out[bus] : g.tr_vm0[i];
         const bool dead = ISL_T && g.isl && vm == 0.0;
-        const double va = dead ? 0.0 : ((g.init_dc && i < n) ? va_out[bus] : g.tr_va0[i]);
+        const double va = dead ? 0.0 : ((g.init_dc && i < n) ? (dc_here ? s.t[2 * i] : va_out[bus]) : g.tr_va0[i]);
         double sn, cs;
         sincos(va, &sn, &cs);
         if (live) { vm_out[bus] = vm; va_out[bus] = va; }
@@ -1459,7 +1523,10 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         bool in_service = true;
         if (bry_env) {
             const int d = g.dyn_of_branch[l];
-            if (d >= 0) { y = bry_env + 8 * (size_t)d; in_service = ref_val(g, S, g.dyn_svc_ref[d]) != 0.0; }
+            if (d >= 0) {                 // out of service (cell or switches): kernel 1 left no admittance at all
+                y = bry_env + 8 * (size_t)d;
+                in_service = !(y[0] == 0.0 && y[1] == 0.0 && y[6] == 0.0 && y[7] == 0.0);
+            }
         }
         const int f = g.br_f[l], t = g.br_t[l];
         const double vfr = s.vr[f], vfi = s.vi[f], vtr = s.vr[t], vti = s.vi[t];
