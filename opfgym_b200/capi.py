@@ -12,6 +12,7 @@ import os
 LIB_NAME = "libopfg_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 N_STATS = 24
+DYN_TAP_LV, DYN_TRAFO = 1, 2      # OpfgDynBranchDesc.flags bits (include/opfg_b200.h)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -20,6 +20,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
+from . import capi as capi_flags
 from . import ppc as P
 from .constraints import Constraint
 from .reward import RewardFunction
@@ -385,30 +386,53 @@ class Compiler:
         dyn = None
         dyn_rows = []
         one, nan = self.consts.ref(1.0), self.consts.ref(np.nan)
-        if lay.has("line", "in_service"):
-            for pos, br in enumerate(ppc.line_branch):
-                if br >= 0:
-                    dyn_rows.append((int(br), nan, 0.0, 0.0, 1.0, self.value_ref("line", "in_service", pos)))
-        if lay.has("trafo", "tap_pos") or lay.has("trafo", "in_service"):
-            tr = net.trafo
-            for pos, br in enumerate(ppc.trafo_branch):
-                if br < 0:
-                    continue
-                k = int(np.nonzero(self.builder.trafo_pos == pos)[0][0])
-                tap = nan
-                if lay.has("trafo", "tap_pos"):
-                    if not self.builder.trafo_tap_on_hv[k]:
-                        raise NotImplementedError("per-environment tap_pos needs an HV-side tap changer")
-                    tap = self.value_ref("trafo", "tap_pos", pos)
-                svc = self.value_ref("trafo", "in_service", pos) if lay.has("trafo", "in_service") else one
-                dyn_rows.append((int(br), tap, float(tr.tap_neutral.iloc[pos]),
-                                 float(tr.tap_step_percent.iloc[pos]),
-                                 float(self.builder.trafo_ratio_neutral[k]), svc))
+        # `switch.closed` cells of line-bus / trafo-bus switches (examples/network_reconfiguration.py:34,
+        # security_constrained.py:31): one reference per branch end; bus-bus switches would change the bus count
+        sw_ends = {}
+        if lay.has("switch", "closed"):
+            sw = net.switch
+            bus_pos = {int(b): i for i, b in enumerate(net.bus.index)}
+            for spos, (et, el, bus) in enumerate(zip(sw.et.to_numpy(object), sw.element.to_numpy(), sw.bus.to_numpy())):
+                if et == "b":
+                    continue           # static (fused by the builder); as an ACTION it is rejected in opf_env
+                table = "line" if et == "l" else "trafo"
+                epos = int(np.nonzero(net[table].index.to_numpy() == int(el))[0][0])
+                first = net[table]["from_bus" if et == "l" else "hv_bus"].iloc[epos]
+                end = 0 if int(bus) == int(first) else 1
+                if (table, epos, end) in sw_ends:
+                    raise NotImplementedError(f"two switches at one end of {table} {el}")
+                sw_ends[table, epos, end] = self.value_ref("switch", "closed", spos)
+        for pos, br in enumerate(ppc.line_branch):
+            has_sw = ("line", pos, 0) in sw_ends or ("line", pos, 1) in sw_ends
+            if br >= 0 and (lay.has("line", "in_service") or has_sw):
+                svc = self.value_ref("line", "in_service", pos) if lay.has("line", "in_service") else one
+                dyn_rows.append((int(br), nan, 0.0, 0.0, 1.0, svc, sw_ends.get(("line", pos, 0), one),
+                                 sw_ends.get(("line", pos, 1), one), 0))
+        tr = net.trafo
+        for pos, br in enumerate(ppc.trafo_branch):
+            has_sw = ("trafo", pos, 0) in sw_ends or ("trafo", pos, 1) in sw_ends
+            if br < 0 or not (lay.has("trafo", "tap_pos") or lay.has("trafo", "in_service") or has_sw):
+                continue
+            k = int(np.nonzero(self.builder.trafo_pos == pos)[0][0])
+            tap, flags = nan, capi_flags.DYN_TRAFO
+            if lay.has("trafo", "tap_pos"):
+                tap = self.value_ref("trafo", "tap_pos", pos)
+                if self.builder.trafo_tap_on_lv[k]:
+                    flags |= capi_flags.DYN_TAP_LV
+                elif not self.builder.trafo_tap_on_hv[k]:
+                    tap = nan          # no tap changer: the cell has no effect (pandapower ignores tap_pos then)
+            svc = self.value_ref("trafo", "in_service", pos) if lay.has("trafo", "in_service") else one
+            dyn_rows.append((int(br), tap, float(tr.tap_neutral.iloc[pos]),
+                             float(tr.tap_step_percent.iloc[pos]),
+                             float(self.builder.trafo_ratio_neutral[k]), svc,
+                             sw_ends.get(("trafo", pos, 0), one), sw_ends.get(("trafo", pos, 1), one), flags))
         if dyn_rows:
             cols = list(zip(*dyn_rows))
             dyn = dict(branch=np.asarray(cols[0], _I32), tap_pos=np.asarray(cols[1], _I32),
                        tap_neutral=np.asarray(cols[2], float), tap_step_percent=np.asarray(cols[3], float),
-                       ratio_neutral=np.asarray(cols[4], float), in_service=np.asarray(cols[5], _I32))
+                       ratio_neutral=np.asarray(cols[4], float), in_service=np.asarray(cols[5], _I32),
+                       closed_from=np.asarray(cols[6], _I32), closed_to=np.asarray(cols[7], _I32),
+                       flags=np.asarray(cols[8], _I32))
 
         rp = reward_function.device_params()
         scoring = dict(
@@ -520,5 +544,7 @@ def fill_descs(capi, program: EnvProgram, tol_pu, max_iter, init_dc, enforce_q_l
         d = program.dyn_branches
         dd = capi.DynBranchDesc(n_dyn=len(d["branch"]), branch=iptr(d["branch"]), tap_pos=iptr(d["tap_pos"]),
                                 tap_neutral=dptr(d["tap_neutral"]), tap_step_percent=dptr(d["tap_step_percent"]),
-                                ratio_neutral=dptr(d["ratio_neutral"]), in_service=iptr(d["in_service"]))
+                                ratio_neutral=dptr(d["ratio_neutral"]), in_service=iptr(d["in_service"]),
+                                closed_from=iptr(d["closed_from"]), closed_to=iptr(d["closed_to"]),
+                                flags=iptr(d["flags"]))
     return gd, ad, sd, dd, keep

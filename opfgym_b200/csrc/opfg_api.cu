@@ -1124,7 +1124,9 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                 d.tr_y_ent = G->tab(col); d.tr_type = G->tab(type_int);
                 // DC start inside the kernel: 1 / d_k and W_k = B'_kp / d_k of the leaf-first factor of B'
                 d.tr_dc = 0; d.tr_dc_inv = d.tr_dc_w = d.tr_dc_rhs0 = d.tr_vm0;
-                const bool dc_in_tree = getenv("OPFG_TREE_DC") ? atoi(getenv("OPFG_TREE_DC")) != 0 : true;
+                // opt-in (OPFG_TREE_DC=1): measured SLOWER on B200 than the GEMM pre-pass -- 36 more dependent phases of
+                // index -> index -> value shared-memory chains cost 110 us per 32 768 environments, the GEMM 83 us
+                const bool dc_in_tree = getenv("OPFG_TREE_DC") ? atoi(getenv("OPFG_TREE_DC")) != 0 : false;
                 if (desc->init_dc && dc_ok && dc_in_tree) {
                     std::vector<double> inv(s.n), w(s.n, 0.0);
                     for (int k = 0; k < s.n; ++k) {

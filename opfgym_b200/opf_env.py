@@ -168,6 +168,15 @@ class BatchedOpfEnv:
         self.rank, self.world_size = int(rank), int(world_size)
         dyn_service = {t for t, c, _ in self.act_keys if c == "in_service" and t in ("line", "trafo")}
         dyn_service |= {t for t, c in dynamic_columns if c == "in_service" and t in ("line", "trafo")}
+        # `switch.closed` as action / contingency cell (examples/network_reconfiguration.py:34): line-bus and
+        # trafo-bus switches only -- a bus-bus switch would change the bus count
+        sw_keys = [(t, c, i) for t, c, i in self.act_keys if (t, c) == ("switch", "closed")]
+        if sw_keys or ("switch", "closed") in [tuple(tc) for tc in dynamic_columns]:
+            dyn_service.add("switch")
+            for _, _, idxs in sw_keys:
+                if (net.switch.et.loc[list(idxs)] == "b").any():
+                    raise NotImplementedError("bus-bus switches as actions change the bus count; only line-bus "
+                                              "and trafo-bus switches can be switched per environment")
         self._builder = PpcBuilder(net, dynamic_service=tuple(sorted(dyn_service)))
         compiler = Compiler(net, self._builder)
         placeholder = reward_mod.Summation()

@@ -105,7 +105,9 @@ class PpcBuilder:
                  trafo_model: str = "t", dynamic_service=()):
         """``dynamic_service``: tables ('line', 'trafo') whose ``in_service`` flag is a
         per-environment cell: their elements stay in the topology (status is applied per
-        environment by kernel 1), so that e.g. normally-open ties can be switched on."""
+        environment by kernel 1), so that e.g. normally-open ties can be switched on.
+        'switch': ``switch.closed`` of line-bus / trafo-bus switches is a per-environment cell;
+        such switches count as closed here (no auxiliary buses), kernel 1 applies them."""
         self.calculate_voltage_angles = calculate_voltage_angles
         self.trafo_model = trafo_model
         self.dynamic_service = tuple(dynamic_service)
@@ -148,7 +150,7 @@ class PpcBuilder:
             l_in[:] = True
         open_f = np.zeros(nl, bool)
         open_t = np.zeros(nl, bool)
-        if len(sw):
+        if len(sw) and "switch" not in self.dynamic_service:
             ls = sw[(sw.et == "l") & ~sw.closed.astype(bool)]
             lpos = {int(l): i for i, l in enumerate(line_index)}
             for b, e in zip(ls.bus.to_numpy(), ls.element.to_numpy()):
@@ -167,7 +169,7 @@ class PpcBuilder:
         t_in = net.trafo.in_service.to_numpy(bool).copy() if nt else np.zeros(0, bool)
         if "trafo" in self.dynamic_service:
             t_in[:] = True
-        if len(sw):
+        if len(sw) and "switch" not in self.dynamic_service:
             ts = sw[(sw.et == "t") & ~sw.closed.astype(bool)]
             tpos = {int(t): i for i, t in enumerate(trafo_index)}
             for e in ts.element.to_numpy():
@@ -296,6 +298,7 @@ class PpcBuilder:
             self.trafo_ratio_neutral = (tr.vn_hv_kv.to_numpy(float) / tr.vn_lv_kv.to_numpy(float)) / \
                 (vn_hv_bus / vn_lv_bus)
             self.trafo_tap_on_hv = on_hv
+            self.trafo_tap_on_lv = on_lv
             shift = tr.shift_degree.to_numpy(float) if self.calculate_voltage_angles else np.zeros(nt)
             par = tr.parallel.to_numpy(float)
             sn_t = tr.sn_mva.to_numpy(float)

@@ -25,9 +25,9 @@ class SecurityConstrainedBatchedOpfEnv(BatchedOpfEnv):
     def __init__(self, *args, n_minus_one_keys, not_converged_penalty: float = 1, **kwargs):
         self.n_minus_one_keys = [(t, c, np.asarray(i)) for t, c, i in n_minus_one_keys]
         for unit_type, column, _ in self.n_minus_one_keys:
-            if column != "in_service" or unit_type not in ("line", "trafo"):
-                raise NotImplementedError("contingencies are line/trafo in_service cells "
-                                          "(switch 'closed' cells change the bus count)")
+            if (unit_type, column) not in (("line", "in_service"), ("trafo", "in_service"), ("switch", "closed")):
+                raise NotImplementedError("contingencies are line/trafo in_service cells or closed cells of "
+                                          "line-bus / trafo-bus switches")
         self.not_converged_penalty = float(not_converged_penalty)
         dyn = list(kwargs.pop("dynamic_columns", ()))
         dyn += [(t, c) for t, c, _ in self.n_minus_one_keys if (t, c) not in dyn]

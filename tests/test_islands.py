@@ -40,7 +40,7 @@ def make_n1_env(n, drop_ties=False, **kw):
     return env, outages
 
 
-def reference_loop(env, outages, b, action):
+def reference_loop(env, outages, b, action, table="line", column="in_service"):
     """security_constrained.py:37-68 on a single pandas net; ``pf.runpp`` rebuilds the ppc, so islands are
     dropped the way pandapower drops them."""
     net = env.net.deepcopy()
@@ -54,7 +54,9 @@ def reference_loop(env, outages, b, action):
     valids, viol, pens = base["valids"].copy(), base["violations"].copy(), base["unscaled_penalties"].copy()
     dropped = []
     for idx in outages:
-        net.line.at[idx, "in_service"] = False
+        if not net[table].at[idx, column]:      # security_constrained.py:46-48
+            continue
+        net[table].at[idx, column] = False
         try:
             pf.runpp(net)
             dropped.append(int(np.isnan(net.res_bus.vm_pu.to_numpy()).sum()))
@@ -66,7 +68,7 @@ def reference_loop(env, outages, b, action):
             valids[:] = False
             viol += env.not_converged_penalty
             pens += env.not_converged_penalty
-        net.line.at[idx, "in_service"] = True
+        net[table].at[idx, column] = True
     reward = scoring.reward(env.reward_function, base["objective"], pens.sum(), bool(valids.all()))
     return valids, viol, pens, reward, dropped
 
@@ -174,3 +176,48 @@ def test_switch_actions_with_islands_hostsim():
 @pytest.mark.gpu
 def test_switch_actions_with_islands_cuda(cuda_lib):
     _check_switch({})
+
+
+# ------------------------------------------------------------------ 'closed' as contingency column
+def _check_switch_contingencies(kw):
+    """security_constrained.py:31 allows column 'closed': switches of line-bus type as N-1 elements."""
+    n = 4
+    net, profiles = grids.build_simbench_net("1-MV-semiurb--1-sw", n_profile_steps=96)
+    net.sgen["controllable"] = net.sgen.max_max_p_mw > np.sort(net.sgen.max_max_p_mw.to_numpy())[-9]
+    net.sgen["min_p_mw"] = 0.0
+    net.sgen["max_p_mw"] = net.sgen.max_max_p_mw
+    for idx in net.sgen.index[net.sgen.controllable]:
+        pn.create_poly_cost(net, idx, "sgen", cp1_eur_per_mw=-0.03)
+    lines = net.line.index[net.line.in_service.to_numpy(bool)]
+    sw = [pn.create_switch(net, int(net.line.from_bus.loc[lines[5]]), int(lines[5]), "l", closed=True),
+          pn.create_switch(net, int(net.line.to_bus.loc[lines[40]]), int(lines[40]), "l", closed=True),
+          pn.create_switch(net, int(net.line.to_bus.loc[lines[70]]), int(lines[70]), "l", closed=False)]
+    obs_keys = [("load", "p_mw", net.load.index), ("sgen", "p_mw", net.sgen.index)]
+    act_keys = [("sgen", "p_mw", net.sgen.index[net.sgen.controllable])]
+    env = SecurityConstrainedBatchedOpfEnv(
+        net, act_keys, obs_keys, profiles=profiles, num_envs=n, train_data="full_uniform",
+        test_data="full_uniform", seed=3, obs_dtype="float64",
+        n_minus_one_keys=[("switch", "closed", np.array(sw))], not_converged_penalty=2.0,
+        reward_function=R.Summation(), **kw)
+    env.reset(seed=7)
+    env._state_before = {(t, c): env.col(t, c).cpu().numpy().copy() for t, c in (("load", "p_mw"), ("sgen", "p_mw"))}
+    act = torch.rand(n, env.single_action_space.shape[0], dtype=torch.float64,
+                     generator=torch.Generator().manual_seed(4))
+    obs, reward, term, trunc, info = env.step(act)
+    assert info["converged"].all()
+    for b in range(n):
+        valids, viol, pens, r, dropped = reference_loop(env, sw, b, act[b].numpy(), "switch", "closed")
+        assert len(dropped) == 2 and min(dropped) >= 1       # the switch that is open already is skipped
+        np.testing.assert_array_equal(info["valids"][b].cpu().numpy(), valids)
+        np.testing.assert_allclose(info["violations"][b].cpu().numpy(), viol, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(info["unscaled_penalties"][b].cpu().numpy(), pens, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(float(reward[b]), r, rtol=1e-7, atol=1e-9)
+
+
+def test_switch_contingencies_hostsim():
+    _check_switch_contingencies(dict(engine_cls=TorchHostSimEngine))
+
+
+@pytest.mark.gpu
+def test_switch_contingencies_cuda(cuda_lib):
+    _check_switch_contingencies({})
