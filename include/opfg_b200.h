@@ -103,7 +103,9 @@ typedef struct {
     int32_t lane_max_row;      /* its largest row pattern (blocks) / warps per CTA / staged tables     */
     int32_t lane_warps_per_cta, lane_tables_staged;
     double lane_scratch_bytes; /* global scratch of the lane kernel (all resident warps)               */
-    int32_t radial_lanes_per_env, radial_envs_per_cta, radial_smem_bytes_per_env, reserved0;
+    int32_t radial_lanes_per_env, radial_envs_per_cta, radial_smem_bytes_per_env;
+    int32_t n_island_critical; /* dynamic branches whose outage can cut buses off (spanning-tree edges): only then
+                                  does opfg_assemble walk the grid of an environment                     */
 } OpfgGridInfo;
 
 /* action application + Sbus scatter (kernel 1) */
@@ -207,7 +209,9 @@ typedef struct {
     const int32_t* flags;           /* host [n_dyn] OPFG_DYN_* bits                                        */
 } OpfgDynBranchDesc;
 enum { OPFG_DYN_TAP_LV = 1,         /* tap changer on the LV side: ratio / t, series impedance * t^2, magnetising branch / t^2 */
-       OPFG_DYN_TRAFO = 2 };        /* transformer: any open switch takes it out of service                 */
+       OPFG_DYN_TRAFO = 2,          /* transformer: any open switch takes it out of service                 */
+       OPFG_DYN_NORMALLY_OPEN = 4 };/* hint: out of service / open in the nominal topology (a tie).  The spanning tree that decides
+                                       which outages can island anything is grown through the other branches first */
 
 /* device buffers of one batch (any pointer may be NULL if the stage that needs it is not run) */
 typedef struct {

@@ -12,7 +12,7 @@ import os
 LIB_NAME = "libopfg_b200.so"
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", LIB_NAME)
 N_STATS = 24
-DYN_TAP_LV, DYN_TRAFO = 1, 2      # OpfgDynBranchDesc.flags bits (include/opfg_b200.h)
+DYN_TAP_LV, DYN_TRAFO, DYN_NORMALLY_OPEN = 1, 2, 4      # OpfgDynBranchDesc.flags bits (include/opfg_b200.h)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -39,7 +39,7 @@ class GridInfo(C.Structure):
                [(n, C.c_int32) for n in ("pf_kernel_used", "lane_max_row", "lane_warps_per_cta",
                                          "lane_tables_staged")] + [("lane_scratch_bytes", C.c_double)] + \
                [(n, C.c_int32) for n in ("radial_lanes_per_env", "radial_envs_per_cta",
-                                         "radial_smem_bytes_per_env", "reserved0")]
+                                         "radial_smem_bytes_per_env", "n_island_critical")]
 
 
 class AssemblyDesc(C.Structure):

@@ -128,6 +128,19 @@ class Compiler:
         v = self.net[table][column].iloc[int(pos)]
         return self.consts.ref(np.nan if v is None else v)
 
+    def _nominally_on(self, table, pos) -> bool:
+        """In service, with every switch at its ends closed, in the net as given (ties are not)."""
+        net = self.net
+        if not bool(net[table].in_service.iloc[pos]):
+            return False
+        sw = net.switch
+        if len(sw):
+            idx = net[table].index[pos]
+            mine = (sw.et == ("l" if table == "line" else "t")) & (sw.element == idx)
+            if (~sw.closed[mine].astype(bool)).any():
+                return False
+        return True
+
     def optional_ref(self, table, column, pos, default) -> int:
         if self.layout.has(table, column) or column in self.net[table].columns:
             return self.value_ref(table, column, pos)
@@ -407,7 +420,8 @@ class Compiler:
             if br >= 0 and (lay.has("line", "in_service") or has_sw):
                 svc = self.value_ref("line", "in_service", pos) if lay.has("line", "in_service") else one
                 dyn_rows.append((int(br), nan, 0.0, 0.0, 1.0, svc, sw_ends.get(("line", pos, 0), one),
-                                 sw_ends.get(("line", pos, 1), one), 0))
+                                 sw_ends.get(("line", pos, 1), one),
+                                 0 if self._nominally_on("line", pos) else capi_flags.DYN_NORMALLY_OPEN))
         tr = net.trafo
         for pos, br in enumerate(ppc.trafo_branch):
             has_sw = ("trafo", pos, 0) in sw_ends or ("trafo", pos, 1) in sw_ends
@@ -415,6 +429,8 @@ class Compiler:
                 continue
             k = int(np.nonzero(self.builder.trafo_pos == pos)[0][0])
             tap, flags = nan, capi_flags.DYN_TRAFO
+            if not self._nominally_on("trafo", pos):
+                flags |= capi_flags.DYN_NORMALLY_OPEN
             if lay.has("trafo", "tap_pos"):
                 tap = self.value_ref("trafo", "tap_pos", pos)
                 if self.builder.trafo_tap_on_lv[k]:

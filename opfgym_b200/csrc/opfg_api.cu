@@ -90,6 +90,7 @@ struct OpfgGrid {
     std::vector<int> br_f_host, br_t_host, type_host;     // ppc branch ends / bus types (island analysis)
     std::vector<unsigned char> br_on_host;                // static branch status
     std::vector<double> br_tap_host;                      // static off-nominal ratio
+    int n_crit = 0;                                       // dynamic branches on the spanning tree (island analysis)
     int n_result_cells = 0;
     double flops_score = 0;
     bool has_assembly = false, has_scoring = false;
@@ -631,7 +632,7 @@ __global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E,
 // each (32 / T environments share a warp and run in lockstep), tables staged once per CTA.
 #define OPFG_TREE_TABLES(X) X(tr_bus_of_int) X(tr_level_ptr) X(tr_y_ptr) X(tr_parent) X(tr_type) X(tr_y_ent) X(tr_y_val) X(tr_vm0) X(tr_va0) \
     X(tr_dc_inv) X(tr_dc_w) X(tr_dc_rhs0)
-template <int T, bool DYN, int MAX_THREADS = (T == 32 ? 768 : T * 32)>
+template <int T, bool DYN, int MAX_THREADS = (T == 32 ? 768 : T * 32), int LOOP = 0>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_pf_tree(GridDev g, OpfgBatch B, int E, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
     {
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_pf_tree(GridDev g, OpfgBatch
         int64_t env = base + grp;
         const bool live = env < hi;
         if (!live) env = hi - 1;               // an idle group shadows its warp's last environment (no stores)
-        env_pf_tree<Grp<T>, DYN>(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
+        env_pf_tree<Grp<T>, DYN, LOOP>(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
                     DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
                     B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env, live);
         __syncwarp();
@@ -1358,7 +1359,7 @@ int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
         // cell first: a dynamic branch that still becomes a tree edge is "critical" -- only when one of those
         // is out can an environment lose buses, and only then does kernel 1 walk the grid (open ties that
         // merely close loops never trigger the walk).
-        d.isl = 0; d.dyn_crit = nullptr; d.isl_ptr = d.isl_adj = d.isl_br = nullptr;
+        d.isl = 0; d.dyn_crit = nullptr; d.isl_ptr = d.isl_adj = d.isl_br = nullptr; G->n_crit = 0;
         bool any_switchable = false;
         std::vector<unsigned char> switchable(d.nbr, 0);
         for (int i = 0; i < dd->n_dyn; ++i) {
@@ -1380,7 +1381,11 @@ int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
             for (int b = 0; b < nb; ++b) ptr[b + 1] += ptr[b];
             adj.resize(ptr[nb]); brs.resize(ptr[nb]);
             std::vector<int> fillp(ptr.begin(), ptr.end() - 1);
-            for (int pass = 0; pass < 2; ++pass)          // fixed branches first: the walk meets them first, too
+            // switchable[l]: 1 = normally in service, 2 = normally open (hint): the forest grows through the former first,
+            // so that ties which merely close loops do not become "critical"
+            for (int i = 0; i < dd->n_dyn; ++i)
+                if (switchable[dd->branch[i]] && (flags[i] & OPFG_DYN_NORMALLY_OPEN)) switchable[dd->branch[i]] = 2;
+            for (int pass = 0; pass < 3; ++pass)          // fixed branches first: the walk meets them first, too
                 for (int l = 0; l < nbr; ++l) {
                     if (!G->br_on_host[l] || G->br_f_host[l] == G->br_t_host[l] || (int)switchable[l] != pass) continue;
                     const int f = G->br_f_host[l], t = G->br_t_host[l];
@@ -1400,18 +1405,19 @@ int opfg_set_dynamic_branches(OpfgGrid* G, const OpfgDynBranchDesc* dd) {
                         if (!switchable[brs[e]] && !seen[adj[e]]) { seen[adj[e]] = 1; queue.push_back(adj[e]); }
                 }
                 bool grown = false;                        // one switchable edge out of the reached set, then go on
-                for (size_t q = 0; q < queue.size() && !grown; ++q) {
-                    const int a = queue[q];
-                    for (int e = ptr[a]; e < ptr[a + 1] && !grown; ++e)
-                        if (switchable[brs[e]] && !seen[adj[e]]) {
-                            seen[adj[e]] = 1; queue.push_back(adj[e]);
-                            crit[of[brs[e]]] = 1; grown = true;
-                        }
-                }
+                for (int kind = 1; kind <= 2 && !grown; ++kind)
+                    for (size_t q = 0; q < queue.size() && !grown; ++q) {
+                        const int a = queue[q];
+                        for (int e = ptr[a]; e < ptr[a + 1] && !grown; ++e)
+                            if (switchable[brs[e]] == kind && !seen[adj[e]]) {
+                                seen[adj[e]] = 1; queue.push_back(adj[e]);
+                                crit[of[brs[e]]] = 1; grown = true;
+                            }
+                    }
                 if (!grown) break;
             }
             bool any_crit = false;
-            for (unsigned char c : crit) any_crit |= c != 0;
+            for (unsigned char c : crit) { any_crit |= c != 0; G->n_crit += c != 0; }
             if (any_crit) {
                 d.dyn_crit = G->up(crit); d.isl_ptr = G->up(ptr); d.isl_adj = G->up(adj); d.isl_br = G->up(brs);
                 d.isl = 1;
@@ -1536,6 +1542,7 @@ int opfg_grid_info(const OpfgGrid* G, OpfgGridInfo* o) {
         o->pf_kernel_used = use_tree(G, &none) ? 3 : (use_lanes(G, &none) ? 2 : 1);
         o->radial_lanes_per_env = G->tree_T; o->radial_envs_per_cta = G->tree_E;
         o->radial_smem_bytes_per_env = (int)(G->tree_env_doubles * 8);
+        o->n_island_critical = G->n_crit;
         o->lane_max_row = d.ln_max_row; o->lane_warps_per_cta = G->lane_warps_per_cta; o->lane_tables_staged = G->lane_stage;
         o->lane_scratch_bytes = 8.0 * (double)G->lane_warp_doubles * std::max(1, G->lane_warps_per_cta * G->lane_ctas);
     }
@@ -1717,9 +1724,10 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         OpfgGrid* Gm = const_cast<OpfgGrid*>(G);
         const bool dyn = G->d.n_dyn > 0 && B->yval;
         // the last two: 16 lanes x at most 24 environments with the register cap of 384 threads (155 instead of 128)
-        void (*fns[8])(GridDev, OpfgBatch, int, int) = {k_pf_tree<8, false>, k_pf_tree<16, false>, k_pf_tree<32, false>,
-                                                        k_pf_tree<8, true>, k_pf_tree<16, true>, k_pf_tree<32, true>,
-                                                        k_pf_tree<16, false, 384>, k_pf_tree<16, true, 384>};
+        void (*fns[10])(GridDev, OpfgBatch, int, int) = {k_pf_tree<8, false>, k_pf_tree<16, false>, k_pf_tree<32, false>,
+                                                         k_pf_tree<8, true>, k_pf_tree<16, true>, k_pf_tree<32, true>,
+                                                         k_pf_tree<16, false, 384>, k_pf_tree<16, true, 384>,
+                                                         k_pf_tree<16, false, 384, 1>, k_pf_tree<16, true, 384, 1>};
         if (!Gm->tree_attr_set) {      // per grid, hence per device
             for (auto* f : fns) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             Gm->tree_attr_set = true;
@@ -1731,7 +1739,8 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         // measured on B200 (122-bus grid, 32 768 environments): 0.80 instead of 0.90 ms -- under the 128-register cap
         // the staged-table base addresses were recomputed at their use sites
         static const bool wide_regs = getenv("OPFG_TREE_WIDE_REGS") ? atoi(getenv("OPFG_TREE_WIDE_REGS")) != 0 : true;
-        if (wide_regs && T == 16 && E <= 24) fn = fns[dyn ? 7 : 6];
+        static const int loop_form = getenv("OPFG_TREE_LOOP") ? atoi(getenv("OPFG_TREE_LOOP")) : 0;
+        if (wide_regs && T == 16 && E <= 24) fn = fns[(dyn ? 7 : 6) + (loop_form == 1 ? 2 : 0)];
         fn<<<grid, T * E, G->tree_smem, (cudaStream_t)stream>>>(tree_view(G->d), *B, E, (int)G->tree_env_doubles);
         ++g_launches;
         cudaError_t e = cudaGetLastError();

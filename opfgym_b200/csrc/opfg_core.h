@@ -943,7 +943,7 @@ OPFG_HD void tree_entry(const TreeSmem& s, TreeAcc& a, uint32_t ent, D2 y, D2 vj
     }
 }
 
-template <bool JAC, bool ISL = false>
+template <bool JAC, bool ISL = false, int LOOP = 0>
 OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D2 sp, int k) {
     const D2 vk = ld2(s.vri + 2 * k);
     const bool dead = ISL && vk.x == 0.0 && vk.y == 0.0;      // cut off from every slack (kernel 1): V stays 0
@@ -957,16 +957,32 @@ OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D
         a.ir = dr; a.ii = di;
     }
     int e = e0 + 1;
-    for (; e + 1 < e1; e += 2) {                              // two entries per trip: their loads overlap
-        const uint32_t ea = g.tr_y_ent[e], eb = g.tr_y_ent[e + 1];
-        const D2 ya = ld2(yv + 2 * e), yb = ld2(yv + 2 * e + 2);
-        const D2 va = ld2(s.vri + 2 * (ea & 0xffffu)), vb = ld2(s.vri + 2 * (eb & 0xffffu));
-        tree_entry<JAC>(s, a, ea, ya, va, vk, pq);
-        tree_entry<JAC>(s, a, eb, yb, vb, vk, pq);
-    }
-    if (e < e1) {
-        const uint32_t ea = g.tr_y_ent[e];
-        tree_entry<JAC>(s, a, ea, ld2(yv + 2 * e), ld2(s.vri + 2 * (ea & 0xffffu)), vk, pq);
+    if (LOOP == 1) {
+        // ONE entry per trip, the next entry's operands requested before this one is worked on: a single copy of
+        // the child / parent code for the whole warp (the two-entries form below runs up to three copies of it
+        // per level when the lanes' rows differ in length)
+        uint32_t en = 0;
+        D2 yn{0, 0}, vn{0, 0};
+        if (e < e1) { en = g.tr_y_ent[e]; yn = ld2(yv + 2 * e); vn = ld2(s.vri + 2 * (en & 0xffffu)); }
+        while (e < e1) {
+            const uint32_t ec = en;
+            const D2 yc = yn, vc = vn;
+            ++e;
+            if (e < e1) { en = g.tr_y_ent[e]; yn = ld2(yv + 2 * e); vn = ld2(s.vri + 2 * (en & 0xffffu)); }
+            tree_entry<JAC>(s, a, ec, yc, vc, vk, pq);
+        }
+    } else {
+        for (; e + 1 < e1; e += 2) {                          // two entries per trip: their loads overlap
+            const uint32_t ea = g.tr_y_ent[e], eb = g.tr_y_ent[e + 1];
+            const D2 ya = ld2(yv + 2 * e), yb = ld2(yv + 2 * e + 2);
+            const D2 va = ld2(s.vri + 2 * (ea & 0xffffu)), vb = ld2(s.vri + 2 * (eb & 0xffffu));
+            tree_entry<JAC>(s, a, ea, ya, va, vk, pq);
+            tree_entry<JAC>(s, a, eb, yb, vb, vk, pq);
+        }
+        if (e < e1) {
+            const uint32_t ea = g.tr_y_ent[e];
+            tree_entry<JAC>(s, a, ea, ld2(yv + 2 * e), ld2(s.vri + 2 * (ea & 0xffffu)), vk, pq);
+        }
     }
     const double P = fma(vk.x, a.ir, vk.y * a.ii), Q = fma(vk.y, a.ir, -(vk.x * a.ii));   // S_k = V_k conj(I_k)
     const double dp = dead ? 0.0 : P - sp.x, dq = (pq && !dead) ? Q - sp.y : 0.0;
@@ -992,7 +1008,7 @@ OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D
     return res;
 }
 
-template <class C, bool ISL_T = false>
+template <class C, bool ISL_T = false, int LOOP = 0>
 OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const double* sbus, const double* yval_env,
                          double* vm_out, double* va_out, uint8_t* conv_out, int32_t* iter_out, bool live) {
     const int T = cx.nthreads();
@@ -1071,7 +1087,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             double part = 0;
             bool bad = false;
             for (int k = cx.tid; k < n; k += T) {
-                const double r = tree_row<false, ISL_T>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
+                const double r = tree_row<false, ISL_T, LOOP>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
                 if (r != r) bad = true; else if (r > part) part = r;
             }
             const double nrm = cx.group_max(bad ? NAN : part);
@@ -1097,10 +1113,10 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             }
             int k = g.tr_level_ptr[l] + cx.tid;
             if (k < le) {
-                double r = tree_row<true, ISL_T>(g, s, yv, sp0, k);
+                double r = tree_row<true, ISL_T, LOOP>(g, s, yv, sp0, k);
                 if (r != r) bad = true; else if (r > part) part = r;
                 for (k += T; k < le; k += T) {                // levels wider than the group (unbalanced schedule)
-                    r = tree_row<true, ISL_T>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
+                    r = tree_row<true, ISL_T, LOOP>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
                     if (r != r) bad = true; else if (r > part) part = r;
                 }
             }
