@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E,
 // each (32 / T environments share a warp and run in lockstep), tables staged once per CTA.
 #define OPFG_TREE_TABLES(X) X(tr_bus_of_int) X(tr_level_ptr) X(tr_y_ptr) X(tr_parent) X(tr_type) X(tr_y_ent) X(tr_y_val) X(tr_vm0) X(tr_va0) \
     X(tr_dc_inv) X(tr_dc_w) X(tr_dc_rhs0)
-template <int T, bool DYN, int MAX_THREADS = (T == 32 ? 768 : T * 32), int LOOP = 0>
+template <int T, bool DYN, int MAX_THREADS = (T == 32 ? 768 : T * 32)>
 __global__ void __launch_bounds__(MAX_THREADS, 1) k_pf_tree(GridDev g, OpfgBatch B, int E, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
     {
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_pf_tree(GridDev g, OpfgBatch
         int64_t env = base + grp;
         const bool live = env < hi;
         if (!live) env = hi - 1;               // an idle group shadows its warp's last environment (no stores)
-        env_pf_tree<Grp<T>, DYN, LOOP>(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
+        env_pf_tree<Grp<T>, DYN>(g, cx, mine, B.sbus + env * (int64_t)g.nb * 2,
                     DYN ? B.yval + env * (int64_t)g.nnz_y * 2 : (const double*)nullptr,
                     B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env, live);
         __syncwarp();
@@ -1256,6 +1256,10 @@ int opfg_set_assembly(OpfgGrid* G, const OpfgAssemblyDesc* a) {
         d.act_diff_step = a->act_diff_step;
         d.consts = G->up(a->consts, a->n_const);
         G->consts_host.assign(a->consts, a->consts + a->n_const);
+        {
+            std::vector<double> rev(G->consts_host.rbegin(), G->consts_host.rend());
+            d.consts_end = G->up(rev) + a->n_const;
+        }
         auto check_ref = [&](const int* r, int n, const char* what) {
             for (int i = 0; i < n; ++i)
                 if (r[i] >= a->n_state || -r[i] - 1 >= a->n_const) throw std::runtime_error(std::string("reference out of range in ") + what);
@@ -1724,10 +1728,9 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         OpfgGrid* Gm = const_cast<OpfgGrid*>(G);
         const bool dyn = G->d.n_dyn > 0 && B->yval;
         // the last two: 16 lanes x at most 24 environments with the register cap of 384 threads (155 instead of 128)
-        void (*fns[10])(GridDev, OpfgBatch, int, int) = {k_pf_tree<8, false>, k_pf_tree<16, false>, k_pf_tree<32, false>,
-                                                         k_pf_tree<8, true>, k_pf_tree<16, true>, k_pf_tree<32, true>,
-                                                         k_pf_tree<16, false, 384>, k_pf_tree<16, true, 384>,
-                                                         k_pf_tree<16, false, 384, 1>, k_pf_tree<16, true, 384, 1>};
+        void (*fns[8])(GridDev, OpfgBatch, int, int) = {k_pf_tree<8, false>, k_pf_tree<16, false>, k_pf_tree<32, false>,
+                                                        k_pf_tree<8, true>, k_pf_tree<16, true>, k_pf_tree<32, true>,
+                                                        k_pf_tree<16, false, 384>, k_pf_tree<16, true, 384>};
         if (!Gm->tree_attr_set) {      // per grid, hence per device
             for (auto* f : fns) cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             Gm->tree_attr_set = true;
@@ -1739,8 +1742,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         // measured on B200 (122-bus grid, 32 768 environments): 0.80 instead of 0.90 ms -- under the 128-register cap
         // the staged-table base addresses were recomputed at their use sites
         static const bool wide_regs = getenv("OPFG_TREE_WIDE_REGS") ? atoi(getenv("OPFG_TREE_WIDE_REGS")) != 0 : true;
-        static const int loop_form = getenv("OPFG_TREE_LOOP") ? atoi(getenv("OPFG_TREE_LOOP")) : 0;
-        if (wide_regs && T == 16 && E <= 24) fn = fns[(dyn ? 7 : 6) + (loop_form == 1 ? 2 : 0)];
+        if (wide_regs && T == 16 && E <= 24) fn = fns[dyn ? 7 : 6];
         fn<<<grid, T * E, G->tree_smem, (cudaStream_t)stream>>>(tree_view(G->d), *B, E, (int)G->tree_env_doubles);
         ++g_launches;
         cudaError_t e = cudaGetLastError();

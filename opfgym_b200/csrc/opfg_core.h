@@ -96,6 +96,7 @@ struct GridDev {
     int n_state, n_const, n_act, n_inj;
     double act_diff_step;
     const double* consts;
+    const double* consts_end;          // one past a back-to-front copy of the constants: consts_end[r] = consts[-r-1], r < 0
     const int* act_slot;
     const int *act_lo, *act_hi, *act_div, *act_kind, *act_clamp_lo, *act_clamp_hi;
     const int* inj_ptr;                // [nb+1] CSR by ppc bus
@@ -260,8 +261,10 @@ struct Ctx {
 // value of a reference: state cell (r >= 0) or constant (r < 0); one load behind a selected
 // address, so lanes holding different kinds of reference do not diverge
 OPFG_HD double ref_val(const GridDev& g, const double* S, int r) {
-    const double* p = r >= 0 ? S + r : g.consts + (-r - 1);
-    return *p;
+    // constants are ALSO stored back to front, ending at consts_end: C[-r-1] == consts_end[r].  Only the base
+    // depends on the kind of reference then, the index is r itself (two instructions fewer per reference)
+    const double* base = r >= 0 ? S : g.consts_end;
+    return base[r];
 }
 
 constexpr int OPFG_NO_REF = -2147483647 - 1;
@@ -318,7 +321,13 @@ OPFG_HD void gather_obs(const GridDev& g, const C& cx, const double* S, const Op
         // whole columns of the state row: coalesced copies, no reference loads in front of the data loads
         for (int r = 0; r < g.n_obs_runs; ++r) {
             const int src = g.obs_runs[3 * r], dst = g.obs_runs[3 * r + 1], len = g.obs_runs[3 * r + 2];
-            for (int k = cx.tid; k < len; k += T) {
+            int k = cx.tid;
+            for (; k + 3 * T < len; k += 4 * T) {          // four loads in flight per lane (the row comes from DRAM)
+                const double v0 = S[src + k], v1 = S[src + k + T], v2 = S[src + k + 2 * T], v3 = S[src + k + 3 * T];
+                if (o32) { o32[dst + k] = (float)v0; o32[dst + k + T] = (float)v1; o32[dst + k + 2 * T] = (float)v2; o32[dst + k + 3 * T] = (float)v3; }
+                if (o64) { o64[dst + k] = v0; o64[dst + k + T] = v1; o64[dst + k + 2 * T] = v2; o64[dst + k + 3 * T] = v3; }
+            }
+            for (; k < len; k += T) {
                 const double v = S[src + k];
                 if (o32) o32[dst + k] = (float)v;
                 if (o64) o64[dst + k] = v;
@@ -943,7 +952,7 @@ OPFG_HD void tree_entry(const TreeSmem& s, TreeAcc& a, uint32_t ent, D2 y, D2 vj
     }
 }
 
-template <bool JAC, bool ISL = false, int LOOP = 0>
+template <bool JAC, bool ISL = false>
 OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D2 sp, int k) {
     const D2 vk = ld2(s.vri + 2 * k);
     const bool dead = ISL && vk.x == 0.0 && vk.y == 0.0;      // cut off from every slack (kernel 1): V stays 0
@@ -957,32 +966,18 @@ OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D
         a.ir = dr; a.ii = di;
     }
     int e = e0 + 1;
-    if (LOOP == 1) {
-        // ONE entry per trip, the next entry's operands requested before this one is worked on: a single copy of
-        // the child / parent code for the whole warp (the two-entries form below runs up to three copies of it
-        // per level when the lanes' rows differ in length)
-        uint32_t en = 0;
-        D2 yn{0, 0}, vn{0, 0};
-        if (e < e1) { en = g.tr_y_ent[e]; yn = ld2(yv + 2 * e); vn = ld2(s.vri + 2 * (en & 0xffffu)); }
-        while (e < e1) {
-            const uint32_t ec = en;
-            const D2 yc = yn, vc = vn;
-            ++e;
-            if (e < e1) { en = g.tr_y_ent[e]; yn = ld2(yv + 2 * e); vn = ld2(s.vri + 2 * (en & 0xffffu)); }
-            tree_entry<JAC>(s, a, ec, yc, vc, vk, pq);
-        }
-    } else {
-        for (; e + 1 < e1; e += 2) {                          // two entries per trip: their loads overlap
-            const uint32_t ea = g.tr_y_ent[e], eb = g.tr_y_ent[e + 1];
-            const D2 ya = ld2(yv + 2 * e), yb = ld2(yv + 2 * e + 2);
-            const D2 va = ld2(s.vri + 2 * (ea & 0xffffu)), vb = ld2(s.vri + 2 * (eb & 0xffffu));
-            tree_entry<JAC>(s, a, ea, ya, va, vk, pq);
-            tree_entry<JAC>(s, a, eb, yb, vb, vk, pq);
-        }
-        if (e < e1) {
-            const uint32_t ea = g.tr_y_ent[e];
-            tree_entry<JAC>(s, a, ea, ld2(yv + 2 * e), ld2(s.vri + 2 * (ea & 0xffffu)), vk, pq);
-        }
+    // two entries per trip: their loads overlap.  (Measured alternative: ONE entry per trip with the next entry's
+    // operands requested a trip ahead -- a single copy of the child / parent code per warp -- is 4 % slower.)
+    for (; e + 1 < e1; e += 2) {
+        const uint32_t ea = g.tr_y_ent[e], eb = g.tr_y_ent[e + 1];
+        const D2 ya = ld2(yv + 2 * e), yb = ld2(yv + 2 * e + 2);
+        const D2 va = ld2(s.vri + 2 * (ea & 0xffffu)), vb = ld2(s.vri + 2 * (eb & 0xffffu));
+        tree_entry<JAC>(s, a, ea, ya, va, vk, pq);
+        tree_entry<JAC>(s, a, eb, yb, vb, vk, pq);
+    }
+    if (e < e1) {
+        const uint32_t ea = g.tr_y_ent[e];
+        tree_entry<JAC>(s, a, ea, ld2(yv + 2 * e), ld2(s.vri + 2 * (ea & 0xffffu)), vk, pq);
     }
     const double P = fma(vk.x, a.ir, vk.y * a.ii), Q = fma(vk.y, a.ir, -(vk.x * a.ii));   // S_k = V_k conj(I_k)
     const double dp = dead ? 0.0 : P - sp.x, dq = (pq && !dead) ? Q - sp.y : 0.0;
@@ -1008,7 +1003,7 @@ OPFG_HD double tree_row(const GridDev& g, const TreeSmem& s, const double* yv, D
     return res;
 }
 
-template <class C, bool ISL_T = false, int LOOP = 0>
+template <class C, bool ISL_T = false>
 OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const double* sbus, const double* yval_env,
                          double* vm_out, double* va_out, uint8_t* conv_out, int32_t* iter_out, bool live) {
     const int T = cx.nthreads();
@@ -1087,7 +1082,7 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             double part = 0;
             bool bad = false;
             for (int k = cx.tid; k < n; k += T) {
-                const double r = tree_row<false, ISL_T, LOOP>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
+                const double r = tree_row<false, ISL_T>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
                 if (r != r) bad = true; else if (r > part) part = r;
             }
             const double nrm = cx.group_max(bad ? NAN : part);
@@ -1113,10 +1108,10 @@ OPFG_HD void env_pf_tree(const GridDev& g, const C& cx, double* smem, const doub
             }
             int k = g.tr_level_ptr[l] + cx.tid;
             if (k < le) {
-                double r = tree_row<true, ISL_T, LOOP>(g, s, yv, sp0, k);
+                double r = tree_row<true, ISL_T>(g, s, yv, sp0, k);
                 if (r != r) bad = true; else if (r > part) part = r;
                 for (k += T; k < le; k += T) {                // levels wider than the group (unbalanced schedule)
-                    r = tree_row<true, ISL_T, LOOP>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
+                    r = tree_row<true, ISL_T>(g, s, yv, ldg2(sbus + 2 * g.tr_bus_of_int[k]), k);
                     if (r != r) bad = true; else if (r > part) part = r;
                 }
             }
