@@ -89,10 +89,13 @@ def _check(kw):
     assert (info["violations"] > 0).any()       # the contingencies do bite (max_loading=30)
 
 
-def test_n_minus_one_hostsim():
-    _check(dict(engine_cls=TorchHostSimEngine))
+@pytest.mark.parametrize("batched", [True, False])
+def test_n_minus_one_hostsim(batched):
+    """batched: all (environment, contingency) pairs as ONE batch of rows; else one pass per contingency."""
+    _check(dict(engine_cls=TorchHostSimEngine, batch_contingencies=batched))
 
 
 @pytest.mark.gpu
-def test_n_minus_one_cuda(cuda_lib):
-    _check({})
+@pytest.mark.parametrize("batched", [True, False])
+def test_n_minus_one_cuda(cuda_lib, batched):
+    _check(dict(batch_contingencies=batched))
