@@ -46,6 +46,8 @@ class PowerFlowSolver:
         results = [(t, c) for t, c in _RESULTS if len(net[t[4:]]) or t == "res_bus"]
         self.program = comp.compile(act_keys=[], obs_keys=[], state_keys=inputs, constraints=[],
                                     reward_function=reward_mod.Summation(), extra_results=results)
+        from .engine import check_engine_class
+        check_engine_class(engine_cls)
         self.engine = engine_cls(self.program, 1, device=device, tolerance_mva=tolerance_mva,
                                  max_iteration=max_iteration, obs_dtype="float64", **engine_kwargs)
         self.inputs = inputs

@@ -26,6 +26,15 @@ class ResetPlan:
             pass
 
 
+def check_engine_class(engine_cls):
+    """``engine_cls=`` is a TEST seam (the CPU tier builds the same kernel sources with g++ to check schedules
+    and marshalling without a GPU).  The product has one engine: anything else must mark itself as test
+    infrastructure, so that a CPU engine cannot slip into a product path unnoticed."""
+    if engine_cls is not Engine and not getattr(engine_cls, "OPFG_TEST_ENGINE", False):
+        raise TypeError("engine_cls is a test seam: only opfgym_b200.engine.Engine (CUDA) or a class that sets "
+                        "OPFG_TEST_ENGINE = True (tests/hostsim) is accepted")
+
+
 class Engine:
     STATS_SLOTS = 128
     def __init__(self, program: EnvProgram, num_envs: int, device=None,

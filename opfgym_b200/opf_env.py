@@ -193,6 +193,8 @@ class BatchedOpfEnv:
         self._engine_args = dict(device=device, tolerance_mva=tolerance_mva,
                                  max_iteration=max_iteration, obs_dtype=obs_dtype,
                                  **(engine_kwargs or {}))
+        from .engine import check_engine_class
+        check_engine_class(engine_cls)
         self._engine_cls = engine_cls
         self.program = compiler.compile(reward_function=placeholder, **self._compile_args)
         self.pruned_columns = {tuple(tc) for tc in dynamic if not self.program.layout.has(*tc)}

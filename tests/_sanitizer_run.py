@@ -40,4 +40,19 @@ env.reset(seed=4)
 env.step(torch.rand(33, 14, device="cuda", dtype=torch.float64))
 torch.cuda.synchronize()
 env.close()
+# islands (kernel 1's connectivity walk, dropped buses in both power-flow kernels), switch cells with half-open
+# lines and LV-side taps, N-1 with all contingencies as one batch
+from tests import test_islands, test_switch_cells
+for drop_ties in (True, False):
+    env, _ = test_islands.make_n1_env(6, drop_ties=drop_ties)
+    env.reset(seed=5)
+    out = env.step(torch.rand(6, env.single_action_space.shape[0], device="cuda", dtype=torch.float64))
+    assert out[4]["converged"].all()
+    env.close()
+env, sw = test_switch_cells.make_env(16, "lv")
+env.reset(seed=6)
+out = env.step(torch.rand(16, env.single_action_space.shape[0], device="cuda", dtype=torch.float64))
+torch.cuda.synchronize()
+assert torch.isnan(env.engine.vm).any() and out[4]["converged"].all()
+env.close()
 print("sanitizer run ok")

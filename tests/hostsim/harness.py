@@ -41,6 +41,7 @@ def load():
 
 class HostSimEngine(Engine):
     """Engine plumbing on numpy arrays + the host-sim library (tests only)."""
+    OPFG_TEST_ENGINE = True      # accepted by the env layer's engine_cls= test seam
 
     def __init__(self, program, num_envs, **kw):
         super().__init__(program, num_envs, lib=load(), **kw)
@@ -62,6 +63,7 @@ class HostSimEngine(Engine):
 
 
 class TorchHostSimEngine(Engine):
+    OPFG_TEST_ENGINE = True
     """Engine plumbing on torch CPU tensors + the host-sim library, so that the
     env layer (``BatchedOpfEnv`` and its tensor-op hooks) can be unit-tested on
     the GPU-less builder box.  Tests only."""

@@ -556,3 +556,17 @@ def test_tensor_objective_module_equals_kernel_objective(cls):
     base = make(cls, n=5)
     base.reset(seed=6)
     torch.testing.assert_close(plug.step(act)[1], base.step(act)[1], rtol=1e-10, atol=1e-12)
+
+
+def test_engine_cls_is_a_gated_test_seam():
+    """A CPU engine cannot be injected into the product path unnoticed (round-1 review): `engine_cls=` only
+    accepts the CUDA engine or classes that mark themselves as test infrastructure."""
+    from opfgym_b200.engine import Engine, check_engine_class
+
+    class Sneaky(Engine):
+        pass
+
+    with pytest.raises(TypeError):
+        check_engine_class(Sneaky)
+    check_engine_class(Engine)
+    check_engine_class(TorchHostSimEngine)
