@@ -598,8 +598,10 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // the 96-register cap and cost 10 % of the kernel's instructions.
 // MODE = STAGE | (4 if the Ybus values are per environment): with the shared table the compiler
 // knows the values live in shared memory (LDS instead of generic loads in the row pass).
-template <int T, int MODE>
-__global__ void __launch_bounds__(768) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
+// BOUND: the largest block this instantiation is launched with (T x environments per CTA): 768 caps the kernel at
+// 85 registers (it spills there), so launches of at most 512 / 256 threads get their own, roomier build
+template <int T, int MODE, int BOUND = 768>
+__global__ void __launch_bounds__(BOUND, 1) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
     constexpr int STAGE = MODE & 3;
     constexpr bool DYN = (MODE & 4) != 0;
     extern __shared__ __align__(16) double sm[];
@@ -661,6 +663,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_pf_tree(GridDev g, OpfgBatch
                     B.vm + env * (int64_t)g.nb, B.va + env * (int64_t)g.nb, B.converged + env, B.iterations + env, live);
         __syncwarp();
     }
+}
+template <int T, int MODE>
+static void (*pick_multi(int bound))(GridDev, OpfgBatch, int, int) {
+    return bound == 256 ? k_pf_multi<T, MODE, 256> : (bound == 512 ? k_pf_multi<T, MODE, 512> : k_pf_multi<T, MODE, 768>);
 }
 static GridDev tree_view(const GridDev& d) {
     GridDev view = d;
@@ -1800,14 +1806,17 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             const GridDev view = staged_view(G->d, stage);
             const int env_doubles = (int)(smem / 8);
             void (*fn)(GridDev, OpfgBatch, int, int) = nullptr;
+            static const bool roomy = getenv("OPFG_MULTI_ROOMY") ? atoi(getenv("OPFG_MULTI_ROOMY")) != 0 : true;
+            const int bound = !roomy ? 768 : (TT * E <= 256 ? 256 : (TT * E <= 512 ? 512 : 768));
             switch (stage | ((G->d.n_dyn > 0 && B->yval) ? 4 : 0)) {
-                case 0: fn = k_pf_multi<TT, 0>; break;
-                case 1: fn = k_pf_multi<TT, 1>; break;
-                case 2: fn = k_pf_multi<TT, 2>; break;
-                case 4: fn = k_pf_multi<TT, 4>; break;
-                case 5: fn = k_pf_multi<TT, 5>; break;
-                default: fn = k_pf_multi<TT, 6>; break;
+                case 0: fn = pick_multi<TT, 0>(bound); break;
+                case 1: fn = pick_multi<TT, 1>(bound); break;
+                case 2: fn = pick_multi<TT, 2>(bound); break;
+                case 4: fn = pick_multi<TT, 4>(bound); break;
+                case 5: fn = pick_multi<TT, 5>(bound); break;
+                default: fn = pick_multi<TT, 6>(bound); break;
             }
+            if (bound != 768) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
             fn<<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
         } else {
             k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
