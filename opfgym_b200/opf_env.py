@@ -76,7 +76,7 @@ class BatchedOpfEnv:
                  max_iteration: int = 10, engine_cls=Engine, engine_kwargs: dict | None = None,
                  copy_outputs: bool = True, validate_actions: bool = False, host_obs_dtype: str | None = None,
                  prefetch_reset: bool = True, keep_all_columns: bool = False,
-                 fused_reset: bool | None = None, **kwargs):
+                 fused_reset: bool | None = None, max_reset_resamples: int = 8, **kwargs):
         unknown = set(kwargs) - _SPLIT_KWARGS
         if unknown:
             raise TypeError(f"unknown keyword arguments: {sorted(unknown)}")
@@ -108,6 +108,7 @@ class BatchedOpfEnv:
         # device sync per step; by default a NaN action simply propagates: that env comes back
         # non-converged with NaN reward/obs (its neighbours in the batch are unaffected).
         self.validate_actions = validate_actions
+        self.max_reset_resamples = int(max_reset_resamples)
         self.num_envs = int(num_envs)
         self.profiles = profiles
         self.obs_keys = list(observation_keys)
@@ -511,20 +512,41 @@ class BatchedOpfEnv:
         if fusable:
             self._reset_plans[distr] = (self.engine.make_reset_plan(trace, self._episode * 64),
                                         self._stream_in_episode)
-        if random_action:
-            self.engine.philox_uniform(self.engine.actions_reset, self.seed, self.first_env,
-                                       self._next_stream())
-        else:
-            self.engine.actions_reset.fill_(0.5)
+        self._apply_initial_action(random_action)
+        if not self.pf_for_obs:
+            self.engine.observe()
+            return
+        self._reset_power_flow()
+        # The reference re-samples a state whose reset power flow fails (opf_env.py:209-214: `return self.reset()`).
+        # Batched: every environment draws again (the next RNG streams), the new state is kept only where the
+        # previous one failed; bounded (the reference recurses without limit), one host sync per reset in this
+        # mode.  What still fails after `max_reset_resamples` rounds starts with a NaN observation, converged = 0.
+        e, xp = self.engine, self.xp
+        for _ in range(self.max_reset_resamples):
+            failed = self._results.converged == 0
+            if not bool(failed.any()):
+                break
+            good_state, good_actions = e.state.clone(), e.actions_reset.clone()
+            self._sampling(step, self.test, True)
+            self._apply_initial_action(random_action, assemble=False)
+            e.state.copy_(xp.where(failed[:, None], e.state, good_state))
+            e.actions_reset.copy_(xp.where(failed[:, None], e.actions_reset, good_actions))
+            self._apply_initial_action(random_action, draw=False)
+            self._reset_power_flow()
+
+    def _apply_initial_action(self, random_action, draw=True, assemble=True):
+        """opf_env.py:199-207: the initial (centre / random) action and its set-points."""
+        if draw:
+            if random_action:
+                self.engine.philox_uniform(self.engine.actions_reset, self.seed, self.first_env,
+                                           self._next_stream())
+            else:
+                self.engine.actions_reset.fill_(0.5)
+        if not assemble:
+            return
         if self.pf_for_obs:
             self.engine.actions.copy_(self.engine.actions_reset)
         self.engine.assemble(scatter_sbus=self.pf_for_obs, absolute=True)   # opf_env.py:207
-        if self.pf_for_obs:
-            # the reference re-samples envs whose reset power flow fails (opf_env.py:209-214);
-            # here such envs simply start with a NaN observation and are flagged in `converged`
-            self._reset_power_flow()
-        else:
-            self.engine.observe()
 
     def _reset_power_flow(self):
         """Power flow + scoring of the freshly reset state (opf_env.py:209-216).  It goes to the

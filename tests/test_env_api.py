@@ -570,3 +570,23 @@ def test_engine_cls_is_a_gated_test_seam():
         check_engine_class(Sneaky)
     check_engine_class(Engine)
     check_engine_class(TorchHostSimEngine)
+
+
+def test_failed_reset_states_are_resampled():
+    """opf_env.py:209-214: a reset state whose power flow fails is sampled again (the reference recurses into
+    reset()).  Batched: only the failed environments take the new draw; the others keep their state."""
+    kw = dict(num_envs=48, add_res_obs=True, train_data="full_uniform", test_data="full_uniform", load_scaling=6.5,
+              engine_cls=TorchHostSimEngine, seed=3, n_profile_steps=96)
+    env = envs.VoltageControl(max_reset_resamples=0, **kw)
+    env.reset(seed=1)
+    first = env._results.converged.numpy().astype(bool).copy()
+    first_loads = env.col("load", "p_mw").numpy().copy()
+    assert 0.1 < first.mean() < 0.9                      # the operating point sits at the collapse boundary
+    env = envs.VoltageControl(**kw)
+    obs, _ = env.reset(seed=1)
+    assert env._results.converged.numpy().all()
+    loads = env.col("load", "p_mw").numpy()
+    np.testing.assert_array_equal(loads[first], first_loads[first])          # good states untouched
+    assert (loads[~first] != first_loads[~first]).any(axis=1).all()          # failed ones drawn again
+    vm = env.col("res_bus", "vm_pu").numpy()
+    assert np.isfinite(vm).all()
