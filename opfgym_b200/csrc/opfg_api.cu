@@ -11,6 +11,8 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <stdexcept>
 #include <string>
@@ -76,6 +78,32 @@ void dev_get(void* dst, const void* src, size_t bytes) {
     cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
 #endif
 }
+
+// Function attributes (dynamic shared-memory limit) are per DEVICE: remember what was raised per (device, kernel), so
+// that a process driving several GPUs (envs on different devices, mixed-batch members) raises it on each of them
+// (round-1 advisor finding: the bookkeeping used to live in process-wide statics).
+#ifndef OPFG_HOSTSIM
+template <class F>
+void ensure_dynamic_smem(F* fn, size_t bytes) {
+    if (bytes <= 48 * 1024) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> raised;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = raised[{dev, reinterpret_cast<const void*>(fn)}];
+    if (bytes > cur) {
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cur = bytes;
+    }
+}
+int current_sm_count() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+#endif
 
 }  // namespace
 
@@ -1725,8 +1753,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                      B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);
 #else
     if (G->d.dc_pre && !(use_tree(G, B) && G->d.tr_dc)) {   // the radial kernel has its own DC start
-        static bool dc_attr = false;
-        if (!dc_attr) { cudaFuncSetAttribute(k_dc_start, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DC_SMEM); dc_attr = true; }
+        ensure_dynamic_smem(k_dc_start, DC_SMEM);
         k_dc_start<<<dim3((unsigned)((B->n_env + DC_ENVS - 1) / DC_ENVS), (unsigned)((G->d.n + 63) / 64)), 256, DC_SMEM, (cudaStream_t)stream>>>(G->d, *B);
         ++g_launches;
     }
@@ -1777,11 +1804,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     }
     const size_t smem = G->smem_pf;
     OPFG_DISPATCH_T(G->d.threads, {
-        static size_t attr_smem = 48 * 1024;
-        if (smem > attr_smem) {
-            cudaFuncSetAttribute(k_pf<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_smem = smem;
-        }
+        ensure_dynamic_smem(k_pf<TT>, smem);
         static int carve_set = -1;
         if (G->carveout_pct >= 0 && carve_set != G->carveout_pct) {
             // leave part of the unified L1/shared array to L1: the shared schedule tables must stay
@@ -1792,14 +1815,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         if (G->envs_per_cta > 1) {
             const int E = G->envs_per_cta;
             const size_t smem_multi = G->d.tab_staged_bytes + (size_t)E * smem;
-            static size_t attr_multi = 48 * 1024;
-            if (smem_multi > attr_multi) {
-                for (auto* fn : {k_pf_multi<TT, 0>, k_pf_multi<TT, 1>, k_pf_multi<TT, 2>, k_pf_multi<TT, 4>, k_pf_multi<TT, 5>, k_pf_multi<TT, 6>})
-                    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
-                attr_multi = smem_multi;
-            }
-            int n_sm = 148;
-            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+            const int n_sm = current_sm_count();
             const int64_t groups = (B->n_env + E - 1) / E;
             const unsigned grid = (unsigned)std::min<int64_t>(groups, n_sm);
             const int stage = G->d.tab_staged_bytes == G->d.tab_bytes ? 2 : (G->d.tab_staged_bytes == G->d.tab_warm_bytes ? 1 : 0);
@@ -1816,7 +1832,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                 case 5: fn = pick_multi<TT, 5>(bound); break;
                 default: fn = pick_multi<TT, 6>(bound); break;
             }
-            if (bound != 768) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi);
+            ensure_dynamic_smem(fn, smem_multi);
             fn<<<grid, TT * E, smem_multi, (cudaStream_t)stream>>>(view, *B, E, env_doubles);
         } else {
             k_pf<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);
@@ -1845,19 +1861,11 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
 #else
     const size_t smem = score_smem_doubles(G->d.nb, G->d.nbr, G->score_threads) * sizeof(double);
     OPFG_DISPATCH_T(G->score_threads, {
-        static size_t attr_smem = 48 * 1024;
-        if (smem > attr_smem) {
-            cudaFuncSetAttribute(k_score<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_smem = smem;
-        }
+        ensure_dynamic_smem(k_score<TT>, smem);
         if (TT == 32) {
             static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
             const size_t per_env = (smem + 15) & ~size_t(15);
-            static size_t attr_w = 48 * 1024;
-            if (per_env * warps > attr_w) {
-                cudaFuncSetAttribute(k_score_warps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_env * warps));
-                attr_w = per_env * warps;
-            }
+            ensure_dynamic_smem(k_score_warps, per_env * warps);
             k_score_warps<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, per_env * warps, (cudaStream_t)stream>>>(
                 G->d, *B, (int)(per_env / 8));
         } else {
@@ -1937,10 +1945,7 @@ static int mixed_launch(OpfgMixed* M, const OpfgBatch* batches, int which, void*
     if (which == 0) {
         k_assemble_mixed<<<cta, 128, 0, (cudaStream_t)stream>>>((const MixedMember*)M->dev, M->n);
     } else {
-        static size_t attr = 48 * 1024;      // raised per process; the kernel is the same on every device of the process
-        if (M->smem_score > attr) {
-            cudaFuncSetAttribute(k_score_mixed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M->smem_score);
-        }
+        ensure_dynamic_smem(k_score_mixed, M->smem_score);
         k_score_mixed<<<cta, 128, M->smem_score, (cudaStream_t)stream>>>((const MixedMember*)M->dev, M->n);
     }
     ++g_launches;
@@ -2145,12 +2150,8 @@ int opfg_reset_episode(const OpfgGrid* G, const OpfgBatch* B, const OpfgResetPla
     constexpr int T = 128;
     const size_t smem = sizeof(double) * n_row + sizeof(ResetStage) * n_st + sizeof(OpfgRowOp) * P->n_ops_total +
                         sizeof(double) * T * P->n_regs;
-    static size_t attr = 48 * 1024;
-    if (smem > attr) {
-        if (cudaFuncSetAttribute(k_reset<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return fail("reset: %zu bytes of shared memory per environment", smem);
-        attr = smem;
-    }
+    if (smem > 227 * 1024) return fail("reset: %zu bytes of shared memory per environment", smem);
+    ensure_dynamic_smem(k_reset<T>, smem);
     k_reset<T><<<(unsigned)B->n_env, T, smem, (cudaStream_t)stream>>>(
         G->d, *B, P->dev, n_st, n_row, staged && !P->covers_all, P->n_ops_total, seed, first_env, stream_base,
         random_action, action_stream_offset);

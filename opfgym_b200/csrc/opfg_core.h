@@ -279,7 +279,8 @@ OPFG_HD void branch_admittance(const double* p, double* y) {
     const double z2 = r * r + x * x;
     const double ysr = r / z2, ysi = -x / z2;
     const double ttr = ysr + 0.5 * gsh, tti = ysi + 0.5 * b;
-    const double c = cos(sh), s = sin(sh);
+    double c = 1.0, s = 0.0;                                  // lines and most transformers: no phase shift
+    if (sh != 0.0) { c = cos(sh); s = sin(sh); }
     const double t2 = tap * tap;
     y[0] = ttr / t2;  y[1] = tti / t2;                        // Yff = Ytt / |tap|^2
     // Yft = -Ys / conj(tap) = -Ys * tap / |tap|^2 ; tap = tap*(c + js)
