@@ -105,3 +105,28 @@ def test_engine_vs_pandapower(name, net, source):
         except LoadflowNotConverged:
             target.converged = False
         _compare(ref, target, f"{name} {source} case {k}")
+
+
+def test_oracle_topology_semantics_vs_pandapower():
+    """The restated topology rules (oracle/ppc_ref.py, all [ext-mem]) against pandapower itself: an
+    out-of-service line, a line opened at one end by its switch (auxiliary bus), an outage that islands part of
+    a feeder (`_check_connectivity`: dropped buses report NaN).  The engine is pinned to the oracle on exactly
+    these cases by tests/test_islands.py and tests/test_switch_cells.py."""
+    from oracle import pf
+    net = pn.mv_oberrhein()
+    line_switches = net.switch.index[(net.switch.et == "l") & net.switch.closed]
+    cases = {"line out of service": lambda n: n.line.__setitem__("in_service", n.line.in_service.where(n.line.index != n.line.index[7], False)),
+             "line open at one end": lambda n: n.switch.__setitem__("closed", n.switch.closed.where(n.switch.index != line_switches[3], False)),
+             "islanding outage": lambda n: n.line.__setitem__("in_service", n.line.in_service.where(n.line.index != n.line.index[40], False))}
+    import copy
+    for label, change in cases.items():
+        ref = copy.deepcopy(net)
+        change(ref)
+        pp.runpp(ref, enforce_q_lims=True)
+        mine = _to_container(ref)
+        pf.runpp(mine, enforce_q_lims=True)
+        for table, column, tol in (("res_bus", "vm_pu", TOL["vm"]), ("res_line", "loading_percent", TOL["loading"]),
+                                   ("res_trafo", "loading_percent", TOL["loading"])):
+            a, b = ref[table][column].to_numpy(float), mine[table][column].to_numpy(float)
+            assert (np.isnan(a) == np.isnan(b)).all(), f"{label}: NaN pattern of {table}.{column}"
+            np.testing.assert_allclose(b[~np.isnan(a)], a[~np.isnan(a)], atol=tol, err_msg=f"{label} {table}.{column}")

@@ -221,3 +221,17 @@ def test_switch_contingencies_hostsim():
 @pytest.mark.gpu
 def test_switch_contingencies_cuda(cuda_lib):
     _check_switch_contingencies({})
+
+
+def test_ties_are_not_island_critical():
+    """Only a switchable branch that is an edge of the static grid's spanning forest can cut buses off; the
+    forest is grown through normally-closed branches first, so normally-open ties never trigger kernel 1's
+    connectivity walk (with ties as forest edges BASELINE config 5 lost 20 % of its throughput)."""
+    from tests.test_dynamic_branches import make_env
+    env, ties = make_env(3, engine_cls=TorchHostSimEngine)
+    n_lines_in_service = int(env.net.line.in_service.to_numpy(bool).sum())
+    assert env.engine.bry.shape[1] == len(env.net.line) + len(env.net.trafo)         # every branch has a cell
+    # the whole line column is per-environment: exactly the regular lines are critical, none of the four ties
+    assert env.engine.info["n_island_critical"] == n_lines_in_service
+    env, switched = make_switch_env(3, engine_cls=TorchHostSimEngine)
+    assert env.engine.info["n_island_critical"] == n_lines_in_service
