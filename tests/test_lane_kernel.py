@@ -89,3 +89,19 @@ def test_kernels_agree_cuda(cuda_lib, name, n_env, lam, kernels):
     from opfgym_b200.engine import Engine
     _same(_pair(Engine, name, n_env, seed=33, lam=lam, sync=torch.cuda.synchronize, kernels=kernels),
           mixed=lam is not None)
+
+
+@pytest.mark.gpu
+def test_block_kernel_builds_by_block_size_cuda(cuda_lib, monkeypatch):
+    """k_pf_multi exists in three builds (launch bounds 768 / 512 / 256 threads: 80 / ~124 / ~144 registers).  The MV
+    grid normally runs the 768 build (11 environments x 64 threads); capped at 8 and at 4 environments per CTA it
+    runs the 512 and the 256 build: same bits as the lane kernel in all three."""
+    import torch
+    from opfgym_b200.engine import Engine
+    for cap in (None, "8", "4"):
+        if cap is None:
+            monkeypatch.delenv("OPFG_ENVS_PER_CTA", raising=False)
+        else:
+            monkeypatch.setenv("OPFG_ENVS_PER_CTA", cap)
+        _same(_pair(Engine, "1-MV-semiurb--1-sw", 2051, seed=35, lam=(5.0, 12.0), sync=torch.cuda.synchronize,
+                    kernels=("cta", "lanes")), mixed=True)
