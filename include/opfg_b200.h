@@ -21,6 +21,7 @@
  *                         opfgym/reward.py:61-98, OpfEnv._get_obs opf_env.py:532-549
  *   opfg_philox_uniform   np_random.uniform in OpfEnv._sample_from_range  opf_env.py:278
  *   opfg_sample_uniform   OpfEnv._sample_uniform / _sample_from_range      opf_env.py:253-284
+ *   opfg_sample_uniform_obs   ... with the reset observation written on the way   opf_env.py:218
  *   opfg_sample_profiles  OpfEnv._set_simbench_state (profile row, noise, clip)    opf_env.py:317-372
  *   opfg_assemble         OpfEnv._apply_actions + makeSbus (kernel 1)
  *   opfg_pf_solve         pp.runpp(net, enforce_q_lims=True)  opf_env.py:696-709
@@ -274,6 +275,14 @@ int opfg_philox_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id,
 int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env,
                         int32_t n_cols, const int32_t* slots, const double* lo, const double* hi,
                         const double* div, double* state, int32_t n_state, void* cuda_stream);
+/* The same, and the sampled values go straight into the observation as well (OpfEnv._get_obs after reset,
+ * opf_env.py:218, 532-549, when the observed cells are exactly cells this sampler writes): obs_pos[j] = position of
+ * column j in the observation row or -1; exactly one of obs_f32 / obs_f64 ([n_env, n_obs]) is given.  Saves
+ * re-reading the state row for the reset observation (opfg_observe). */
+int opfg_sample_uniform_obs(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env,
+                            int32_t n_cols, const int32_t* slots, const double* lo, const double* hi,
+                            const double* div, double* state, int32_t n_state, const int32_t* obs_pos,
+                            float* obs_f32, double* obs_f64, int32_t n_obs, void* cuda_stream);
 
 /* OpfEnv._set_simbench_state (opf_env.py:317-372; the reference's DEFAULT sampler, train_data='simbench'):
  * S[b, slots[j]] = clip(noise(table[step[b], j] (optionally interpolated towards step + 1 with interp_r[b])),

@@ -115,6 +115,10 @@ PROTOTYPES = {
     "opfg_sample_uniform": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "opfg_sample_uniform_obs": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64,
+                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int32, C.c_void_p]),
     "opfg_sample_profiles": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_double, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -499,20 +499,25 @@ __global__ void k_philox(uint64_t seed, uint64_t first_env, uint64_t stream, int
 }
 __global__ void k_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols,
                                  const int* slots, const double* lo, const double* hi, const double* dv,
-                                 double* state, int n_state, int w_log2) {
+                                 double* state, int n_state, int w_log2, const int* obs_pos, float* o32, double* o64,
+                                 int n_obs) {
     const int pr0 = (int)(blockIdx.x << w_log2) + (int)(threadIdx.x & ((1u << w_log2) - 1u));
     if (2 * pr0 >= n_cols) return;
     const int j0 = 2 * pr0, j1 = 2 * pr0 + 1;
     const bool two = j1 < n_cols;
     const int s0 = slots[j0], s1 = two ? slots[j1] : 0;
+    const int p0 = obs_pos ? obs_pos[j0] : -1, p1 = (obs_pos && two) ? obs_pos[j1] : -1;
     const double lo0 = lo[j0], w0 = hi[j0] - lo0, d0 = dv[j0];
     const double lo1 = two ? lo[j1] : 0.0, w1 = two ? hi[j1] - lo1 : 0.0, d1 = two ? dv[j1] : 1.0;
     OPFG_ITEM_LOOP(pr, b, n_env, w_log2) {
         double u0, u1;
         philox_two_doubles(seed, first_env + (uint64_t)b, stream, (uint32_t)pr, &u0, &u1);
         double* row = state + b * (int64_t)n_state;
-        row[s0] = (lo0 + w0 * u0) / d0;
-        if (two) row[s1] = (lo1 + w1 * u1) / d1;
+        const double v0 = (lo0 + w0 * u0) / d0, v1 = (lo1 + w1 * u1) / d1;
+        row[s0] = v0;
+        if (two) row[s1] = v1;
+        if (p0 >= 0) { if (o32) o32[b * (int64_t)n_obs + p0] = (float)v0; else o64[b * (int64_t)n_obs + p0] = v0; }
+        if (p1 >= 0) { if (o32) o32[b * (int64_t)n_obs + p1] = (float)v1; else o64[b * (int64_t)n_obs + p1] = v1; }
     }
 }
 __global__ void k_sample_profiles(uint64_t seed, uint64_t first_env, uint64_t stream, int64_t n_env, int n_cols,
@@ -1623,7 +1628,17 @@ int opfg_philox_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
 int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env, int32_t n_cols,
                         const int32_t* slots, const double* lo, const double* hi, const double* dv, double* state,
                         int32_t n_state, void* cuda_stream) {
+    return opfg_sample_uniform_obs(seed, first_env, stream_id, n_env, n_cols, slots, lo, hi, dv, state, n_state,
+                                   nullptr, nullptr, nullptr, 0, cuda_stream);
+}
+
+int opfg_sample_uniform_obs(uint64_t seed, uint64_t first_env, uint64_t stream_id, int64_t n_env, int32_t n_cols,
+                            const int32_t* slots, const double* lo, const double* hi, const double* dv, double* state,
+                            int32_t n_state, const int32_t* obs_pos, float* obs_f32, double* obs_f64, int32_t n_obs,
+                            void* cuda_stream) {
     if (!slots || !lo || !hi || !dv || !state || n_env < 0 || n_cols < 0) return fail("bad argument");
+    if (obs_pos && ((obs_f32 != nullptr) == (obs_f64 != nullptr) || n_obs <= 0))
+        return fail("opfg_sample_uniform_obs: exactly one of obs_f32 / obs_f64, and n_obs > 0");
     if (n_env == 0 || n_cols == 0) return 0;
     const int pairs = (n_cols + 1) / 2;
 #ifdef OPFG_HOSTSIM
@@ -1634,13 +1649,20 @@ int opfg_sample_uniform(uint64_t seed, uint64_t first_env, uint64_t stream_id, i
             philox_two_doubles(seed, first_env + (uint64_t)b, stream_id, (uint32_t)pr, &u[0], &u[1]);
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * pr + h;
-                if (j < n_cols) state[b * (int64_t)n_state + slots[j]] = (lo[j] + (hi[j] - lo[j]) * u[h]) / dv[j];
+                if (j >= n_cols) continue;
+                const double v = (lo[j] + (hi[j] - lo[j]) * u[h]) / dv[j];
+                state[b * (int64_t)n_state + slots[j]] = v;
+                if (obs_pos && obs_pos[j] >= 0) {
+                    if (obs_f32) obs_f32[b * (int64_t)n_obs + obs_pos[j]] = (float)v;
+                    else obs_f64[b * (int64_t)n_obs + obs_pos[j]] = v;
+                }
             }
         }
 #else
     const ItemGrid ig = item_grid(n_env, pairs);
     k_sample_uniform<<<ig.grid, 256, 0, (cudaStream_t)cuda_stream>>>(
-        seed, first_env, stream_id, n_env, n_cols, slots, lo, hi, dv, state, n_state, ig.w_log2);
+        seed, first_env, stream_id, n_env, n_cols, slots, lo, hi, dv, state, n_state, ig.w_log2, obs_pos, obs_f32,
+        obs_f64, n_obs);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail("sample launch: %s", cudaGetErrorString(e));

@@ -230,14 +230,24 @@ class Engine:
             self.handle, C.byref(self.batch_setpoints), plan.handle, seed, first_env, stream_base,
             int(random_action), action_stream_offset, self._stream()))
 
-    def sample_uniform(self, slots, lo, hi, div, seed: int, first_env: int, stream_id: int):
+    def sample_uniform(self, slots, lo, hi, div, seed: int, first_env: int, stream_id: int, obs_pos=None):
+        """``obs_pos`` (device int32, per sampled column: its position in the observation or -1): the sampled
+        values are written into ``self.obs`` on the way (opfg_sample_uniform_obs)."""
         if self.trace is not None:
             self.trace.append(("sample", slots, lo, hi, div, stream_id))
         n = int(slots.shape[0])
-        capi.check(self.lib, self.lib.opfg_sample_uniform(
+        if obs_pos is None:
+            capi.check(self.lib, self.lib.opfg_sample_uniform(
+                seed, first_env, stream_id, self.num_envs, n, self._ptr(slots), self._ptr(lo),
+                self._ptr(hi), self._ptr(div), self._ptr(self.state), self.program.layout.n,
+                self._stream()))
+            return
+        f32 = str(self.obs.dtype).endswith("float32")
+        capi.check(self.lib, self.lib.opfg_sample_uniform_obs(
             seed, first_env, stream_id, self.num_envs, n, self._ptr(slots), self._ptr(lo),
             self._ptr(hi), self._ptr(div), self._ptr(self.state), self.program.layout.n,
-            self._stream()))
+            self._ptr(obs_pos), self._ptr(self.obs) if f32 else None, None if f32 else self._ptr(self.obs),
+            int(self.obs.shape[1]), self._stream()))
 
     def sample_profiles(self, slots, table, step, interp_r, pmin, pmax, noise_factor: float, noise_kind: int,
                         seed: int, first_env: int, stream_id: int):

@@ -590,3 +590,45 @@ def test_failed_reset_states_are_resampled():
     assert (loads[~first] != first_loads[~first]).any(axis=1).all()          # failed ones drawn again
     vm = env.col("res_bus", "vm_pu").numpy()
     assert np.isfinite(vm).all()
+
+
+@pytest.mark.parametrize("env_name", ["VoltageControl", "QMarket", "EcoDispatch", "LoadShedding", "MaxRenewable"])
+def test_reset_observation_written_by_the_sampler(env_name):
+    _check_reset_observation_by_sampler(env_name, dict(engine_cls=TorchHostSimEngine), lambda t: t.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_name", ["VoltageControl", "EcoDispatch", "LoadShedding"])
+def test_reset_observation_written_by_the_sampler_cuda(cuda_lib, env_name):
+    _check_reset_observation_by_sampler(env_name, dict(prefetch_reset=False), lambda t: t.cpu().numpy())
+
+
+def _check_reset_observation_by_sampler(env_name, kw, to_np):
+    """From the second reset on, the uniform sampler writes the observation itself where that is provably the
+    same thing (every observed cell is a sampled cell that nothing writes afterwards) and `opfg_observe` is
+    skipped: the result must be what the gather produces, bit for bit."""
+    cls = getattr(envs, env_name)
+    env = cls(num_envs=7, train_data="full_uniform", test_data="full_uniform", seed=11, n_profile_steps=96,
+              fused_reset=False, **kw)
+    plain = cls(num_envs=7, train_data="full_uniform", test_data="full_uniform", seed=11, n_profile_steps=96,
+                fused_reset=False, fuse_reset_obs=False, **kw)
+    took_shortcut = []
+    calls = []
+    real_observe = env.engine.observe
+    env.engine.observe = lambda: (calls.append(1), real_observe())[1]
+    for episode in range(4):
+        del calls[:]
+        obs, _ = env.reset(seed=20 + episode)
+        used = len(calls)
+        ref, _ = plain.reset(seed=20 + episode)
+        np.testing.assert_array_equal(to_np(obs), to_np(ref))
+        gathered = env.engine.obs.clone()
+        real_observe()                                    # the gather, on the same state
+        np.testing.assert_array_equal(to_np(gathered), to_np(env.engine.obs))
+        took_shortcut.append(used)
+    assert not plain._obs_by_sampler
+    assert took_shortcut[0] == 1                          # the first reset gathers (and decides)
+    assert took_shortcut[1:] == [0 if env._obs_by_sampler else 1] * 3
+    # which envs qualify is a property of their observation keys; VoltageControl (loads and sgens only) must
+    if env_name == "VoltageControl":
+        assert env._obs_by_sampler
