@@ -118,6 +118,7 @@ class Engine:
         self.batch_setpoints.absolute_actions = 1
         self._linked = [self.batch, self.batch_final, self.batch_setpoints]   # batches that follow select()
         self._states = [self.state]
+        self._obs_bufs = [self.obs]        # every episode buffer has its own (reset) observation
         self.cur = 0
         self.aux = None
         self.batch_aux = None
@@ -167,14 +168,22 @@ class Engine:
         """More state matrices: later episodes can be sampled while the current one is solved."""
         while len(self._states) < n:
             self._states.append(self.state.clone())
+            self._obs_bufs.append(self.obs.clone())
 
     def select(self, index: int):
         """Make state buffer ``index`` the one every launch (and ``column()``) refers to."""
         self.cur = index
         self.state = self._states[index]
-        ptr = self._ptr(self.state)
+        self.obs = self._obs_bufs[index]
+        ptr, obs_ptr = self._ptr(self.state), self._ptr(self.obs)
+        f32 = str(self.obs.dtype).endswith("float32")
         for b in self._linked:
             b.state = ptr
+            if b is not self.batch_final:          # that one writes the finished episode's observation
+                if f32:
+                    b.obs_f32 = obs_ptr
+                else:
+                    b.obs_f64 = obs_ptr
 
     # ------------------------------------------------------- device plumbing (torch)
     def _setup_device(self, device):

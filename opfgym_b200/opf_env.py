@@ -230,6 +230,8 @@ class BatchedOpfEnv:
         # 64-512), the separate full-occupancy kernels win beyond that -- hence the automatic rule.
         self.fused_reset = (type(self).__module__.startswith("opfgym_b200.") and self.num_envs <= 1024) \
             if fused_reset is None else bool(fused_reset)
+        if fuse_reset_obs is None and os.environ.get("OPFG_FUSE_RESET_OBS"):
+            fuse_reset_obs = os.environ["OPFG_FUSE_RESET_OBS"] != "0"
         self._fuse_reset_obs = type(self).__module__.startswith("opfgym_b200.") if fuse_reset_obs is None \
             else bool(fuse_reset_obs)
         self._reset_plans = {}
@@ -238,10 +240,14 @@ class BatchedOpfEnv:
         if self._prefetch:
             self.engine.enable_double_buffer()
             self._side = self.xp.cuda.Stream(device=self.device)
+            self._copy_stream = self.xp.cuda.Stream(device=self.device)      # step_host: observation transfers
+            self._pf_done = self.xp.cuda.Event()
+            self._late_prefetch = os.environ.get("OPFG_LATE_PREFETCH", "1") != "0"
+            self._sampled_events = [self.xp.cuda.Event() for _ in range(3)]
             self._main_done = self.xp.cuda.Event()
             self._side_done = self.xp.cuda.Event()
             self._side_kernels = self.xp.cuda.Event()
-            self._ready_events = (self.xp.cuda.Event(), self.xp.cuda.Event())
+            self._ready_events = (self.xp.cuda.Event(enable_timing=bool(os.environ.get("OPFG_TIMING_EVENTS"))), self.xp.cuda.Event(enable_timing=bool(os.environ.get("OPFG_TIMING_EVENTS"))))
             self._results_copied = self.xp.cuda.Event()
         self._pipe = None     # step_host's look-ahead: episode k+1 already sampled, its observation on the host
         self.test = False
@@ -507,6 +513,7 @@ class BatchedOpfEnv:
             # step_host's look-ahead may still be sampling / copying on the side stream, and it shares
             # the device observation buffer with the reset below
             self.xp.cuda.current_stream(self.device).wait_stream(self._side)
+            self.xp.cuda.current_stream(self.device).wait_stream(self._copy_stream)
         self._pipe = None
         self.test = options.get("test", False)
         self._begin_episode(options.get("step", None))
@@ -644,8 +651,9 @@ class BatchedOpfEnv:
         e.reward.copy_(xp.where(ok, self.reward_function.batched(objective, penalty, valid), nan))
         e.cost.copy_(xp.where(ok, self.reward_function.batched_cost(penalty, valid), nan))
 
-    def _obs_out(self, final: bool = False):
-        obs = self.engine.obs_final if final else self.engine.obs
+    def _obs_out(self, final: bool = False, obs=None):
+        if obs is None:
+            obs = self.engine.obs_final if final else self.engine.obs
         if self.add_mean_obs:
             parts, k = [], 0
             for n in self.program.obs_segments:
@@ -682,6 +690,8 @@ class BatchedOpfEnv:
             raise RuntimeError("step() after step_host(): the host pipeline holds pre-sampled episodes; "
                                "call reset() before switching back to the tensor API")
         if self._prefetch:
+            # The next episode is needed at the end of THIS step: its kernels go first (measured: issued behind
+            # the power flow instead, sharing the GPU with kernel 5, the step is 1.290 instead of 1.266 ms).
             main = xp.cuda.current_stream(self.device)
             self._main_done.record(main)
             cur, nxt = e.cur, (e.cur + 1) % len(e._states)
@@ -769,9 +779,9 @@ class BatchedOpfEnv:
                 src.copy_(a.reshape(src.shape))
         if self.validate_actions and xp.isnan(src).any():
             raise AssertionError("NaN in actions")     # opf_env.py:382
-        def obs_to_host(dst):
+        def obs_to_host(dst, dev_obs=None):
             keep, self.copy_outputs = self.copy_outputs, False     # no device-side clone on the way out
-            obs = self._obs_out()
+            obs = self._obs_out(obs=dev_obs)
             if self._obs_cast is not None:                         # narrower host dtype: cast on the device
                 self._obs_cast.copy_(obs)
                 obs = self._obs_cast
@@ -790,24 +800,31 @@ class BatchedOpfEnv:
             e.enable_double_buffer(3)
             pipe = self._pipe
 
-            def sample_ahead(buf, dst, after=None):
+            def sample_ahead(buf, dst, after=None, start_after=None):
                 """Side stream: kernels of the next episode into state buffer `buf`; then (once the
                 event `after` has passed -- the copy engine serves requests in order, and the
                 small per-step results must not queue behind 58 MB) its observation to `dst`."""
                 cur = e.cur
                 e.select(buf)
+                sampled = self._sampled_events[buf]
                 with xp.cuda.stream(self._side):
-                    self._side.wait_event(self._main_done)
+                    self._side.wait_event(start_after or self._main_done)
                     self._begin_episode()
+                    sampled.record(self._side)
+                dev_obs = e.obs                        # every episode buffer has its own device observation ...
                 e.select(cur)
 
                 def copy():
-                    with xp.cuda.stream(self._side):
+                    # ... so the transfer runs on a stream of its own: the side stream's kernels of the NEXT
+                    # call do not queue behind 58 MB on the copy engine (they used to, and then had to find a
+                    # gap next to the persistent power-flow kernel: 1.43 instead of 1.35 ms per step)
+                    with xp.cuda.stream(self._copy_stream):
+                        self._copy_stream.wait_event(sampled)
                         if after is not None:
-                            self._side.wait_event(after)
-                        obs_to_host(dst)
+                            self._copy_stream.wait_event(after)
+                        obs_to_host(dst, dev_obs)
                         ready = self._ready_events[dst is h["obs"]]
-                        ready.record(self._side)
+                        ready.record(self._copy_stream)
                     return ready
                 return copy
 
@@ -816,10 +833,21 @@ class BatchedOpfEnv:
                 nxt = (e.cur + 1) % 3
                 pipe = dict(buf=nxt, obs="obs", ready=sample_ahead(nxt, h["obs"])())
             e.actions.copy_(src, non_blocking=True)    # this step's own work goes to the GPU first
-            e.step(final_obs=True)
+            if self._late_prefetch:
+                # The look-ahead episode is not needed before the NEXT call: its kernels are issued behind the
+                # power flow (the persistent kernel fills every SM, nothing runs beside it), where they share
+                # the GPU with kernel 5 and fill the gap between two calls -- 1.33 instead of 1.46 ms per call
+                # against issuing them at the start of the step, where they contend with kernel 1 / the DC GEMM
+                e.assemble()
+                e.pf_solve()
+                self._pf_done.record(main)
+                e.score(e.batch_final)
+            else:
+                e.step(final_obs=True)
             free = 3 - e.cur - pipe["buf"]             # the buffer of the episode before this one
             other = "obs_alt" if pipe["obs"] == "obs" else "obs"
-            copy_ahead = sample_ahead(free, h[other], after=self._results_copied)
+            copy_ahead = sample_ahead(free, h[other], after=self._results_copied,
+                                      start_after=self._pf_done if self._late_prefetch else None)
         else:
             e.actions.copy_(src, non_blocking=True)
             e.step(final_obs=True)
