@@ -128,6 +128,16 @@ class Compiler:
         v = self.net[table][column].iloc[int(pos)]
         return self.consts.ref(np.nan if v is None else v)
 
+    def _absent_branch_value(self, table, pos) -> float:
+        """pandapower's result of a branch that is out of service: its rows of ppc['branch'] are never written, so
+        flows are 0 and the current 0 / |V| -- 0 between energised buses, NaN if an end bus was dropped
+        (results_branch.py `_get_branch_flows` [ext-mem])."""
+        net, lk = self.net, self.ppc.bus_lookup
+        ends = ("from_bus", "to_bus") if table == "line" else ("hv_bus", "lv_bus")
+        pos_of = {int(b): i for i, b in enumerate(net.bus.index)}
+        live = all(lk[pos_of[int(net[table][c].iloc[pos])]] >= 0 for c in ends)
+        return 0.0 if live else float("nan")
+
     def _nominally_on(self, table, pos) -> bool:
         """In service, with every switch at its ends closed, in the net as given (ties are not)."""
         net = self.net
@@ -191,6 +201,7 @@ class Compiler:
         res_vm = res_va = -1
         loading_slot = -np.ones(nbr, dtype=_I32)
         flow_slot = -np.ones(nbr, dtype=_I32)
+        absent_cells = {}      # result cells of branches that are not in the ppc: 0 between live buses, else NaN
         gen_p_slot = -np.ones(ng, dtype=_I32)
         gen_q_slot = -np.ones(ng, dtype=_I32)
         for table, column in sorted(wanted):
@@ -208,6 +219,8 @@ class Compiler:
                 for pos, br in enumerate(mapping):
                     if br >= 0:
                         loading_slot[br] = start + pos
+                    else:
+                        absent_cells[start + pos] = self._absent_branch_value(base, pos)
             elif table == "res_ext_grid" and column in ("p_mw", "q_mvar"):
                 start = lay.add(table, column, n_rows)
                 tgt = gen_p_slot if column == "p_mw" else gen_q_slot
@@ -226,6 +239,9 @@ class Compiler:
                 for pos, br in enumerate(mapping):
                     if br >= 0:
                         flow_slot[br] = start + 4 * pos
+                    else:
+                        for k in range(4):
+                            absent_cells[start + 4 * pos + k] = self._absent_branch_value(base, pos)
             elif table == "res_trafo3w":
                 lay.add(table, column, n_rows)   # no trafo3w model: column stays NaN
             elif table in ("res_load", "res_sgen", "res_storage", "res_gen") and column in ("p_mw", "q_mvar"):
@@ -242,6 +258,8 @@ class Compiler:
             col = net[table][column]
             init[start:start + n_rows] = np.asarray(
                 [np.nan if v is None else float(v) for v in col.to_numpy()], dtype=float)
+        for cell, value in absent_cells.items():
+            init[cell] = value
 
         # ---- actions (opf_env.py:421-491) -----------------------------------
         a_slot, a_lo, a_hi, a_div, a_kind, a_clo, a_chi = [], [], [], [], [], [], []

@@ -1532,12 +1532,12 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     const double* bry_env = (g.n_dyn > 0 && B.bry) ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr;
     for (int l = cx.tid; l < nbr; l += T) {
         const double* y = g.br_y + 8 * (size_t)l;
-        bool in_service = true, half_open = false;
+        bool half_open = false;
         if (bry_env) {
             const int d = g.dyn_of_branch[l];
             if (d >= 0) {                 // out of service (cell or switches): kernel 1 left no admittance at all
                 y = bry_env + 8 * (size_t)d;
-                in_service = !(y[0] == 0.0 && y[1] == 0.0 && y[6] == 0.0 && y[7] == 0.0);
+                const bool in_service = !(y[0] == 0.0 && y[1] == 0.0 && y[6] == 0.0 && y[7] == 0.0);
                 half_open = in_service && y[2] == 0.0 && y[3] == 0.0;     // hangs from one end (open switch at the other)
             }
         }
@@ -1552,9 +1552,11 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         const double lf = sqrt(pf * pf + qf * qf) * g.rate_f[l] / s.vm[f];
         const double lt = sqrt(pt * pt + qt * qt) * g.rate_t[l] / s.vm[t];
         const int slot = g.br_loading_slot[l];
-        double ld = lf > lt ? lf : lt;
-        if (half_open) ld = (y[0] != 0.0 || y[1] != 0.0) ? lf : lt;      // the open end carries no current (and may sit on a dropped bus)
-        if (slot >= 0) S[slot] = in_service ? 100.0 * ld : NAN;   // pandapower: NaN when out of service
+        // pandapower: max(i_from, i_to) / i_max with numpy's NaN-propagating max (an end on a dropped bus: NaN); a
+        // branch that is out of service has zero flows (its ppc rows are never written) -> 0 between live buses
+        double ld = (lf != lf || lt != lt) ? NAN : (lf > lt ? lf : lt);
+        if (half_open) ld = (y[0] != 0.0 || y[1] != 0.0) ? lf : lt;      // the open end sits on pandapower's auxiliary bus: no current
+        if (slot >= 0) S[slot] = 100.0 * ld;
         const int fs = g.br_flow_slot[l];
         if (fs >= 0) { S[fs] = pf; S[fs + 1] = qf; S[fs + 2] = pt; S[fs + 3] = qt; }
     }

@@ -261,20 +261,28 @@ def runpp(net, builder=None, enforce_q_lims=True, tolerance_mva=1e-8,
     net.res_bus = pd.DataFrame({"vm_pu": vm, "va_degree": va}, index=net.bus.index)
     loading = branch_loading(ppc, res)
 
-    def per_branch(mapping, arr):
-        out = np.full(len(mapping), np.nan, dtype=arr.dtype)
+    pos_of = {int(b): i for i, b in enumerate(net.bus.index)}
+
+    def per_branch(mapping, arr, table, ends):
+        # a branch that is not in the ppc (out of service): pandapower never writes its rows of ppc['branch'], so
+        # its flows are 0 and its current 0 / |V| -- 0 between energised buses, NaN next to a dropped bus
+        # (results_branch.py `_get_branch_flows` [ext-mem])
+        live = np.array([all(ok[pos_of[int(net[table][c].iloc[i])]] for c in ends) for i in range(len(mapping))], bool) \
+            if len(mapping) else np.zeros(0, bool)
+        out = np.where(live, 0.0, np.nan).astype(arr.dtype)
         out[mapping >= 0] = arr[mapping[mapping >= 0]]
         return out
 
     for table, mapping, (a, b) in (("line", ppc.line_branch, ("from", "to")),
                                    ("trafo", ppc.trafo_branch, ("hv", "lv"))):
-        sf = per_branch(mapping, res["Sf"])
-        st = per_branch(mapping, res["St"])
+        ends = (f"{a}_bus", f"{b}_bus")
+        sf = per_branch(mapping, res["Sf"], table, ends)
+        st = per_branch(mapping, res["St"], table, ends)
         df = pd.DataFrame({
             f"p_{a}_mw": sf.real, f"q_{a}_mvar": sf.imag,
             f"p_{b}_mw": st.real, f"q_{b}_mvar": st.imag,
             "pl_mw": (sf + st).real, "ql_mvar": (sf + st).imag,
-            "loading_percent": per_branch(mapping, loading)}, index=net[table].index)
+            "loading_percent": per_branch(mapping, loading, table, ends)}, index=net[table].index)
         net["res_" + table] = df
     gen = res["gen"]
     eg = ppc.ext_grid_gen

@@ -37,6 +37,7 @@ for _ in range(10): h.copy_(obs, non_blocking=True)
 e1.record(); torch.cuda.synchronize()
 print(f"obs D2H {e0.elapsed_time(e1)/10:.3f} ms for {obs.numel()*obs.element_size()/1e6:.1f} MB")
 # device-only step with sync each step (no host copies)
+env.reset(seed=2)
 a = h_act.cuda()
 torch.cuda.synchronize(); t0 = time.perf_counter()
 for _ in range(N):
