@@ -107,7 +107,6 @@ typedef struct {
     int32_t radial_lanes_per_env, radial_envs_per_cta, radial_smem_bytes_per_env;
     int32_t n_island_critical; /* dynamic branches whose outage can cut buses off (spanning-tree edges): only then
                                   does opfg_assemble walk the grid of an environment                     */
-    int32_t dc_in_assemble, reserved1; /* 1: opfg_assemble can produce the DC start (OpfgBatch.dc_in_assemble)  */
 } OpfgGridInfo;
 
 /* action application + Sbus scatter (kernel 1) */
@@ -245,11 +244,6 @@ typedef struct {
     int32_t stats_slots;            /* > 1: `stats` is [stats_slots][OPFG_N_STATS] and environment b adds to
                                        row b % stats_slots (the caller sums the rows); thousands of
                                        atomics on ONE row serialise in L2 (0.11 ms of kernel 5 at 32 768 envs) */
-    int32_t dc_in_assemble;         /* != 0, and the grid supports it (OpfgGridInfo.dc_in_assemble: radial grids):
-                                       opfg_assemble also writes the DC start angles (pandapower init='dc') into `va`,
-                                       and opfg_pf_solve called with the same flag takes them from there instead of
-                                       computing them itself.  0: opfg_pf_solve is self-contained (default).       */
-    int32_t reserved_;
 } OpfgBatch;
 
 enum { OPFG_STAT_N = 0, OPFG_STAT_CONVERGED = 1, OPFG_STAT_VALID = 2, OPFG_STAT_SUM_REWARD = 3,

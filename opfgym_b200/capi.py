@@ -39,8 +39,7 @@ class GridInfo(C.Structure):
                [(n, C.c_int32) for n in ("pf_kernel_used", "lane_max_row", "lane_warps_per_cta",
                                          "lane_tables_staged")] + [("lane_scratch_bytes", C.c_double)] + \
                [(n, C.c_int32) for n in ("radial_lanes_per_env", "radial_envs_per_cta",
-                                         "radial_smem_bytes_per_env", "n_island_critical",
-                                         "dc_in_assemble", "reserved1")]
+                                         "radial_smem_bytes_per_env", "n_island_critical")]
 
 
 class AssemblyDesc(C.Structure):
@@ -97,8 +96,7 @@ class Batch(C.Structure):
                 ("actions", "state", "sbus", "vm", "va", "converged", "iterations",
                  "reward", "objective", "penalty", "cost", "valids", "violations",
                  "penalties", "obs_f32", "obs_f64", "stats", "yval", "bry", "objective_offset")] + [
-                ("absolute_actions", C.c_int32), ("stats_slots", C.c_int32),
-                ("dc_in_assemble", C.c_int32), ("reserved_", C.c_int32)]
+                ("absolute_actions", C.c_int32), ("stats_slots", C.c_int32)]
 
 
 # every symbol include/opfg_b200.h declares: name -> (restype, argtypes)

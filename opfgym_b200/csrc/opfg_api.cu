@@ -542,18 +542,15 @@ __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
                  B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
 }
 // One warp per environment, W environments per CTA (lifts the 32-CTAs-per-SM limit on resident envs).
-__global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B, int dc_doubles) {
-    extern __shared__ __align__(16) double asm_sm[];     // DC start: n doubles per warp (dc_doubles, else nothing)
+__global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) {
     const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (env >= B.n_env) return;
     Ctx<32> cx{(int)(threadIdx.x & 31), nullptr, 0};
-    const bool dc = dc_doubles > 0 && B.va != nullptr;
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                  B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
                  B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
                  B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0,
-                 B.vm ? B.vm + env * (int64_t)g.nb : nullptr, dc ? B.va + env * (int64_t)g.nb : nullptr,
-                 dc ? asm_sm + (size_t)(threadIdx.x >> 5) * dc_doubles : nullptr);
+                 B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
 }
 __global__ void __launch_bounds__(128) k_score_warps(GridDev g, OpfgBatch B, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
@@ -567,8 +564,7 @@ __global__ void __launch_bounds__(128) k_score_warps(GridDev g, OpfgBatch B, int
 // Mixed batch (BASELINE config 4): ONE launch of kernel 1 / kernel 5 over several grids.  Every CTA looks
 // up its member (grid descriptor + batch, in device memory) from its block index; environments of
 // different grids therefore run side by side in one grid of CTAs, each with its own tables.
-__global__ void __launch_bounds__(128) k_assemble_mixed(const MixedMember* members, int n_members, int dc_doubles) {
-    extern __shared__ __align__(16) double asm_sm[];     // DC start of radial members: dc_doubles per warp
+__global__ void __launch_bounds__(128) k_assemble_mixed(const MixedMember* members, int n_members) {
     int m = 0;
     while (m + 1 < n_members && (int)blockIdx.x >= members[m].cta_end) ++m;
     const MixedMember& mm = members[m];
@@ -577,13 +573,11 @@ __global__ void __launch_bounds__(128) k_assemble_mixed(const MixedMember* membe
     const int64_t env = (int64_t)(blockIdx.x - mm.cta_begin) * 4 + (threadIdx.x >> 5);
     if (env >= B.n_env) return;
     Ctx<32> cx{(int)(threadIdx.x & 31), nullptr, 0};
-    const bool dc = B.dc_in_assemble && g.asm_dc && B.sbus && B.va && dc_doubles >= g.n;
     env_assemble(g, cx, B.actions ? B.actions + env * g.n_act : nullptr, B.state + env * (int64_t)g.n_state,
                  B.sbus ? B.sbus + env * (int64_t)g.nb * 2 : nullptr,
                  B.yval ? B.yval + env * (int64_t)g.nnz_y * 2 : nullptr,
                  B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0,
-                 B.vm ? B.vm + env * (int64_t)g.nb : nullptr, dc ? B.va + env * (int64_t)g.nb : nullptr,
-                 dc ? asm_sm + (size_t)(threadIdx.x >> 5) * dc_doubles : nullptr);
+                 B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
 }
 __global__ void __launch_bounds__(128) k_score_mixed(const MixedMember* members, int n_members) {
     extern __shared__ __align__(16) double sm[];
@@ -1145,7 +1139,6 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         }
         // ---- fused kernel for radial grids: every pivot has at most one later neighbour ----
         d.tr_ok = 0;
-        d.asm_dc = 0; d.asm_dc_inv = d.asm_dc_w = d.asm_dc_rhs0 = nullptr;
         {
             bool forest = pf_kernel != 1 && pf_kernel != 2 && d.n_qlim == 0 && nb < 65535;
             for (int k = 0; k < s.n && forest; ++k) forest = s.up_ptr[k + 1] - s.up_ptr[k] <= 1;
@@ -1186,18 +1179,6 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                 d.tab4_bytes = (int)((G->tab_used + 15) & ~size_t(15));
                 G->tab_base = keep_base; G->tab_cap = keep_cap; G->tab_used = keep_used;
                 d.tr_ok = 1;
-                // DC start in kernel 1 (OpfgBatch.dc_in_assemble): the same factor in plain global arrays (not in the
-                // staged arena: the radial kernel has no shared memory to spare for tables it does not read)
-                const bool dc_in_asm = getenv("OPFG_ASM_DC") ? atoi(getenv("OPFG_ASM_DC")) != 0 : true;
-                if (desc->init_dc && dc_ok && dc_in_asm) {
-                    std::vector<double> inv(s.n), w(s.n, 0.0);
-                    for (int k = 0; k < s.n; ++k) {
-                        inv[k] = dc_val[k];
-                        if (s.up_ptr[k + 1] > s.up_ptr[k]) w[k] = dc_val[s.up_w[s.up_ptr[k]]];
-                    }
-                    d.asm_dc_inv = G->up(inv); d.asm_dc_w = G->up(w); d.asm_dc_rhs0 = G->up(dc_rhs0);
-                    d.asm_dc = 1;
-                }
             }
         }
         if (const char* cv = getenv("OPFG_CARVEOUT")) G->carveout_pct = atoi(cv);
@@ -1605,7 +1586,6 @@ int opfg_grid_info(const OpfgGrid* G, OpfgGridInfo* o) {
         o->radial_lanes_per_env = G->tree_T; o->radial_envs_per_cta = G->tree_E;
         o->radial_smem_bytes_per_env = (int)(G->tree_env_doubles * 8);
         o->n_island_critical = G->n_crit;
-        o->dc_in_assemble = d.asm_dc;
         o->lane_max_row = d.ln_max_row; o->lane_warps_per_cta = G->lane_warps_per_cta; o->lane_tables_staged = G->lane_stage;
         o->lane_scratch_bytes = 8.0 * (double)G->lane_warp_doubles * std::max(1, G->lane_warps_per_cta * G->lane_ctas);
     }
@@ -1727,23 +1707,16 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
 #ifdef OPFG_HOSTSIM
     (void)stream;
     Ctx<1> cx;
-    const bool dc = B->dc_in_assemble && G->d.asm_dc && B->sbus && B->va;
-    std::vector<double> dc_scratch(G->d.n + 2);
     for (int64_t env = 0; env < B->n_env; ++env)
         env_assemble(G->d, cx, B->actions ? B->actions + env * G->d.n_act : nullptr,
                      B->state + env * (int64_t)G->d.n_state, B->sbus ? B->sbus + env * (int64_t)G->d.nb * 2 : nullptr,
                      B->yval ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr,
                      B->bry ? B->bry + env * (int64_t)G->d.n_dyn * 8 : nullptr, B->absolute_actions != 0,
-                     B->vm ? B->vm + env * (int64_t)G->d.nb : nullptr, dc ? B->va + env * (int64_t)G->d.nb : nullptr,
-                     dc ? dc_scratch.data() : nullptr);
+                     B->vm ? B->vm + env * (int64_t)G->d.nb : nullptr);
 #else
     {
         static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
-        // DC start of radial grids inside kernel 1 (OpfgBatch.dc_in_assemble): n doubles of shared memory per warp
-        const bool dc = B->dc_in_assemble && G->d.asm_dc && B->sbus && B->va;
-        const int dc_doubles = dc ? ((G->d.n + 1) & ~1) : 0;
-        k_assemble_warps<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, sizeof(double) * dc_doubles * warps,
-                           (cudaStream_t)stream>>>(G->d, *B, dc_doubles);
+        k_assemble_warps<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, 0, (cudaStream_t)stream>>>(G->d, *B);
     }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -1760,7 +1733,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
     (void)stream;
     Ctx<1> cx;
     std::vector<double> sm(pf_smem_doubles(G->d.n_blocks, G->d.n, G->d.nb, 32, G->d.n_qlim));
-    if (G->d.dc_pre && !(use_tree(G, B) && G->d.tr_dc) && !(B->dc_in_assemble && G->d.asm_dc)) {   // the dense DC pre-pass, as a plain loop (unless kernel 1 or the radial kernel made the DC start)
+    if (G->d.dc_pre && !(use_tree(G, B) && G->d.tr_dc)) {   // the dense DC pre-pass, as a plain loop (the radial kernel has its own DC start)
         const GridDev& d = G->d;
         for (int64_t env = 0; env < B->n_env; ++env)
             for (int i = 0; i < d.n; ++i) {
@@ -1801,7 +1774,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
                      (G->d.n_dyn > 0 && B->yval) ? B->yval + env * (int64_t)G->d.nnz_y * 2 : nullptr, B->vm + env * (int64_t)G->d.nb,
                      B->va + env * (int64_t)G->d.nb, B->converged + env, B->iterations + env);
 #else
-    if (G->d.dc_pre && !(use_tree(G, B) && G->d.tr_dc) && !(B->dc_in_assemble && G->d.asm_dc)) {   // kernel 1 (dc_in_assemble) or the radial kernel (opt-in) made the DC start
+    if (G->d.dc_pre && !(use_tree(G, B) && G->d.tr_dc)) {   // the radial kernel has its own DC start
         ensure_dynamic_smem(k_dc_start, DC_SMEM);
         k_dc_start<<<dim3((unsigned)((B->n_env + DC_ENVS - 1) / DC_ENVS), (unsigned)((G->d.n + 63) / 64)), 256, DC_SMEM, (cudaStream_t)stream>>>(G->d, *B);
         ++g_launches;
@@ -1992,10 +1965,7 @@ static int mixed_launch(OpfgMixed* M, const OpfgBatch* batches, int which, void*
     // the member table travels on the same stream as the launch (a few KB)
     cudaMemcpyAsync(M->dev, M->host.data(), sizeof(MixedMember) * M->n, cudaMemcpyHostToDevice, (cudaStream_t)stream);
     if (which == 0) {
-        int dc_doubles = 0;                     // shared memory for the DC start of the radial members (per warp)
-        for (int m = 0; m < M->n; ++m)
-            if (M->host[m].B.dc_in_assemble && M->host[m].g.asm_dc) dc_doubles = std::max(dc_doubles, (M->host[m].g.n + 1) & ~1);
-        k_assemble_mixed<<<cta, 128, sizeof(double) * dc_doubles * 4, (cudaStream_t)stream>>>((const MixedMember*)M->dev, M->n, dc_doubles);
+        k_assemble_mixed<<<cta, 128, 0, (cudaStream_t)stream>>>((const MixedMember*)M->dev, M->n);
     } else {
         ensure_dynamic_smem(k_score_mixed, M->smem_score);
         k_score_mixed<<<cta, 128, M->smem_score, (cudaStream_t)stream>>>((const MixedMember*)M->dev, M->n);

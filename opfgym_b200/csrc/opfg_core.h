@@ -159,10 +159,6 @@ struct GridDev {
     // y_k = P_k + rhs0_k - sum_children W_c y_c;  theta_k = y_k / d_k - W_k theta_parent,  W_k = B'_kp / d_k
     int tr_dc;
     const double *tr_dc_inv, *tr_dc_w, *tr_dc_rhs0;
-    // ... or in kernel 1 (warp per environment, 30+ warps per SM hide the dependent phases that cost 110 us inside the
-    // persistent kernel): global copies of the factor; the tree tables above are read through L1
-    int asm_dc;
-    const double *asm_dc_inv, *asm_dc_w, *asm_dc_rhs0;
     const char* tab4_base;
     int tab4_bytes;
     const char* tab_base;              // contiguous arena holding the power-flow tables
@@ -354,45 +350,11 @@ OPFG_HD void gather_obs(const GridDev& g, const C& cx, const double* S, const Op
     }
 }
 
-// DC start of a radial grid (pandapower init='dc': B' theta = P): B' of a tree needs no fill, so the solve is one
-// upward and one downward sweep of scalars over the leaf-first levels.  y: n doubles of scratch (shared memory);
-// inv / w / rhs0: 1 / d_k, W_k = B'_kp / d_k and the constant part of the right-hand side of the leaf-first factor.
-template <class C>
-OPFG_HD void tree_dc_start(const GridDev& g, const C& cx, double* y, const double* sbus, double* va_out,
-                           const double* inv, const double* w, const double* rhs0) {
-    const int T = cx.nthreads(), n = g.n;
-    for (int k = cx.tid; k < n; k += T) y[k] = sbus[2 * g.tr_bus_of_int[k]] + rhs0[k];
-    cx.sync();
-    for (int l = 0; l < g.n_levels; ++l) {
-        const int le = g.tr_level_ptr[l + 1];
-        for (int k = g.tr_level_ptr[l] + cx.tid; k < le; k += T) {
-            double acc = y[k];
-            for (int e = g.tr_y_ptr[k] + 1; e < g.tr_y_ptr[k + 1]; ++e) {
-                const uint32_t ent = g.tr_y_ent[e];
-                if ((ent >> 16) == 1u) { const int j = (int)(ent & 0xffffu); acc = fma(-w[j], y[j], acc); }
-            }
-            y[k] = acc;
-        }
-        cx.sync();
-    }
-    for (int l = g.n_levels - 1; l >= 0; --l) {
-        const int le = g.tr_level_ptr[l + 1];
-        for (int k = g.tr_level_ptr[l] + cx.tid; k < le; k += T) {
-            const int p = g.tr_parent[k];
-            double x = y[k] * inv[k];
-            if (p >= 0) x = fma(-w[k], y[p], x);
-            y[k] = x;
-        }
-        cx.sync();
-    }
-    for (int k = cx.tid; k < n; k += T) va_out[g.tr_bus_of_int[k]] = y[k];
-}
-
 // --------------------------------------- kernel 1b: actions -> set-points -> Sbus
 template <class C>
 OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, double* S, double* sbus,
                           double* yval_env = nullptr, double* bry_env = nullptr, bool absolute = false,
-                          double* vm_out = nullptr, double* va_out = nullptr, double* dc_scratch = nullptr) {
+                          double* vm_out = nullptr) {
     const int T = cx.nthreads();
     for (int j = cx.tid; act != nullptr && j < g.n_act; j += T) {
         double a = act[j];
@@ -520,13 +482,6 @@ OPFG_HD void env_assemble(const GridDev& g, const C& cx, const double* act, doub
         }
         sbus[2 * bus] = p * inv_base;
         sbus[2 * bus + 1] = q * inv_base;
-    }
-    if (g.asm_dc && va_out && dc_scratch) {      // the DC start of this environment, while its injections are at hand
-        cx.sync();
-#ifdef OPFG_DEVICE_BUILD
-        __threadfence_block();
-#endif
-        tree_dc_start(g, cx, dc_scratch, sbus, va_out, g.asm_dc_inv, g.asm_dc_w, g.asm_dc_rhs0);
     }
 }
 

@@ -102,8 +102,6 @@ class Engine:
             obs_f32=self._ptr(self.obs) if obs_dtype == "float32" else None,
             obs_f64=self._ptr(self.obs) if obs_dtype == "float64" else None,
             stats=self._ptr(self.stats), stats_slots=self.STATS_SLOTS,
-            # radial grids: kernel 1 also produces the DC start, opfg_pf_solve skips its GEMM pre-pass
-            dc_in_assemble=int(self.info.get("dc_in_assemble", 0)),
             yval=self._ptr(self.yval) if self.yval is not None else None,
             bry=self._ptr(self.bry) if self.bry is not None else None)
         self.batch_final = capi.Batch.from_buffer_copy(self.batch)
@@ -288,19 +286,14 @@ class Engine:
             batch.absolute_actions = 1
         capi.check(self.lib, self.lib.opfg_assemble(self.handle, C.byref(batch), self._stream()))
 
-    def pf_solve(self, batch=None, fresh_dc_start=False):
-        """Kernels 2-4.  ``fresh_dc_start``: compute the DC start here even where kernel 1 already made it
-        (``dc_in_assemble``) -- for callers that changed ``sbus`` after ``assemble()``.  With ``self.pf_events`` set to a list, CUDA events bracketing the launch(es) on the
+    def pf_solve(self, batch=None):
+        """Kernels 2-4.  With ``self.pf_events`` set to a list, CUDA events bracketing the launch(es) on the
         launching stream are appended to it (bench.py's roofline)."""
         if self.pf_events is not None:
             e0 = self.torch.cuda.Event(enable_timing=True)
             e1 = self.torch.cuda.Event(enable_timing=True)
             e0.record()
-        batch = batch or self.batch
-        if fresh_dc_start and batch.dc_in_assemble:
-            batch = capi.Batch.from_buffer_copy(batch)
-            batch.dc_in_assemble = 0
-        capi.check(self.lib, self.lib.opfg_pf_solve(self.handle, C.byref(batch), self._stream()))
+        capi.check(self.lib, self.lib.opfg_pf_solve(self.handle, C.byref(batch or self.batch), self._stream()))
         if self.pf_events is not None:
             e1.record()
             self.pf_events.append((e0, e1))

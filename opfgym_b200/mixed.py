@@ -82,7 +82,7 @@ class MixedBatchEnv:
         batches = (capi.Batch * n)(*[e.engine.batch_final for e in self.envs])
         stream = self.envs[0].engine._stream()
         capi.check(lib, lib.opfg_assemble_mixed(h, batches, stream))
-        self._each(lambda i, e: e.engine.pf_solve(batches[i]))
+        self._each(lambda i, e: e.engine.pf_solve(e.engine.batch_final))
         capi.check(lib, lib.opfg_score_mixed(h, batches, stream))
         return [e._step_end(a) for e, a in zip(self.envs, acts)]
 

@@ -81,7 +81,7 @@ def _stress(engine_cls, name, n_env, lam, seed, sync=lambda: None, every=1):
     nan_envs = rng.choice(n_env, size=max(2, n_env // 128), replace=False)
     sbus[nan_envs, rng.integers(0, sbus.shape[1], len(nan_envs)), 0] = np.nan
     eng.sbus[:] = sbus if isinstance(eng.sbus, np.ndarray) else eng._from_numpy(sbus)
-    eng.pf_solve(fresh_dc_start=True)          # the injections changed after kernel 1 made its DC start
+    eng.pf_solve()
     sync()
     conv = common._np(eng.converged).astype(bool)
     iters = common._np(eng.iterations)

@@ -21,7 +21,7 @@ def _pair(engine_cls, name, n_env, seed, lam=None, sync=lambda: None, kernels=("
             f = np.random.default_rng(seed).uniform(lam[0], lam[1], n_env)
             sb = common._np(eng.sbus) * f[:, None, None]
             eng.sbus[:] = sb if isinstance(eng.sbus, np.ndarray) else eng._from_numpy(sb)
-        eng.pf_solve(fresh_dc_start=lam is not None)   # scaled injections: kernel 1's DC start is stale
+        eng.pf_solve()
         eng.score()
         sync()
         out[kernel] = {k: common._np(getattr(eng, k)).copy() for k in

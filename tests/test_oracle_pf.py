@@ -106,38 +106,3 @@ def test_nonconvergence_is_reported():
     from opfgym_b200.net import LoadflowNotConverged
     with pytest.raises(LoadflowNotConverged):
         pf.runpp(net)
-
-
-def _check_dc_start_of_kernel_1(engine_cls, sync=lambda: None):
-    """Radial grids: kernel 1 also produces pandapower's init='dc' start (B' theta = P as two sweeps over the
-    tree; OpfgBatch.dc_in_assemble).  Checked right after opfg_assemble against the oracle's sparse solve."""
-    from oracle import pf
-    from tests import common
-    case = common.make_case("1-MV-semiurb--1-sw")
-    eng = engine_cls(case.program, 9, obs_dtype="float64")
-    assert eng.info["dc_in_assemble"] == 1 and eng.batch.dc_in_assemble == 1
-    common.randomize(case, eng, seed=5)
-    eng.assemble()
-    sync()
-    va = common._np(eng.va)
-    ppc = case.program.ppc
-    from oracle import ppc_ref
-    for b in range(9):
-        net = common.oracle_env(case, eng, b)["net"]          # environment b's cells and set-points on a pandas net
-        ref = ppc_ref.build(net)                              # the oracle's own net -> ppc conversion
-        theta = pf.dc_angles(ref.base_mva, ref.bus, ref.gen, ref.branch)
-        lk_eng, lk_ref = ppc.bus_lookup, ref.bus_lookup
-        has = (lk_eng >= 0) & (lk_ref >= 0)
-        np.testing.assert_allclose(va[b][lk_eng[has]], theta[lk_ref[has]], atol=1e-12)
-
-
-def test_dc_start_of_kernel_1_hostsim():
-    from tests.hostsim.harness import TorchHostSimEngine
-    _check_dc_start_of_kernel_1(TorchHostSimEngine)
-
-
-@pytest.mark.gpu
-def test_dc_start_of_kernel_1_cuda(cuda_lib):
-    import torch
-    from opfgym_b200.engine import Engine
-    _check_dc_start_of_kernel_1(Engine, torch.cuda.synchronize)
