@@ -297,6 +297,19 @@ class Compiler:
                 inj_p.append(self.value_ref(table, "p_mw", pos))
                 inj_q.append(self.value_ref(table, "q_mvar", pos))
                 inj_c.append(self.consts.ref(coef))
+        if len(net.ward):
+            # constant-power part of a ward: a load without a scaling column (its pz / qz sit in the bus shunt)
+            buses = self.builder.element_bus(net, "ward")
+            if self.layout.has("ward", "in_service") or self.layout.has("ward", "pz_mw") \
+                    or self.layout.has("ward", "qz_mvar"):
+                raise NotImplementedError("per-environment ward.in_service / pz_mw / qz_mvar")
+            for pos in range(len(net.ward)):
+                if buses[pos] < 0:
+                    continue
+                inj_bus.append(buses[pos])
+                inj_p.append(self.value_ref("ward", "ps_mw", pos))
+                inj_q.append(self.value_ref("ward", "qs_mvar", pos))
+                inj_c.append(self.consts.ref(-float(bool(net.ward.in_service.iloc[pos]))))
         for pos, g in enumerate(ppc.gen_gen):
             if g < 0:
                 continue

@@ -38,6 +38,8 @@ _TABLES = {
             "scaling", "slack", "in_service"],
     "ext_grid": ["name", "bus", "vm_pu", "va_degree", "in_service"],
     "shunt": ["name", "bus", "p_mw", "q_mvar", "vn_kv", "step", "in_service"],
+    "ward": ["name", "bus", "ps_mw", "qs_mvar", "pz_mw", "qz_mvar", "in_service"],
+    "impedance": ["name", "from_bus", "to_bus", "rft_pu", "xft_pu", "rtf_pu", "xtf_pu", "sn_mva", "in_service"],
     "switch": ["bus", "element", "et", "closed"],
     "poly_cost": ["element", "et", "cp0_eur", "cp1_eur_per_mw",
                   "cp2_eur_per_mw2", "cq0_eur", "cq1_eur_per_mvar",
@@ -255,6 +257,21 @@ def create_shunt(net, bus, q_mvar, p_mw=0.0, **cols) -> int:
             "vn_kv": [vn]}
     data.update({k: [v] for k, v in cols.items()})
     return int(_bulk(net, "shunt", data)[0])
+
+
+def create_ward(net, bus, ps_mw, qs_mvar, pz_mw, qz_mvar, **cols) -> int:
+    data = {"bus": [int(bus)], "ps_mw": [float(ps_mw)], "qs_mvar": [float(qs_mvar)], "pz_mw": [float(pz_mw)],
+            "qz_mvar": [float(qz_mvar)]}
+    data.update({k: [v] for k, v in cols.items()})
+    return int(_bulk(net, "ward", data)[0])
+
+
+def create_impedance(net, from_bus, to_bus, rft_pu, xft_pu, sn_mva, rtf_pu=None, xtf_pu=None, **cols) -> int:
+    data = {"from_bus": [int(from_bus)], "to_bus": [int(to_bus)], "rft_pu": [float(rft_pu)], "xft_pu": [float(xft_pu)],
+            "rtf_pu": [float(rft_pu if rtf_pu is None else rtf_pu)], "xtf_pu": [float(xft_pu if xtf_pu is None else xtf_pu)],
+            "sn_mva": [float(sn_mva)]}
+    data.update({k: [v] for k, v in cols.items()})
+    return int(_bulk(net, "impedance", data)[0])
 
 
 def create_switch(net, bus, element, et, closed=True) -> int:

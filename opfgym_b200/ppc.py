@@ -64,6 +64,7 @@ class Ppc:
     rate_t: np.ndarray
     init_vm_pu: float = 1.0
     meta: dict = field(default_factory=dict)
+    impedance_branch: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # net.impedance position -> branch row
 
     @property
     def nb(self):
@@ -90,7 +91,7 @@ class _DSU:
                 self.p[ra] = rb
 
 
-UNSUPPORTED_TABLES = ("trafo3w", "impedance", "ward", "xward", "dcline", "motor", "asymmetric_load",
+UNSUPPORTED_TABLES = ("trafo3w", "xward", "dcline", "motor", "asymmetric_load",
                       "asymmetric_sgen", "svc", "tcsc", "ssc", "vsc")
 
 
@@ -118,7 +119,7 @@ class PpcBuilder:
             if df is not None and len(df):
                 raise NotImplementedError(
                     f"net.{table} has {len(df)} rows: {table} elements are not modelled by PpcBuilder "
-                    "(supported: bus, line, trafo, switch, load, sgen, storage, gen, ext_grid, shunt)")
+                    "(supported: bus, line, trafo, impedance, switch, load, sgen, storage, ward, gen, ext_grid, shunt)")
         self._analyse(net)
 
     # ------------------------------------------------------------------ topology
@@ -194,8 +195,23 @@ class PpcBuilder:
             k += 1
         n_nodes = n_pp + n_aux
 
+        # impedance elements (pandapower build_branch._calc_impedance_parameter): plain series branches
+        imp = getattr(net, "impedance", None)
+        ni = len(imp) if imp is not None else 0
+        if ni:
+            imf = np.array([pos_of[int(b)] for b in imp.from_bus.to_numpy()], dtype=np.int64)
+            imt = np.array([pos_of[int(b)] for b in imp.to_bus.to_numpy()], dtype=np.int64)
+            i_in = imp.in_service.to_numpy(bool) & bus_in[imf] & bus_in[imt]
+        else:
+            imf = imt = np.zeros(0, np.int64)
+            i_in = np.zeros(0, bool)
+
         # connectivity from in-service ext_grid buses
         adj = [[] for _ in range(n_nodes)]
+        for i in np.nonzero(i_in)[0]:
+            a, b = root[imf[i]], root[imt[i]]
+            adj[a].append(b)
+            adj[b].append(a)
         for i in np.nonzero(l_in)[0]:
             adj[node_f[i]].append(node_t[i])
             adj[node_t[i]].append(node_f[i])
@@ -244,6 +260,13 @@ class PpcBuilder:
         self.line_branch[self.line_pos] = np.arange(len(self.line_pos))
         self.trafo_branch = -np.ones(nt, dtype=np.int64)
         self.trafo_branch[self.trafo_pos] = len(self.line_pos) + np.arange(len(self.trafo_pos))
+        if ni:
+            i_in &= (node_id[root[imf]] >= 0) & (node_id[root[imt]] >= 0)
+        self.imp_pos = np.nonzero(i_in)[0]
+        self.imp_f = node_id[root[imf[self.imp_pos]]] if ni else np.zeros(0, np.int64)
+        self.imp_t = node_id[root[imt[self.imp_pos]]] if ni else np.zeros(0, np.int64)
+        self.impedance_branch = -np.ones(ni, dtype=np.int64)
+        self.impedance_branch[self.imp_pos] = len(self.line_pos) + len(self.trafo_pos) + np.arange(len(self.imp_pos))
         self.n_pp_bus = n_pp
 
     def element_bus(self, net, table) -> np.ndarray:
@@ -254,13 +277,13 @@ class PpcBuilder:
     # ------------------------------------------------------------------- numbers
     def branch_table(self, net) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         sn = net.sn_mva
-        nl, nt = len(self.line_pos), len(self.trafo_pos)
-        br = np.zeros((nl + nt, BRANCH_COLS))
+        nl, nt, ni = len(self.line_pos), len(self.trafo_pos), len(self.imp_pos)
+        br = np.zeros((nl + nt + ni, BRANCH_COLS))
         br[:, TAP] = 1.0
         br[:, BR_STATUS] = 1.0
         br[:, ANGMIN], br[:, ANGMAX] = -360.0, 360.0
-        rate_f = np.zeros(nl + nt)
-        rate_t = np.zeros(nl + nt)
+        rate_f = np.zeros(nl + nt + ni)
+        rate_t = np.zeros(nl + nt + ni)
         if nl:
             ln = net.line.iloc[self.line_pos]
             vn_f = self.base_kv[self.line_f]
@@ -343,6 +366,19 @@ class PpcBuilder:
             # trafo_loading='current': 100*max(i_hv*vn_hv, i_lv*vn_lv)*sqrt3/sn
             rate_f[sl] = tr.vn_hv_kv.to_numpy(float) / (vn_hv_bus * sn_t * par * df)
             rate_t[sl] = tr.vn_lv_kv.to_numpy(float) / (vn_lv_bus * sn_t * par * df)
+        if ni:
+            # pandapower build_branch._calc_impedance_parameter [ext-mem]: per unit on the element's own
+            # sn_mva, rescaled to the net's; no shunt part, ratio 1, no rating (res_impedance has no loading)
+            im = net.impedance.iloc[self.imp_pos]
+            k = sn / im.sn_mva.to_numpy(float)
+            rft, xft = im.rft_pu.to_numpy(float) * k, im.xft_pu.to_numpy(float) * k
+            rtf, xtf = im.rtf_pu.to_numpy(float) * k, im.xtf_pu.to_numpy(float) * k
+            if not (np.array_equal(rft, rtf) and np.array_equal(xft, xtf)):
+                raise NotImplementedError("net.impedance with rtf_pu != rft_pu or xtf_pu != xft_pu: the branch "
+                                          "model of the kernels is symmetric (pandapower's BR_R_ASYM / BR_X_ASYM)")
+            sl = slice(nl + nt, nl + nt + ni)
+            br[sl, F_BUS], br[sl, T_BUS] = self.imp_f, self.imp_t
+            br[sl, BR_R], br[sl, BR_X] = rft, xft
         return br, rate_f, rate_t
 
     def build(self, net) -> Ppc:
@@ -373,6 +409,17 @@ class PpcBuilder:
             step = df.step.to_numpy(float)
             bus[:, GS] += np.bincount(b[ok], (df.p_mw.to_numpy(float) * step * ratio)[ok], nb)
             bus[:, BS] -= np.bincount(b[ok], (df.q_mvar.to_numpy(float) * step * ratio)[ok], nb)
+
+        if len(net.ward):
+            # pandapower build_bus: ps/qs join the loads (_calc_pq_elements_and_add_on_ppc), pz/qz the shunts
+            # at the bus's own rated voltage (_calc_shunts_and_add_on_ppc) [ext-mem]
+            df = net.ward
+            b = self.element_bus(net, "ward")
+            ok = (b >= 0) & df.in_service.to_numpy(bool)
+            bus[:, PD] += np.bincount(b[ok], df.ps_mw.to_numpy(float)[ok], nb)
+            bus[:, QD] += np.bincount(b[ok], df.qs_mvar.to_numpy(float)[ok], nb)
+            bus[:, GS] += np.bincount(b[ok], df.pz_mw.to_numpy(float)[ok], nb)
+            bus[:, BS] -= np.bincount(b[ok], df.qz_mvar.to_numpy(float)[ok], nb)
 
         # generators: ext_grids (REF) first, then gens (PV)
         eg, gn = net.ext_grid, net.gen
@@ -420,7 +467,8 @@ class PpcBuilder:
                    line_branch=self.line_branch.copy(),
                    trafo_branch=self.trafo_branch.copy(),
                    ext_grid_gen=ext_grid_gen, gen_gen=gen_gen,
-                   rate_f=rate_f, rate_t=rate_t, init_vm_pu=init_vm)
+                   rate_f=rate_f, rate_t=rate_t, init_vm_pu=init_vm,
+                   impedance_branch=self.impedance_branch.copy())
 
 
 def build_ppc(net, **kwargs) -> Ppc:

@@ -98,6 +98,10 @@ def build(net, calculate_voltage_angles=True, trafo_model="t"):
         if not (bool(tr["in_service"]) and in_service[hb] and in_service[lb]) or int(idx) in open_trafos:
             continue
         edges.append(("trafo", int(idx), ("bus", find(hb)), ("bus", find(lb)), tr))
+    for idx, im in (_rows(net.impedance) if len(getattr(net, "impedance", ())) else []):
+        fb, tb = int(im["from_bus"]), int(im["to_bus"])
+        if bool(im["in_service"]) and in_service[fb] and in_service[tb]:
+            edges.append(("impedance", int(idx), ("bus", find(fb)), ("bus", find(tb)), im))
 
     # ---- connectivity (pd2ppc.py: _check_connectivity): only what hangs on a slack survives;
     # the walk order IS this builder's bus numbering ----
@@ -160,6 +164,16 @@ def build(net, calculate_voltage_angles=True, trafo_model="t"):
         bus[k, GS] += float(sh["p_mw"]) * float(sh["step"]) * v_ratio
         bus[k, BS] -= float(sh["q_mvar"]) * float(sh["step"]) * v_ratio
 
+    for _, w in (_rows(net.ward) if len(getattr(net, "ward", ())) else []):
+        # a ward = constant power (joins PD/QD) + constant impedance rated at the bus voltage (joins GS/BS)
+        k = ppc_bus(w["bus"])
+        if k < 0 or not bool(w["in_service"]):
+            continue
+        bus[k, PD] += float(w["ps_mw"])
+        bus[k, QD] += float(w["qs_mvar"])
+        bus[k, GS] += float(w["pz_mw"])
+        bus[k, BS] -= float(w["qz_mvar"])
+
     # ---- generators (build_gen.py): ext_grid rows (REF), then gen rows (PV) ----
     gen_rows, ext_grid_gen, gen_gen = [], {}, {}
     for idx, eg in _rows(net.ext_grid):
@@ -204,6 +218,9 @@ def build(net, calculate_voltage_angles=True, trafo_model="t"):
     branch_rows, rate_f, rate_t = [], [], []
     line_branch = {int(i): -1 for i in net.line.index}
     trafo_branch = {int(i): -1 for i in net.trafo.index}
+    impedance_branch = {int(i): -1 for i in (net.impedance.index if len(getattr(net, "impedance", ())) else [])}
+    # pandapower stacks the branch table by element type: lines, transformers, impedances
+    edges.sort(key=lambda e: ("line", "trafo", "impedance").index(e[0]))
     for kind, idx, a, b, el in edges:
         if a not in number or b not in number:
             continue
@@ -224,6 +241,16 @@ def build(net, calculate_voltage_angles=True, trafo_model="t"):
             rate_f.append(1.0 / (math.sqrt(3.0) * base_kv[fa] * i_max))
             rate_t.append(1.0 / (math.sqrt(3.0) * base_kv[tb] * i_max))
             line_branch[idx] = len(branch_rows)
+        elif kind == "impedance":                            # _calc_impedance_parameter
+            scale = sn / float(el["sn_mva"])
+            z_ft = complex(float(el["rft_pu"]), float(el["xft_pu"])) * scale
+            z_tf = complex(float(el["rtf_pu"]), float(el["xtf_pu"])) * scale
+            if z_ft != z_tf:
+                raise NotImplementedError("asymmetric impedance element")
+            row[BR_R], row[BR_X] = z_ft.real, z_ft.imag
+            rate_f.append(0.0)
+            rate_t.append(0.0)
+            impedance_branch[idx] = len(branch_rows)
         else:                                                # _calc_branch_values_from_trafo_df
             vn_hv_bus, vn_lv_bus = base_kv[fa], base_kv[tb]
             vn_hv, vn_lv = float(el["vn_hv_kv"]), float(el["vn_lv_kv"])
@@ -275,6 +302,8 @@ def build(net, calculate_voltage_angles=True, trafo_model="t"):
         line_branch=as_array(line_branch, net.line.index), trafo_branch=as_array(trafo_branch, net.trafo.index),
         ext_grid_gen=as_array(ext_grid_gen, net.ext_grid.index),
         gen_gen=as_array(gen_gen, net.gen.index) if len(net.gen) else np.zeros(0, np.int64),
+        impedance_branch=as_array(impedance_branch, net.impedance.index) if impedance_branch
+        else np.zeros(0, np.int64),
         rate_f=np.array(rate_f), rate_t=np.array(rate_t))
 
 
