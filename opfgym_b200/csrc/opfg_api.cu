@@ -124,6 +124,7 @@ struct OpfgGrid {
     bool has_assembly = false, has_scoring = false;
     int act_ref_max = -1, obs_ref_max = -1;   // largest state cell the action / observation tables touch
     size_t smem_pf = 0, smem_score = 0;
+    int n_blocks_sym = 0;          // blocks of the filled Jacobian (d.n_blocks counts storage slots)
     int carveout_pct = -1;   // -1: leave the driver's default L1/shared split
     int envs_per_cta = 1;
     // lane-per-environment kernel: schedule, per-warp scratch in global memory, launch shape
@@ -959,19 +960,89 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         d.type_int = G->tab(type_int);
         d.level_ptr = G->tab(s.level_ptr); d.fill_ids = G->tab(s.fill_ids);
         if (s.n_blocks >= 65535 || nb >= 65535) { delete G; return fail("grid too large for 16-bit schedule ids (%d blocks)", s.n_blocks); }
+        const bool dc_prepass = getenv("OPFG_DC_PREPASS") ? atoi(getenv("OPFG_DC_PREPASS")) != 0 : true;
         {   // pack the schedule into 16-bit ids (halves the L1 footprint of the shared tables)
+            // ---- storage slots of the blocks (meshed grids) ----
+            // A block id names a 2x2 block of the filled Jacobian; the kernel addresses shared memory by SLOT.
+            // A fill block does not exist before the off-diagonal item that forms it runs (level of its
+            // pivot), and an L~ block is dead once the last item that gathers with it has run (at the latest
+            // the level of its row: the right-hand side is carried along, the backward sweep reads W only).
+            // So a fill block born in level l takes the slot of a block last read in a level < l (the
+            // barrier between two levels orders the last read before the first write): 1 899 blocks ->
+            // 1 449 slots on the 372-bus grid, 75.7 -> 61.3 KB per environment -- a THIRD environment per SM.
+            // Only addresses change: every sum keeps its operands and its order (same bits).
+            std::vector<int> slot(s.n_blocks);
+            for (int b = 0; b < s.n_blocks; ++b) slot[b] = b;
+            std::vector<char> is_fill(s.n_blocks, 0);
+            for (int f : s.fill_ids) is_fill[f] = 1;
+            int n_slots = s.n_blocks;
+            // the DC start inside the kernel indexes its static factor by the packed ids: no sharing then
+            const bool share_slots = (getenv("OPFG_SHARE_SLOTS") ? atoi(getenv("OPFG_SHARE_SLOTS")) != 0 : true) &&
+                                     !s.fill_ids.empty() && (dc_prepass || !desc->init_dc);
+            if (share_slots) {
+                const int NEVER = 1 << 30;
+                std::vector<int> level_of(s.n, 0), last(s.n_blocks, -1), born(s.n_blocks, -1);
+                for (int l = 0; l < s.n_levels; ++l)
+                    for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) level_of[k] = l;
+                auto read_at = [&](int b, int l) { if (last[b] < l) last[b] = l; };
+                for (int k = 0; k < s.n; ++k)
+                    for (int p = s.dp_ptr[k]; p < s.dp_ptr[k + 1]; ++p) { read_at(s.dp_l[p], level_of[k]); read_at(s.dp_w[p], level_of[k]); }
+                for (int l = 0; l < s.n_levels; ++l)
+                    for (int item = s.off_ptr[l]; item < s.off_ptr[l + 1]; ++item) {
+                        born[s.off_tgt[item]] = l;
+                        read_at(s.off_tgt[item], l);
+                        for (int p = s.op_ptr[item]; p < s.op_ptr[item + 1]; ++p) { read_at(s.op_l[p], l); read_at(s.op_w[p], l); }
+                    }
+                for (int w : s.up_w) last[w] = NEVER;                       // backward sweep
+                bool ok = true;
+                for (int f : s.fill_ids) ok = ok && born[f] >= 0 && f >= s.n;
+                if (ok) {
+                    int next = s.n;                                          // diagonals keep slot == pivot
+                    for (int b = s.n; b < s.n_blocks; ++b) if (!is_fill[b]) slot[b] = next++;   // written by the Jacobian pass
+                    std::vector<std::vector<int>> births(s.n_levels), deaths(s.n_levels);
+                    for (int b = s.n; b < s.n_blocks; ++b) {
+                        if (is_fill[b]) births[born[b]].push_back(b);
+                        if (last[b] >= 0 && last[b] < s.n_levels) deaths[last[b]].push_back(b);
+                    }
+                    std::vector<int> pool;
+                    for (int l = 0; l < s.n_levels; ++l) {
+                        for (int b : births[l]) {
+                            if (!pool.empty()) { slot[b] = pool.back(); pool.pop_back(); }
+                            else slot[b] = next++;
+                        }
+                        for (int b : deaths[l]) pool.push_back(slot[b]);
+                    }
+                    n_slots = next;
+                    // safety net: within one level no item may read a slot another item of that level writes
+                    std::vector<int> written_in(n_slots, -1);
+                    for (int l = 0; l < s.n_levels && ok; ++l) {
+                        for (int item = s.off_ptr[l]; item < s.off_ptr[l + 1]; ++item) written_in[slot[s.off_tgt[item]]] = l;
+                        for (int item = s.off_ptr[l]; item < s.off_ptr[l + 1] && ok; ++item)
+                            for (int p = s.op_ptr[item]; p < s.op_ptr[item + 1]; ++p)
+                                if (written_in[slot[s.op_l[p]]] == l || written_in[slot[s.op_w[p]]] == l) ok = false;
+                        for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1] && ok; ++k)   // next level's gathers vs this level's writes: other phase, but
+                            for (int p = s.dp_ptr[k]; p < s.dp_ptr[k + 1]; ++p)          // an operand must not have been overwritten in ITS level either
+                                if (written_in[slot[s.dp_l[p]]] == l || written_in[slot[s.dp_w[p]]] == l) ok = false;
+                    }
+                    if (!ok) { for (int b = 0; b < s.n_blocks; ++b) slot[b] = b; n_slots = s.n_blocks; }
+                }
+            }
+            G->n_blocks_sym = s.n_blocks;
+            d.n_blocks = n_slots;
             std::vector<U2> dp(s.dp_l.size()), hdr(s.off_tgt.size() + 1);
             std::vector<uint32_t> op(s.op_l.size()), upk(s.up_w.size());
             std::vector<U2> ym(s.y_col.size());
-            for (size_t i = 0; i < dp.size(); ++i) dp[i] = U2{(uint32_t)s.dp_l[i] | ((uint32_t)s.dp_w[i] << 16), (uint32_t)s.dp_m[i]};
+            for (size_t i = 0; i < dp.size(); ++i) dp[i] = U2{(uint32_t)slot[s.dp_l[i]] | ((uint32_t)slot[s.dp_w[i]] << 16), (uint32_t)s.dp_m[i]};
+            // bit 31 of the pair pointer: the target is a fill block -- it starts from zero instead of a stored value
             for (size_t i = 0; i < s.off_tgt.size(); ++i)
-                hdr[i] = U2{(uint32_t)s.off_tgt[i] | ((uint32_t)(s.off_piv[i] + 1) << 16), (uint32_t)s.op_ptr[i]};
+                hdr[i] = U2{(uint32_t)slot[s.off_tgt[i]] | ((uint32_t)(s.off_piv[i] + 1) << 16),
+                            (uint32_t)s.op_ptr[i] | (is_fill[s.off_tgt[i]] ? 0x80000000u : 0u)};
             hdr[s.off_tgt.size()] = U2{0u, (uint32_t)s.op_l.size()};
-            for (size_t i = 0; i < op.size(); ++i) op[i] = (uint32_t)s.op_l[i] | ((uint32_t)s.op_w[i] << 16);
-            for (size_t i = 0; i < upk.size(); ++i) upk[i] = (uint32_t)s.up_w[i] | ((uint32_t)s.up_j[i] << 16);
+            for (size_t i = 0; i < op.size(); ++i) op[i] = (uint32_t)slot[s.op_l[i]] | ((uint32_t)slot[s.op_w[i]] << 16);
+            for (size_t i = 0; i < upk.size(); ++i) upk[i] = (uint32_t)slot[s.up_w[i]] | ((uint32_t)s.up_j[i] << 16);
             for (int r = 0; r < nb; ++r)
                 for (int e = s.y_ptr[r]; e < s.y_ptr[r + 1]; ++e)
-                    ym[e] = U2{(uint32_t)s.y_col[e] | ((uint32_t)(s.y_blk[e] + 1) << 16), (uint32_t)r};
+                    ym[e] = U2{(uint32_t)s.y_col[e] | ((uint32_t)((s.y_blk[e] < 0 ? -1 : slot[s.y_blk[e]]) + 1) << 16), (uint32_t)r};
             d.nnz_y_nonref = s.y_ptr[s.n];
             // per level: one lane per pivot, or eight lanes per pivot (component-parallel gather)
             std::vector<unsigned char> mode(s.n_levels, 0);
@@ -979,7 +1050,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             // (meshed 372-bus grid: -7 %); with ten resident environments the kernel is bound by
             // shared-memory throughput and the extra partial-sum traffic costs 2 %.
             const bool eager = getenv("OPFG_EAGER_GATHER") ? atoi(getenv("OPFG_EAGER_GATHER")) != 0
-                             : pf_smem_doubles(s.n_blocks, s.n, nb, T, 0) * sizeof(double) * 4 > 227 * 1024;
+                             : pf_smem_doubles(n_slots, s.n, nb, T, 0) * sizeof(double) * 4 > 227 * 1024;
             if (!eager) {
                 for (int k = 0; k < s.n; ++k) s.dp_own[k] = s.dp_ptr[k];
                 s.eg_ptr.assign(s.n_levels + 1, 0);
@@ -1042,7 +1113,6 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
         // of dependent scalar work: 17 % of the kernel on the 372-bus grid (4.47 -> 3.82 ms with the
         // pre-pass), 11 % on the 122-bus grid (0.14 ms in the kernel against 0.08 ms for the GEMM).
         // B'^-1 is built column by column with the factor the kernel would use.
-        const bool dc_prepass = getenv("OPFG_DC_PREPASS") ? atoi(getenv("OPFG_DC_PREPASS")) != 0 : true;
         if (desc->init_dc && s.n > 0 && dc_prepass) {
             const int n = s.n, ld = (n + 63) / 64 * 64, kp = (nb + 15) / 16 * 16;   // rows: ppc bus order (coalesced P reads)
             std::vector<double> binv_t((size_t)kp * ld, 0.0), x(n), theta0(n, 0.0);
@@ -1182,7 +1252,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             }
         }
         if (const char* cv = getenv("OPFG_CARVEOUT")) G->carveout_pct = atoi(cv);
-        G->smem_pf = (pf_smem_doubles(s.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
+        G->smem_pf = (pf_smem_doubles(d.n_blocks, s.n, nb, T, d.n_qlim) * sizeof(double) + 31) & ~size_t(31);
         {   // environments per CTA: stage the tables in shared memory when several environments share them
             const size_t budget = 227 * 1024;
             const int cap = std::min(15, 768 / T);    // named barriers 1..15; k_pf_multi is bounded to 768 threads
@@ -1192,12 +1262,21 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             auto fit = [&](int bytes) { return (size_t)bytes < budget ? std::min((int)((budget - bytes) / G->smem_pf), cap) : 0; };
             const int sizes[3] = {d.tab_hot_bytes, d.tab_warm_bytes, d.tab_bytes};
             int level = fit(sizes[2]) >= 2 ? 2 : ((fit(sizes[1]) >= 2 && (size_t)sizes[1] * 3 <= budget) ? 1 : 0);
+            // with two environments per SM the kernel is latency-bound on 8 warps: a third environment is worth
+            // more than staged Ybus tables (372-bus grid, shared slots: 3 x 61 KB + the 34 KB LU schedule)
+            static const bool prefer_envs = getenv("OPFG_PREFER_ENVS") ? atoi(getenv("OPFG_PREFER_ENVS")) != 0 : true;
+            if (prefer_envs && fit(sizes[level]) <= 2)
+                for (int lv = level - 1; lv >= 0; --lv)
+                    if (fit(sizes[lv]) > fit(sizes[level])) level = lv;
             if (const char* sv = getenv("OPFG_STAGE")) level = std::max(0, std::min(2, atoi(sv)));
             d.tab_staged_bytes = sizes[level];
             int E = fit(sizes[level]);
             if (const char* ev = getenv("OPFG_ENVS_PER_CTA")) E = std::min(atoi(ev), E);   // can only lower it
             if (E < 2) E = 1;
             G->envs_per_cta = E;
+            if (getenv("OPFG_DEBUG_SCHEDULE"))
+                fprintf(stderr, "blocks %d slots %d: %zu B per environment, tables hot/warm/all %d/%d/%d B, staged level %d, %d environments per CTA\n",
+                        G->n_blocks_sym, d.n_blocks, G->smem_pf, sizes[0], sizes[1], sizes[2], level, E);
         }
         G->smem_score = score_smem_doubles(nb, nbr, T) * sizeof(double);
         if (G->smem_pf > 227 * 1024) { delete G; return fail("grid needs %zu B shared memory per environment (> 227 KB)", G->smem_pf); }
@@ -1572,7 +1651,7 @@ int opfg_grid_info(const OpfgGrid* G, OpfgGridInfo* o) {
     if (!G || !o) return fail("null argument");
     const GridDev& d = G->d;
     memset(o, 0, sizeof *o);
-    o->nb = d.nb; o->n_nonref = d.n; o->nnz_y = d.nnz_y; o->n_blocks = d.n_blocks; o->n_fill_blocks = d.n_fill;
+    o->nb = d.nb; o->n_nonref = d.n; o->nnz_y = d.nnz_y; o->n_blocks = G->n_blocks_sym; o->n_fill_blocks = d.n_fill;
     o->n_levels = d.n_levels; o->threads_per_env = d.threads;
     o->smem_bytes_pf = (int)G->smem_pf; o->smem_bytes_score = (int)G->smem_score;
     o->n_state = d.n_state; o->n_const = d.n_const; o->n_act = d.n_act; o->n_obs = d.n_obs; o->n_constraints = d.n_con;

@@ -652,10 +652,12 @@ OPFG_HD void lu_diag_finish(const PfSmem& s, int k, int sub, double a, double b,
 
 OPFG_HD void lu_off_item(const GridDev& g, const PfSmem& s, int item) {
     const U2 hdr = g.off_hdr[item];
-    const int pe = (int)g.off_hdr[item + 1].y;
+    const int pe = (int)(g.off_hdr[item + 1].y & 0x7fffffffu);
     const int xi = 2 * (int)(hdr.x & 0xffffu);
-    D2 r0 = ld2(s.lu + xi), r1 = ld2(s.lu1 + xi);
-    for (int p = (int)hdr.y; p < pe; ++p) {
+    // a fill block (bit 31) has no stored value yet: its slot may still hold a block that died a level ago
+    D2 r0{0.0, 0.0}, r1{0.0, 0.0};
+    if (!(hdr.y >> 31)) { r0 = ld2(s.lu + xi); r1 = ld2(s.lu1 + xi); }
+    for (int p = (int)(hdr.y & 0x7fffffffu); p < pe; ++p) {
         const uint32_t id = g.op_pack[p];
         const int li = 2 * (int)(id & 0xffffu), wi = 2 * (int)(id >> 16);
         const D2 l0 = ld2(s.lu + li), l1 = ld2(s.lu1 + li), w0 = ld2(s.lu + wi), w1 = ld2(s.lu1 + wi);
@@ -768,11 +770,7 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
             }
             if (jac) {
                 for (int e = cx.tid; e < g.nnz_y_nonref; e += T) jacobian_entry(g, s, yv, e);
-                for (int f = cx.tid; f < g.n_fill; f += T) {
-                    const int fi = 2 * g.fill_ids[f];
-                    st2(s.lu + fi, 0.0, 0.0);
-                    st2(s.lu1 + fi, 0.0, 0.0);
-                }
+                // fill blocks are not zeroed here: their item starts from zero (lu_off_item), their slot may be shared
             }
             nrm = cx.block_max(bad ? NAN : part);
             cx.sync();
