@@ -615,14 +615,14 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // Persistent multi-environment CTA: E environments of T threads each share ONE shared-memory copy of
 // the schedule / Ybus tables (their reads are on the critical path of every level); each environment
 // group synchronises on its own named barrier and walks through its share of the batch.
-// Tables of the staged arena, in allocation order: the LU schedule ("hot", always staged), the Ybus
-// tables ("warm", read in every iteration) and the start-value / DC-factor / q-limit tables ("cold",
+// Tables of the staged arena, in allocation order: the LU schedule and the Ybus index tables ("hot", always
+// staged), the Ybus values ("warm", read in every iteration) and the start-value / DC-factor / q-limit tables ("cold",
 // read once per solve).  STAGE = 0 stages the hot part, 1 hot + warm, 2 everything -- whichever lets
 // the most environments share an SM.
 #define OPFG_HOT_TABLES(X)                                                                      \
     X(bus_of_int) X(type_int) X(level_ptr) X(fill_ids) X(diag_mode) X(dp_ptr) X(dp_pack) X(dp_own) \
-    X(eg_ptr) X(eg_item) X(off_ptr) X(off_hdr) X(op_pack) X(up_ptr) X(up_pack)
-#define OPFG_WARM_TABLES(X) X(y_ptr) X(y_meta) X(y_val)
+    X(eg_ptr) X(eg_item) X(off_ptr) X(off_hdr) X(op_pack) X(up_ptr) X(up_pack) X(y_ptr) X(y_meta)
+#define OPFG_WARM_TABLES(X) X(y_val)
 #define OPFG_COLD_TABLES(X) X(vm0_int) X(va0_int) X(dc_val) X(dc_rhs0) X(qlim_bus) X(qlim_min) X(qlim_max)
 
 // The kernel receives a view of GridDev in which every staged table pointer holds its BYTE OFFSET in
@@ -1079,8 +1079,11 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             d.dp_own = G->tab(s.dp_own); d.eg_ptr = G->tab(s.eg_ptr); d.eg_item = G->tab(eg);
             d.off_ptr = G->tab(s.off_ptr); d.off_hdr = G->tab(hdr); d.op_pack = G->tab(op);
             d.up_ptr = G->tab(s.up_ptr); d.up_pack = G->tab(upk);
-            d.tab_hot_bytes = (int)((G->tab_used + 15) & ~size_t(15));   // LU schedule ends here
+            // the Ybus INDEX tables belong to the always-staged part: the row pass reads them in every iteration and
+            // every other load of an entry depends on them (their values can be requested ahead by entry number);
+            // on the 372-bus grid they are what still fits beside three environments (46 KB + 3 x 61 KB)
             d.y_ptr = G->tab(s.y_ptr); d.y_diag = G->up(s.y_diag); d.y_meta = G->tab(ym);
+            d.tab_hot_bytes = (int)((G->tab_used + 15) & ~size_t(15));   // LU schedule + Ybus index tables end here
         }
         d.yc_ptr = G->up(s.yc_ptr); d.yc_branch = G->up(s.yc_branch); d.yc_role = G->up(s.yc_role);
         d.br_param = G->up(br_param); d.bus_ysh = G->up(ysh); d.br_f = G->up(br_f); d.br_t = G->up(br_t);

@@ -650,29 +650,42 @@ OPFG_HD void lu_diag_finish(const PfSmem& s, int k, int sub, double a, double b,
     else if (sub == 5) s.rhs[2 * k + 1] = fma(ic, y0, id_ * y1);
 }
 
-OPFG_HD void lu_off_item(const GridDev& g, const PfSmem& s, int item) {
+// An off-diagonal item in two parts.  The GATHER (target -= sum L~ W over pairs from lower levels) depends on
+// nothing its own level produces, so it runs in the same phase as the level's diagonal items -- which leave most
+// lanes idle (a handful of pivots per level in the upper half of the elimination tree); the SCALE part of a U block
+// (W = D_k^-1 U) waits for the barrier behind the inversion of D_k and is short.  Same operations in the same
+// order as the one-piece item: same bits.
+OPFG_HD void lu_off_gather(const GridDev& g, const PfSmem& s, int item) {
     const U2 hdr = g.off_hdr[item];
     const int pe = (int)(g.off_hdr[item + 1].y & 0x7fffffffu);
+    int p = (int)(hdr.y & 0x7fffffffu);
+    const bool fill = (hdr.y >> 31) != 0;
+    if (p == pe && !fill) return;                             // a U block nothing updates: only scaled
     const int xi = 2 * (int)(hdr.x & 0xffffu);
     // a fill block (bit 31) has no stored value yet: its slot may still hold a block that died a level ago
     D2 r0{0.0, 0.0}, r1{0.0, 0.0};
-    if (!(hdr.y >> 31)) { r0 = ld2(s.lu + xi); r1 = ld2(s.lu1 + xi); }
-    for (int p = (int)(hdr.y & 0x7fffffffu); p < pe; ++p) {
+    if (!fill) { r0 = ld2(s.lu + xi); r1 = ld2(s.lu1 + xi); }
+    for (; p < pe; ++p) {
         const uint32_t id = g.op_pack[p];
         const int li = 2 * (int)(id & 0xffffu), wi = 2 * (int)(id >> 16);
         const D2 l0 = ld2(s.lu + li), l1 = ld2(s.lu1 + li), w0 = ld2(s.lu + wi), w1 = ld2(s.lu1 + wi);
         r0.x = fma(-l0.y, w1.x, fma(-l0.x, w0.x, r0.x));  r0.y = fma(-l0.y, w1.y, fma(-l0.x, w0.y, r0.y));
         r1.x = fma(-l1.y, w1.x, fma(-l1.x, w0.x, r1.x));  r1.y = fma(-l1.y, w1.y, fma(-l1.x, w0.y, r1.y));
     }
-    const int piv = (int)(hdr.x >> 16) - 1;
-    if (piv >= 0) {   // W = D^-1 * U
-        const D2 i0 = ld2(s.lu + 2 * piv), i1 = ld2(s.lu1 + 2 * piv);
-        const double a = fma(i0.x, r0.x, i0.y * r1.x), b = fma(i0.x, r0.y, i0.y * r1.y);
-        const double c = fma(i1.x, r0.x, i1.y * r1.x), d = fma(i1.x, r0.y, i1.y * r1.y);
-        r0.x = a; r0.y = b; r1.x = c; r1.y = d;
-    }
     st2(s.lu + xi, r0.x, r0.y);
     st2(s.lu1 + xi, r1.x, r1.y);
+}
+OPFG_HD void lu_off_scale(const GridDev& g, const PfSmem& s, int item) {
+    const uint32_t hx = g.off_hdr[item].x;
+    const int piv = (int)(hx >> 16) - 1;
+    if (piv < 0) return;                                      // L~ blocks stay unscaled
+    const int xi = 2 * (int)(hx & 0xffffu);
+    const D2 r0 = ld2(s.lu + xi), r1 = ld2(s.lu1 + xi);
+    const D2 i0 = ld2(s.lu + 2 * piv), i1 = ld2(s.lu1 + 2 * piv);   // W = D^-1 * U
+    const double a = fma(i0.x, r0.x, i0.y * r1.x), b = fma(i0.x, r0.y, i0.y * r1.y);
+    const double c = fma(i1.x, r0.x, i1.y * r1.x), d = fma(i1.x, r0.y, i1.y * r1.y);
+    st2(s.lu + xi, a, b);
+    st2(s.lu1 + xi, c, d);
 }
 
 OPFG_HD void bwd_item(const GridDev& g, const PfSmem& s, int k) {
@@ -770,7 +783,7 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
             }
             if (jac) {
                 for (int e = cx.tid; e < g.nnz_y_nonref; e += T) jacobian_entry(g, s, yv, e);
-                // fill blocks are not zeroed here: their item starts from zero (lu_off_item), their slot may be shared
+                // fill blocks are not zeroed here: their item starts from zero (lu_off_gather), their slot may be shared
             }
             nrm = cx.block_max(bad ? NAN : part);
             cx.sync();
@@ -805,9 +818,12 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
                     else lu_eager_item(g, s, g.eg_item[eb + idx - n_own]);
                 }
             }
+            // gathers of this level's off-diagonal items, from the far end of the lanes (the diagonals took the near end)
+            const int ob = g.off_ptr[l], oe = g.off_ptr[l + 1];
+            for (int item = ob + (T - 1 - cx.tid); item < oe; item += T) lu_off_gather(g, s, item);
             cx.sync();
             OPFG_TICK(16 + l);
-            for (int item = g.off_ptr[l] + cx.tid; item < g.off_ptr[l + 1]; item += T) lu_off_item(g, s, item);
+            for (int item = ob + (T - 1 - cx.tid); item < oe; item += T) lu_off_scale(g, s, item);
             cx.sync();
             OPFG_TICK(32 + l);
         }
