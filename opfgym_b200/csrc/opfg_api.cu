@@ -543,7 +543,10 @@ __global__ void __launch_bounds__(T) k_assemble(GridDev g, OpfgBatch B) {
                  B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
 }
 // One warp per environment, W environments per CTA (lifts the 32-CTAs-per-SM limit on resident envs).
-__global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) {
+// CAP: 0 = the compiler's default for 128-thread launches (56 / 62 registers); 3 = no occupancy target (70 / 72);
+// 1 / 2 / 4 = two-warp CTAs with at least 20 / 24 / 32 CTAs per SM (48 / 40 / 32 registers): both kernels wait on DRAM loads behind references, more resident warps = more loads in flight
+template <int CAP>
+__global__ void __launch_bounds__((CAP == 1 || CAP == 2 || CAP == 4) ? 64 : 128, CAP == 4 ? 32 : (CAP == 2 ? 24 : (CAP == 1 ? 20 : (CAP == 3 ? 1 : 0)))) k_assemble_warps(GridDev g, OpfgBatch B) {
     const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (env >= B.n_env) return;
     Ctx<32> cx{(int)(threadIdx.x & 31), nullptr, 0};
@@ -553,7 +556,8 @@ __global__ void __launch_bounds__(128) k_assemble_warps(GridDev g, OpfgBatch B) 
                  B.bry ? B.bry + env * (int64_t)g.n_dyn * 8 : nullptr, B.absolute_actions != 0,
                  B.vm ? B.vm + env * (int64_t)g.nb : nullptr);
 }
-__global__ void __launch_bounds__(128) k_score_warps(GridDev g, OpfgBatch B, int env_doubles) {
+template <int CAP>
+__global__ void __launch_bounds__((CAP == 1 || CAP == 2 || CAP == 4) ? 64 : 128, CAP == 4 ? 32 : (CAP == 2 ? 24 : (CAP == 1 ? 20 : (CAP == 3 ? 1 : 0)))) k_score_warps(GridDev g, OpfgBatch B, int env_doubles) {
     extern __shared__ __align__(16) double sm[];
     const int64_t env = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (env >= B.n_env) return;
@@ -1798,7 +1802,9 @@ int opfg_assemble(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
 #else
     {
         static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
-        k_assemble_warps<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, 0, (cudaStream_t)stream>>>(G->d, *B);
+        static int cap = getenv("OPFG_ASSEMBLE_CAP") ? atoi(getenv("OPFG_ASSEMBLE_CAP")) : 0;
+        void (*fn)(GridDev, OpfgBatch) = (warps == 2 && cap == 2) ? k_assemble_warps<2> : ((warps == 2 && cap == 1) ? k_assemble_warps<1> : (cap == 3 ? k_assemble_warps<3> : k_assemble_warps<0>));
+        fn<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, 0, (cudaStream_t)stream>>>(G->d, *B);
     }
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -1969,8 +1975,11 @@ int opfg_score(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
         if (TT == 32) {
             static int warps = getenv("OPFG_AUX_WARPS") ? atoi(getenv("OPFG_AUX_WARPS")) : 2;
             const size_t per_env = (smem + 15) & ~size_t(15);
-            ensure_dynamic_smem(k_score_warps, per_env * warps);
-            k_score_warps<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, per_env * warps, (cudaStream_t)stream>>>(
+            // measured (122-bus grid, 32 768 environments): 56 registers 234 us, 48 -> 217, 40 -> 210, 70 -> 254
+            static int cap = getenv("OPFG_SCORE_CAP") ? atoi(getenv("OPFG_SCORE_CAP")) : 2;
+            void (*fn)(GridDev, OpfgBatch, int) = (warps == 2 && cap == 4) ? k_score_warps<4> : (warps == 2 && cap == 2) ? k_score_warps<2> : ((warps == 2 && cap == 1) ? k_score_warps<1> : (cap == 3 ? k_score_warps<3> : k_score_warps<0>));
+            ensure_dynamic_smem(fn, per_env * warps);
+            fn<<<(unsigned)((B->n_env + warps - 1) / warps), 32 * warps, per_env * warps, (cudaStream_t)stream>>>(
                 G->d, *B, (int)(per_env / 8));
         } else {
             k_score<TT><<<(unsigned)B->n_env, TT, smem, (cudaStream_t)stream>>>(G->d, *B);

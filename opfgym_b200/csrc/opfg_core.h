@@ -1488,6 +1488,23 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     const double* vm = B.vm + env * (int64_t)nb;
     const double* va = B.va + env * (int64_t)nb;
     const double* sbus = B.sbus + env * (int64_t)nb * 2;
+#ifdef OPFG_DEVICE_BUILD
+    // (issued before the converged flag is looked at: the flag costs a DRAM round trip of its own)
+    // the row is read piecemeal through references below: pull what will be read towards the SM now --
+    // the observation runs if the observation is made of runs (the whole 10 KB row used to be fetched:
+    // 348 MB per launch of 32 768 environments, two thirds of it never read), else the whole row
+    if (g.score_prefetch == 2 && g.n_obs_runs > 0) {
+        for (int r = 0; r < g.n_obs_runs; ++r) {
+            const char* p0 = reinterpret_cast<const char*>(S + g.obs_runs[3 * r]);
+            const int bytes = g.obs_runs[3 * r + 2] * 8;
+            for (int off = cx.tid * 128; off < bytes + 127; off += T * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (off < bytes ? off : bytes - 1)));
+        }
+    } else if (g.score_prefetch != 0) {
+        for (int off = cx.tid * 128; off < g.n_state * 8; off += T * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S) + off));
+    }
+#endif
     const bool conv = B.converged[env] != 0;
     const double base = g.base_mva;
     const double* yv = yval_env ? yval_env : g.y_val;
@@ -1517,29 +1534,27 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
         return;
     }
 
-#ifdef OPFG_DEVICE_BUILD
-    // the row is read piecemeal through references below: pull what will be read towards the SM now --
-    // the observation runs if the observation is made of runs (the whole 10 KB row used to be fetched:
-    // 348 MB per launch of 32 768 environments, two thirds of it never read), else the whole row
-    if (g.score_prefetch == 2 && g.n_obs_runs > 0) {
-        for (int r = 0; r < g.n_obs_runs; ++r) {
-            const char* p0 = reinterpret_cast<const char*>(S + g.obs_runs[3 * r]);
-            const int bytes = g.obs_runs[3 * r + 2] * 8;
-            for (int off = cx.tid * 128; off < bytes + 127; off += T * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (off < bytes ? off : bytes - 1)));
+    // four buses per lane and trip: all eight loads are requested before the first sincos waits for one
+    // (one DRAM round trip per trip instead of four; 17 % of this kernel's stall samples sat on these loads)
+    for (int i0 = cx.tid; i0 < nb; i0 += 4 * T) {
+        double m4[4], a4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * T;
+            m4[u] = i < nb ? vm[i] : 1.0;
+            a4[u] = i < nb ? va[i] : 0.0;
         }
-    } else if (g.score_prefetch != 0) {
-        for (int off = cx.tid * 128; off < g.n_state * 8; off += T * 128)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(S) + off));
-    }
-#endif
-    for (int i = cx.tid; i < nb; i += T) {
-        double sn, cs;
-        const bool dead = g.isl && vm[i] != vm[i];          // dropped bus (island): V = 0 towards its neighbours, NaN results
-        sincos(dead ? 0.0 : va[i], &sn, &cs);
-        s.vm[i] = vm[i];
-        s.vr[i] = dead ? 0.0 : vm[i] * cs;
-        s.vi[i] = dead ? 0.0 : vm[i] * sn;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * T;
+            if (i >= nb) break;
+            double sn, cs;
+            const bool dead = g.isl && m4[u] != m4[u];      // dropped bus (island): V = 0 towards its neighbours, NaN results
+            sincos(dead ? 0.0 : a4[u], &sn, &cs);
+            s.vm[i] = m4[u];
+            s.vr[i] = dead ? 0.0 : m4[u] * cs;
+            s.vi[i] = dead ? 0.0 : m4[u] * sn;
+        }
     }
     cx.sync();
     // branch flows and loading (pfsoln + results_branch.py [ext-mem])
@@ -1578,7 +1593,7 @@ OPFG_HD void env_score(const GridDev& g, const C& cx, double* smem, const OpfgBa
     if (g.res_vm_slot >= 0)
         for (int b = cx.tid; b < g.n_pp_bus; b += T) {
             const int i = g.pp_lookup[b];
-            S[g.res_vm_slot + b] = i >= 0 ? vm[i] : NAN;
+            S[g.res_vm_slot + b] = i >= 0 ? s.vm[i] : NAN;    // the copy in shared memory: no second trip to L2
             if (g.res_va_slot >= 0) S[g.res_va_slot + b] = i >= 0 ? va[i] * (180.0 / M_PI) : NAN;
         }
     // generator results: slack P, and Q of every voltage-controlled generator
