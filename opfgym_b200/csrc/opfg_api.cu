@@ -989,12 +989,17 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                 for (int l = 0; l < s.n_levels; ++l)
                     for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1]; ++k) level_of[k] = l;
                 auto read_at = [&](int b, int l) { if (last[b] < l) last[b] = l; };
-                for (int k = 0; k < s.n; ++k)
+                // a diagonal slot holds D_k (with its eager partial sums), then D_k^-1 until the U blocks of row k are
+                // scaled: dead after level(k) as well (t_k lives in the right-hand side)
+                for (int k = 0; k < s.n; ++k) {
+                    read_at(k, level_of[k]);
                     for (int p = s.dp_ptr[k]; p < s.dp_ptr[k + 1]; ++p) { read_at(s.dp_l[p], level_of[k]); read_at(s.dp_w[p], level_of[k]); }
+                }
                 for (int l = 0; l < s.n_levels; ++l)
                     for (int item = s.off_ptr[l]; item < s.off_ptr[l + 1]; ++item) {
                         born[s.off_tgt[item]] = l;
                         read_at(s.off_tgt[item], l);
+                        if (s.off_piv[item] >= 0) read_at(s.off_piv[item], l);
                         for (int p = s.op_ptr[item]; p < s.op_ptr[item + 1]; ++p) { read_at(s.op_l[p], l); read_at(s.op_w[p], l); }
                     }
                 for (int w : s.up_w) last[w] = NEVER;                       // backward sweep
@@ -1004,7 +1009,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                     int next = s.n;                                          // diagonals keep slot == pivot
                     for (int b = s.n; b < s.n_blocks; ++b) if (!is_fill[b]) slot[b] = next++;   // written by the Jacobian pass
                     std::vector<std::vector<int>> births(s.n_levels), deaths(s.n_levels);
-                    for (int b = s.n; b < s.n_blocks; ++b) {
+                    for (int b = 0; b < s.n_blocks; ++b) {
                         if (is_fill[b]) births[born[b]].push_back(b);
                         if (last[b] >= 0 && last[b] < s.n_levels) deaths[last[b]].push_back(b);
                     }
@@ -1024,6 +1029,10 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                         for (int item = s.off_ptr[l]; item < s.off_ptr[l + 1] && ok; ++item)
                             for (int p = s.op_ptr[item]; p < s.op_ptr[item + 1]; ++p)
                                 if (written_in[slot[s.op_l[p]]] == l || written_in[slot[s.op_w[p]]] == l) ok = false;
+                        for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1] && ok; ++k) if (written_in[k] == l) ok = false;   // own diagonal
+                        for (int i = s.eg_ptr[l]; i < s.eg_ptr[l + 1] && ok; ++i) if (written_in[s.eg_k[i]] == l) ok = false;  // eager targets
+                        for (int item = s.off_ptr[l]; item < s.off_ptr[l + 1] && ok; ++item)
+                            if (s.off_piv[item] >= 0 && written_in[s.off_piv[item]] == l) ok = false;                         // D^-1 of the scale phase
                         for (int k = s.level_ptr[l]; k < s.level_ptr[l + 1] && ok; ++k)   // next level's gathers vs this level's writes: other phase, but
                             for (int p = s.dp_ptr[k]; p < s.dp_ptr[k + 1]; ++p)          // an operand must not have been overwritten in ITS level either
                                 if (written_in[slot[s.dp_l[p]]] == l || written_in[slot[s.dp_w[p]]] == l) ok = false;
@@ -1054,7 +1063,7 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
             // (meshed 372-bus grid: -7 %); with ten resident environments the kernel is bound by
             // shared-memory throughput and the extra partial-sum traffic costs 2 %.
             const bool eager = getenv("OPFG_EAGER_GATHER") ? atoi(getenv("OPFG_EAGER_GATHER")) != 0
-                             : pf_smem_doubles(n_slots, s.n, nb, T, 0) * sizeof(double) * 4 > 227 * 1024;
+                             : pf_smem_doubles(n_slots, s.n, nb, T, 0) * sizeof(double) * 5 > 227 * 1024;   // <= 4 environments beside the tables
             if (!eager) {
                 for (int k = 0; k < s.n; ++k) s.dp_own[k] = s.dp_ptr[k];
                 s.eg_ptr.assign(s.n_levels + 1, 0);
