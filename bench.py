@@ -296,9 +296,14 @@ def gpu_arm(args):
     e2e_steps = max(5, args.steps // 2)
     ms_e2e = timed(e2e_step, e2e_steps)
     e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
-    h2d = sum(p.num_envs * p.single_action_space.shape[0] * 4 for p in parts)
     obs_bytes = 2 if args.host_obs_dtype == "float16" else 4
-    d2h = sum(p.num_envs * (p.single_observation_space.shape[0] * obs_bytes + 8 + 8 + 1) for p in parts)   # obs, reward, cost, flag
+    if len(parts) > 1:
+        # mixed batch: ONE padded action matrix in, ONE padded observation matrix out (MixedBatchEnv.step_host)
+        h2d = B * n_act * 4
+        d2h = B * (env.n_obs * 4 + 8 + 8 + 1 + 1 + 1)        # obs (float32), reward, cost, converged, terminated, truncated
+    else:
+        h2d = sum(p.num_envs * p.single_action_space.shape[0] * 4 for p in parts)
+        d2h = sum(p.num_envs * (p.single_observation_space.shape[0] * obs_bytes + 8 + 8 + 1) for p in parts)   # obs, reward, cost, flag
 
     # ---- FP64 peak probe (roofline denominator not in MEASURED_PEAKS.json) -----------------
     fp64_tflops = None

@@ -21,6 +21,7 @@ class MixedBatchEnv:
             e._custom_solver is None and e._custom_objective is None and type(e).step is BatchedOpfEnv.step
             for e in self.envs)       # subclasses with their own step (multi-stage, N-1) are stepped member by member
         self._mixed = None
+        self._host = None              # pinned host buffers of step_host, allocated on first use
         self.num_envs = sum(e.num_envs for e in self.envs)
         self.xp = self.envs[0].xp
         self.device = self.envs[0].device
@@ -102,25 +103,37 @@ class MixedBatchEnv:
         return obs, reward, term, trunc, info
 
     def step_host(self, actions):
-        """Host-buffer form (``BatchedOpfEnv.step_host``): member after member, each with its own
-        look-ahead pipeline; numpy results concatenated (observations padded with NaN)."""
-        import numpy as np
+        """Host-buffer form (``BatchedOpfEnv.step_host``): the actions go to the device from pinned memory, the
+        batch takes ONE ``step`` (kernel 1 / kernel 5 as single launches over all members), and observations
+        (padded with NaN to the widest member), reward, flags and cost come back into pinned buffers that are
+        allocated once -- one synchronisation per call, no host-side concatenation.  Returns numpy views of
+        those buffers (valid until the next call)."""
         xp = self.xp
+        cuda = getattr(self.device, "type", "cpu") == "cuda"
         act = xp.as_tensor(actions)
-        outs, row = [], 0
-        for e in self.envs:
-            a = act[row:row + e.num_envs, :e.single_action_space.shape[0]]
-            outs.append(e.step_host(a if a.is_contiguous() else a.contiguous()))
-            row += e.num_envs
-        obs = np.full((self.num_envs, self.n_obs), np.nan, dtype=outs[0][0].dtype)
-        row = 0
-        for o, e in zip(outs, self.envs):
-            obs[row:row + e.num_envs, :o[0].shape[1]] = o[0]
-            row += e.num_envs
-        cat = lambda k: np.concatenate([o[k] for o in outs])
-        info = {"cost": np.concatenate([o[4]["cost"] for o in outs]),
-                "converged": np.concatenate([o[4]["converged"] for o in outs])}
-        return obs, cat(1), cat(2), cat(3), info
+        if self._host is None:
+            pin = dict(pin_memory=True) if cuda else {}
+            self._host = dict(
+                act=None, obs=None, reward=xp.empty(self.num_envs, dtype=xp.float64, **pin),
+                term=xp.empty(self.num_envs, dtype=xp.bool, **pin), trunc=xp.empty(self.num_envs, dtype=xp.bool, **pin),
+                cost=xp.empty(self.num_envs, dtype=xp.float64, **pin),
+                conv=xp.empty(self.num_envs, dtype=xp.bool, **pin), pin=pin)
+        h = self._host
+        if not (cuda and act.is_pinned()):          # pageable input: through a pinned buffer of its own dtype
+            if h["act"] is None or h["act"].shape != act.shape or h["act"].dtype != act.dtype:
+                h["act"] = xp.empty(tuple(act.shape), dtype=act.dtype, **h["pin"])
+            h["act"].copy_(act)
+            act = h["act"]
+        obs, reward, term, trunc, info = self.step(act.to(self.device, non_blocking=True).to(xp.float64))
+        if h["obs"] is None or h["obs"].dtype != obs.dtype:
+            h["obs"] = xp.empty(tuple(obs.shape), dtype=obs.dtype, **h["pin"])
+        for dst, src in ((h["obs"], obs), (h["reward"], reward), (h["term"], term), (h["trunc"], trunc),
+                         (h["cost"], info["cost"]), (h["conv"], info["converged"])):
+            dst.copy_(src.to(dst.dtype) if src.dtype != dst.dtype else src, non_blocking=True)
+        if cuda:
+            xp.cuda.current_stream(self.device).synchronize()
+        return (h["obs"].numpy(), h["reward"].numpy(), h["term"].numpy(), h["trunc"].numpy(),
+                {"cost": h["cost"].numpy(), "converged": h["conv"].numpy()})
 
     def episode_statistics(self, reduce=True):
         stats = [e.episode_statistics(reduce=reduce) for e in self.envs]

@@ -56,3 +56,30 @@ def test_mixed_batch_equals_members_stepped_alone(fused):
     assert mixed.episode_statistics()["steps"] == 16
     obs2, reward2 = mixed.step(act)[:2]                 # second step: buffers were switched
     assert torch.equal(reward2, torch.cat([alone[0].step(act[:6, :18])[1], alone[1].step(act[6:, :10])[1]]))
+
+
+def _host_step_equals_device_step(device_kw, sync=lambda: None):
+    def members():
+        return [envs.MaxRenewable(num_envs=6, **device_kw), envs.QMarket(num_envs=10, **device_kw)]
+    a, b = MixedBatchEnv(members()), MixedBatchEnv(members())
+    a.reset(seed=9); b.reset(seed=9)
+    for k in range(3):                                  # the pinned result buffers are reused from the second call on
+        act = torch.rand(16, 18, dtype=torch.float64, generator=torch.Generator().manual_seed(k))
+        obs, reward, term, trunc, info = a.step(act.to(a.device))
+        sync()
+        h_obs, h_reward, h_term, h_trunc, h_info = b.step_host(act.numpy())
+        assert isinstance(h_obs, np.ndarray) and h_obs.shape == (16, 305)
+        np.testing.assert_array_equal(h_obs, obs.cpu().numpy())           # NaN padding compares equal here
+        np.testing.assert_array_equal(h_reward, reward.cpu().numpy())
+        np.testing.assert_array_equal(h_info["cost"], info["cost"].cpu().numpy())
+        assert h_term.all() and h_info["converged"].all() and not h_trunc.any()
+
+
+def test_mixed_step_host_equals_step():
+    _host_step_equals_device_step(KW)
+
+
+@pytest.mark.gpu
+def test_mixed_step_host_equals_step_cuda(cuda_lib):
+    kw = {k: v for k, v in KW.items() if k != "engine_cls"}
+    _host_step_equals_device_step(kw, sync=torch.cuda.synchronize)
