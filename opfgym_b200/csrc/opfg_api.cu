@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(T) k_pf(GridDev g, OpfgBatch B) {
 // MODE = STAGE | (4 if the Ybus values are per environment): with the shared table the compiler
 // knows the values live in shared memory (LDS instead of generic loads in the row pass).
 // BOUND: the largest block this instantiation is launched with (T x environments per CTA): 768 caps the kernel at
-// 85 registers (it spills there), so launches of at most 512 / 256 threads get their own, roomier build
+// 85 registers (it spills there), so launches of at most 384 / 256 threads get their own, roomier build
 template <int T, int MODE, int BOUND = 768>
 __global__ void __launch_bounds__(BOUND, 1) k_pf_multi(GridDev g, OpfgBatch B, int E, int env_doubles) {
     constexpr int STAGE = MODE & 3;
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) k_pf_tree(GridDev g, OpfgBatch
 }
 template <int T, int MODE>
 static void (*pick_multi(int bound))(GridDev, OpfgBatch, int, int) {
-    return bound == 256 ? k_pf_multi<T, MODE, 256> : (bound == 512 ? k_pf_multi<T, MODE, 512> : k_pf_multi<T, MODE, 768>);
+    return bound == 256 ? k_pf_multi<T, MODE, 256> : (bound == 384 ? k_pf_multi<T, MODE, 384> : k_pf_multi<T, MODE, 768>);
 }
 static GridDev tree_view(const GridDev& d) {
     GridDev view = d;
@@ -1085,7 +1085,11 @@ int opfg_grid_create(const OpfgGridDesc* desc, OpfgGrid** out) {
                             s.off_ptr[l + 1] - s.off_ptr[l]);
                 const double narrow = std::ceil(items / (double)T) * (45.0 + 30.0 * maxp);
                 const double wide = std::ceil(items * 8 / (double)T) * (75.0 + 12.0 * maxp);
-                mode[l] = wide < narrow ? 1 : 0;
+                // Measured on the grids that still take this kernel (round 2, final code): one lane per pivot everywhere
+                // beats the model's choice (EcoDispatch 2.785 vs 2.807 ms/step, LoadShedding + ties 13.85 vs 13.60 M env
+                // steps/s; eight lanes per pivot everywhere: 3.96 ms / 11.0 M).  OPFG_DIAG_MODE=model restores the model.
+                const char* dm = getenv("OPFG_DIAG_MODE");
+                mode[l] = !dm ? 0 : (strcmp(dm, "model") == 0 ? (wide < narrow ? 1 : 0) : (atoi(dm) ? 1 : 0));
             }
             d.diag_mode = G->tab(mode);
             d.dp_ptr = G->tab(s.dp_ptr); d.dp_pack = G->tab(dp);
@@ -1942,7 +1946,7 @@ int opfg_pf_solve(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
             const int env_doubles = (int)(smem / 8);
             void (*fn)(GridDev, OpfgBatch, int, int) = nullptr;
             static const bool roomy = getenv("OPFG_MULTI_ROOMY") ? atoi(getenv("OPFG_MULTI_ROOMY")) != 0 : true;
-            const int bound = !roomy ? 768 : (TT * E <= 256 ? 256 : (TT * E <= 512 ? 512 : 768));
+            const int bound = !roomy ? 768 : (TT * E <= 256 ? 256 : (TT * E <= 384 ? 384 : 768));   // 384 = three HV environments of 128 threads: 168 registers
             switch (stage | ((G->d.n_dyn > 0 && B->yval) ? 4 : 0)) {
                 case 0: fn = pick_multi<TT, 0>(bound); break;
                 case 1: fn = pick_multi<TT, 1>(bound); break;
@@ -2106,10 +2110,10 @@ int opfg_observe(const OpfgGrid* G, const OpfgBatch* B, void* stream) {
 #ifdef OPFG_PHASE_TIMING
 /* developer instrumentation: cycles of thread 0 per phase, summed over CTAs (8 slots) */
 extern "C" int opfg_debug_phase_cycles(OpfgGrid* G, unsigned long long* host_out, int reset) {
-    if (!G->d.phase_cycles) G->d.phase_cycles = (unsigned long long*)G->up(std::vector<unsigned long long>(96, 0ull));
+    if (!G->d.phase_cycles) G->d.phase_cycles = (unsigned long long*)G->up(std::vector<unsigned long long>(144, 0ull));
     cudaDeviceSynchronize();
-    if (host_out) cudaMemcpy(host_out, G->d.phase_cycles, 96 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    if (reset) cudaMemset(G->d.phase_cycles, 0, 96 * sizeof(unsigned long long));
+    if (host_out) cudaMemcpy(host_out, G->d.phase_cycles, 144 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (reset) cudaMemset(G->d.phase_cycles, 0, 144 * sizeof(unsigned long long));
     return 0;
 }
 #endif

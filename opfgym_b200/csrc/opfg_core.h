@@ -588,7 +588,10 @@ OPFG_HD void jacobian_entry(const GridDev& g, const PfSmem& s, const double* yv,
 // elimination tree would otherwise walk its whole history in one long dependent chain while most
 // lanes idle); the partial sums wait in D_k / y_k, so the order of additions -- and every bit of
 // the result -- is that of the single gather.
+// (all pair loops below are unrolled four times: the index and block loads of four pairs are in flight while the
+// accumulators take the products IN ORDER -- the chain per pair shrinks from index -> blocks -> FMAs to the FMAs)
 OPFG_HD void lu_gather_pairs(const GridDev& g, const PfSmem& s, int p, int pe, D2& r0, D2& r1, D2& y) {
+#pragma unroll 4
     for (; p < pe; ++p) {
         const U2 id = g.dp_pack[p];
         const int li = 2 * (int)(id.x & 0xffffu), wi = 2 * (int)(id.x >> 16);
@@ -627,6 +630,7 @@ OPFG_HD double* lu_component_cell(const PfSmem& s, int k, int sub) {
 OPFG_HD double lu_diag_component(const GridDev& g, const PfSmem& s, int k, int sub, int p, int pe) {
     const int r = sub < 4 ? (sub >> 1) : (sub - 4);
     double acc = *lu_component_cell(s, k, sub);
+#pragma unroll 4
     for (; p < pe; ++p) {
         const U2 id = g.dp_pack[p];
         const D2 l = ld2((r ? s.lu1 : s.lu) + 2 * (id.x & 0xffffu));
@@ -665,6 +669,7 @@ OPFG_HD void lu_off_gather(const GridDev& g, const PfSmem& s, int item) {
     // a fill block (bit 31) has no stored value yet: its slot may still hold a block that died a level ago
     D2 r0{0.0, 0.0}, r1{0.0, 0.0};
     if (!fill) { r0 = ld2(s.lu + xi); r1 = ld2(s.lu1 + xi); }
+#pragma unroll 4
     for (; p < pe; ++p) {
         const uint32_t id = g.op_pack[p];
         const int li = 2 * (int)(id & 0xffffu), wi = 2 * (int)(id >> 16);
@@ -691,6 +696,7 @@ OPFG_HD void lu_off_scale(const GridDev& g, const PfSmem& s, int item) {
 OPFG_HD void bwd_item(const GridDev& g, const PfSmem& s, int k) {
     D2 x = ld2(s.rhs + 2 * k);
     const int pe = g.up_ptr[k + 1];
+#pragma unroll 4
     for (int p = g.up_ptr[k]; p < pe; ++p) {
         const uint32_t id = g.up_pack[p];
         const int wi = 2 * (int)(id & 0xffffu);
@@ -818,19 +824,20 @@ OPFG_HD void env_pf_solve(const GridDev& g, const C& cx, double* smem, const dou
                     else lu_eager_item(g, s, g.eg_item[eb + idx - n_own]);
                 }
             }
+            OPFG_TICK(112 + l);  // lane 0's own diagonal work (the rest of the phase: gathers of other lanes + barrier)
             // gathers of this level's off-diagonal items, from the far end of the lanes (the diagonals took the near end)
             const int ob = g.off_ptr[l], oe = g.off_ptr[l + 1];
             for (int item = ob + (T - 1 - cx.tid); item < oe; item += T) lu_off_gather(g, s, item);
             cx.sync();
-            OPFG_TICK(16 + l);
+            OPFG_TICK(16 + l);   // slots: 16.. diagonal (+ gather) phase, 48.. scale phase, 80.. backward (up to 32 levels)
             for (int item = ob + (T - 1 - cx.tid); item < oe; item += T) lu_off_scale(g, s, item);
             cx.sync();
-            OPFG_TICK(32 + l);
+            OPFG_TICK(48 + l);
         }
         for (int l = g.n_levels - 1; l >= 0; --l) {
             for (int k = g.level_ptr[l] + cx.tid; k < g.level_ptr[l + 1]; k += T) bwd_item(g, s, k);
             cx.sync();
-            OPFG_TICK(48 + l);
+            OPFG_TICK(80 + l);
         }
         for (int k = cx.tid; k < n; k += T) {
             const D2 dx = ld2(s.rhs + 2 * k);

@@ -26,7 +26,7 @@ eng.pf_solve(); eng.pf_solve()
 lib.opfg_debug_phase_cycles(eng.handle, None, 1)
 n = 5
 for _ in range(n): eng.pf_solve()
-out = np.zeros(96, np.uint64)
+out = np.zeros(144, np.uint64)
 lib.opfg_debug_phase_cycles(eng.handle, out.ctypes.data, 1)
 names = ["dc+init", "rows+J", "rows only", "lu diag", "lu off", "bwd", "update", "output"]
 per_env = out.astype(float) / (n * B)
@@ -35,6 +35,6 @@ for k, v in zip(names, per_env[:8]):
     print(f"  {k:10s} {v:9.0f}  {100*v/per_env.sum():5.1f}%")
 nl = eng.info["n_levels"]
 it = float(eng.iterations.float().mean())
-print("per level, cycles per NR iteration: diag / off / bwd")
+print("per level, cycles per NR iteration: lane 0 diagonal + rest of the phase (gathers, barrier) / scale / bwd")
 for l in range(nl):
-    print(f"  L{l:<2d} {per_env[16+l]/it:8.0f} {per_env[32+l]/it:8.0f} {per_env[48+l]/it:8.0f}")
+    print(f"  L{l:<2d} {per_env[112+l]/it:8.0f} + {per_env[16+l]/it:8.0f} {per_env[48+l]/it:8.0f} {per_env[80+l]/it:8.0f}")
