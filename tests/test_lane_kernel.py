@@ -105,3 +105,45 @@ def test_block_kernel_builds_by_block_size_cuda(cuda_lib, monkeypatch):
             monkeypatch.setenv("OPFG_ENVS_PER_CTA", cap)
         _same(_pair(Engine, "1-MV-semiurb--1-sw", 2051, seed=35, lam=(5.0, 12.0), sync=torch.cuda.synchronize,
                     kernels=("cta", "lanes")), mixed=True)
+
+
+def _slots_on_off(engine_cls, n_env, monkeypatch, sync=lambda: None, **kw):
+    """The meshed-grid kernel with fill blocks sharing the storage slots of dead blocks (default) and with one slot
+    per block (OPFG_SHARE_SLOTS=0): only addresses differ, so every output bit must agree -- on converged, slow and
+    diverging environments (injections scaled across the collapse point)."""
+    case = common.make_case("1-HV-urban--0-sw")
+    out, smem = {}, {}
+    for share in ("1", "0"):
+        monkeypatch.setenv("OPFG_SHARE_SLOTS", share)
+        eng = engine_cls(case.program, n_env, obs_dtype="float64", pf_kernel="cta", **kw)
+        assert eng.info["pf_kernel_used"] == 1 and eng.info["n_fill_blocks"] > 0
+        smem[share] = eng.info["smem_bytes_pf"]
+        common.randomize(case, eng, seed=41)
+        eng.assemble()
+        sync()
+        f = np.random.default_rng(41).uniform(0.5, 40.0, n_env)
+        sb = common._np(eng.sbus) * f[:, None, None]
+        eng.sbus[:] = sb if isinstance(eng.sbus, np.ndarray) else eng._from_numpy(sb)
+        eng.pf_solve()
+        eng.score()
+        sync()
+        out[share] = {k: common._np(getattr(eng, k)).copy() for k in ("vm", "va", "converged", "iterations", "reward")}
+    monkeypatch.delenv("OPFG_SHARE_SLOTS")
+    assert smem["1"] < 0.82 * smem["0"], smem                       # 1 899 blocks -> 1 347 slots on this grid
+    conv = out["1"]["converged"].astype(bool)
+    assert 0 < conv.sum() < n_env                                   # both kinds present
+    for k in out["1"]:
+        a, b = out["1"][k], out["0"][k]
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f"), k
+
+
+def test_shared_block_slots_change_no_bit_hostsim(monkeypatch):
+    from tests.hostsim.harness import HostSimEngine
+    _slots_on_off(HostSimEngine, 24, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_shared_block_slots_change_no_bit_cuda(cuda_lib, monkeypatch):
+    import torch
+    from opfgym_b200.engine import Engine
+    _slots_on_off(Engine, 1024, monkeypatch, sync=torch.cuda.synchronize)
