@@ -92,8 +92,8 @@ typedef struct {
 } OpfgGridDesc;
 
 typedef struct {
-    int32_t nb, n_nonref, nnz_y, n_blocks, n_fill_blocks, n_levels, threads_per_env;
-    int32_t smem_bytes_pf, smem_bytes_score;
+    int32_t nb, n_nonref, nnz_y, n_blocks, n_fill_blocks, n_levels, threads_per_env;   /* n_blocks: 2x2 blocks of the FILLED Jacobian */
+    int32_t smem_bytes_pf, smem_bytes_score;   /* per environment; _pf counts storage SLOTS (fill blocks reuse the slots of dead blocks) */
     int32_t n_state, n_const, n_act, n_obs, n_constraints;
     double flops_per_iter;     /* FP64 flops of one NR iteration (mismatch+Jacobian+LU+solves+update) */
     double flops_score;        /* FP64 flops of branch flows + scoring                                */
