@@ -93,12 +93,12 @@ def test_kernels_agree_cuda(cuda_lib, name, n_env, lam, kernels):
 
 @pytest.mark.gpu
 def test_block_kernel_builds_by_block_size_cuda(cuda_lib, monkeypatch):
-    """k_pf_multi exists in three builds (launch bounds 768 / 512 / 256 threads: 80 / ~124 / ~144 registers).  The MV
-    grid normally runs the 768 build (11 environments x 64 threads); capped at 8 and at 4 environments per CTA it
-    runs the 512 and the 256 build: same bits as the lane kernel in all three."""
+    """k_pf_multi exists in three builds (launch bounds 768 / 384 / 256 threads: 80 / ~142 / ~144 registers).  The MV
+    grid normally runs the 768 build (11 environments x 64 threads); capped at 6 and at 4 environments per CTA it
+    runs the 384 and the 256 build: same bits as the lane kernel in all three."""
     import torch
     from opfgym_b200.engine import Engine
-    for cap in (None, "8", "4"):
+    for cap in (None, "6", "4"):
         if cap is None:
             monkeypatch.delenv("OPFG_ENVS_PER_CTA", raising=False)
         else:
