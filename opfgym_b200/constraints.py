@@ -32,11 +32,18 @@ class Constraint:
                  penalty_power: float = 1.0,
                  violation_count_penalty: float = 0.0,
                  value_scale: float = 1.0):
-        if get_values is not None or get_boundaries is not None:
-            raise NotImplementedError(
-                "Python callables cannot run inside the fused scoring kernel; "
-                "describe a custom constraint with unit_type/values_column "
-                "(any result or net column) and value_scale instead.")
+        # Reference constraints.py:27-64: ``get_values(net)`` / ``get_boundaries(net)`` are Python callables on one
+        # pandapower net.  Here they are BATCHED callables on the env (the contract of ``objective_function=``):
+        #   get_values(env)     -> tensor [num_envs, n] on env.device (read cells with env.col(table, column))
+        #   get_boundaries(env) -> {'min' | 'max': tensor [num_envs, n] | [n] | scalar}   (not scaled again, as in
+        #                          the reference, where a custom get_boundaries replaces scale_boundary too)
+        # Such a constraint does not enter the fused scoring kernel: the env evaluates it with tensor ops behind
+        # kernel 5 and recombines penalty, validity, reward and cost (opf_env.BatchedOpfEnv._apply_plugins).
+        if (get_values is None) != (get_boundaries is None):
+            raise ValueError("a callable constraint needs both get_values and get_boundaries "
+                             "(the kernel's own constraints read unit_type / values_column instead)")
+        self.get_values_fn = get_values
+        self.get_boundaries_fn = get_boundaries
         self.unit_type = unit_type
         self.values_column = values_column
         self.only_worst_case_violations = bool(only_worst_case_violations)
@@ -49,6 +56,34 @@ class Constraint:
         # (values = res_sgen.p_mw / 2, tests/test_constraints.py:131-147) be
         # expressed without a callable.
         self.value_scale = float(value_scale)
+
+    @property
+    def is_batched_callable(self) -> bool:
+        return self.get_values_fn is not None
+
+    def batched_metrics(self, env):
+        """``get_violation_metrics`` (reference constraints.py:70-88) of a callable constraint for every environment:
+        returns (valid[B] bool, violation[B], penalty[B]) as tensors on ``env.device``."""
+        xp = env.xp
+        values = xp.as_tensor(self.get_values_fn(env), device=env.device).to(xp.float64)
+        if values.dim() == 1:
+            values = values.reshape(env.num_envs, -1)
+        violation = xp.zeros(env.num_envs, dtype=xp.float64, device=env.device)
+        n_violations = xp.zeros(env.num_envs, dtype=xp.float64, device=env.device)
+        for min_or_max, boundary in self.get_boundaries_fn(env).items():
+            if min_or_max not in ("min", "max"):
+                raise KeyError(f"get_boundaries returned the key {min_or_max!r}: expected 'min' / 'max'")
+            bound = xp.as_tensor(boundary, device=env.device).to(xp.float64)
+            invalid = values > bound if min_or_max == "max" else values < bound          # :110-111 (NaN compares false)
+            n_violations = n_violations + invalid.sum(dim=1)
+            absolute = xp.where(invalid, (values - bound).abs(), xp.zeros_like(values))   # :113-122
+            violation = violation + (absolute.max(dim=1).values if self.only_worst_case_violations
+                                     else absolute.sum(dim=1))
+        if self.autoscale_violation:                                                      # :82-83 (True multiplies by one)
+            violation = violation * float(self.autoscale_violation)
+        penalty = -(violation ** self.penalty_power * self.penalty_factor
+                    + n_violations * self.violation_count_penalty)                        # :124-128
+        return n_violations == 0, violation, penalty
 
     # the factor the kernel multiplies the summed violation with
     def autoscale_factor(self, net) -> float:

@@ -165,6 +165,13 @@ class BatchedOpfEnv:
             self.constraints = constraints_mod.create_default_constraints(net, constraint_params or {})
         else:
             self.constraints = custom_constraints
+        # constraints with batched callables (reference constraints.py:27-64 ``get_values`` / ``get_boundaries``,
+        # examples/custom_constraint.py) are evaluated behind kernel 5; ``self.constraints`` keeps the ones the
+        # kernel scores.  Their columns of valids / violations / unscaled_penalties FOLLOW the kernel's columns.
+        self.batched_constraints = [c for c in self.constraints if getattr(c, "is_batched_callable", False)]
+        self.constraints = [c for c in self.constraints if not getattr(c, "is_batched_callable", False)]
+        if self.batched_constraints and type(self).step is not BatchedOpfEnv.step:
+            raise NotImplementedError("callable constraints on an env with its own step() (multi-stage, N-1)")
 
         # ---- compile + device buffers ------------------------------------------------
         self.rank, self.world_size = int(rank), int(world_size)
@@ -634,18 +641,30 @@ class BatchedOpfEnv:
         self.power_flow_available = True
         self._results = aux
 
-    def _apply_custom_objective(self):
-        """``objective_function=`` plug-in: costs from the callable, reward / cost recombined with the
-        constraint results of kernel 5 (reward.py:61-98)."""
+    def _apply_plugins(self):
+        """``objective_function=`` plug-in and callable constraints: costs from the callable, callable constraints
+        evaluated with tensor ops; reward / cost recombined with the constraint results of kernel 5
+        (reward.py:61-98, constraints.py:70-88)."""
         e, xp = self.engine, self.xp
-        costs = xp.as_tensor(self._custom_objective(self), device=self.device).to(xp.float64)
-        objective = -(costs.reshape(self.num_envs, -1).sum(dim=1))
-        if e.objective_offset is not None:
-            objective = objective - e.objective_offset
-        nc = max(len(self.constraints), 1)
         ok = e.converged.bool()
+        if self._custom_objective is not None:
+            costs = xp.as_tensor(self._custom_objective(self), device=self.device).to(xp.float64)
+            objective = -(costs.reshape(self.num_envs, -1).sum(dim=1))
+            if e.objective_offset is not None:
+                objective = objective - e.objective_offset
+        else:
+            objective = e.objective.clone()
+        nc = max(len(self.constraints), 1)
         valid = e.valids[:, :nc].bool().all(dim=1)
         penalty = e.penalties[:, :nc].sum(dim=1)
+        self._batched_metrics = []
+        for c in self.batched_constraints:
+            v, viol, pen = c.batched_metrics(self)
+            # a failed power flow reports every constraint violated (opf_env.py:390-399), as kernel 5 does for its own
+            one = xp.ones_like(viol)
+            self._batched_metrics.append((v & ok, xp.where(ok, viol, one), xp.where(ok, pen, one)))
+            valid = valid & v
+            penalty = penalty + pen
         nan = xp.full_like(objective, float("nan"))
         e.objective.copy_(xp.where(ok, objective, nan))
         e.reward.copy_(xp.where(ok, self.reward_function.batched(objective, penalty, valid), nan))
@@ -710,8 +729,8 @@ class BatchedOpfEnv:
         self.power_flow_available = True
         self._results = e
         keep = (lambda t: t.clone()) if self.copy_outputs else (lambda t: t)
-        if self._custom_objective is not None:
-            self._apply_custom_objective()
+        if self._custom_objective is not None or self.batched_constraints:
+            self._apply_plugins()
         reward = keep(e.reward)
         if self.clipped_action_penalty:
             # opf_env.py:429, 488-491: the correction is measured against the CLIPPED action
@@ -721,6 +740,11 @@ class BatchedOpfEnv:
                 "unscaled_penalties": keep(e.penalties[:, :nc]), "cost": keep(e.cost),
                 "converged": e.converged.bool(), "iterations": keep(e.iterations),
                 "final_obs": self._obs_out(final=True)}
+        if self.batched_constraints:          # their columns follow the kernel's (none of the kernel's if it has none)
+            k = len(self.constraints)
+            for key, i in (("valids", 0), ("violations", 1), ("unscaled_penalties", 2)):
+                extra = xp.stack([m[i] for m in self._batched_metrics], dim=1)
+                info[key] = xp.cat([info[key][:, :k], extra], dim=1)
         if self._flags is None:
             self._flags = (xp.ones(self.num_envs, dtype=xp.bool, device=self.device),
                            xp.zeros(self.num_envs, dtype=xp.bool, device=self.device))
@@ -765,7 +789,7 @@ class BatchedOpfEnv:
         device->host transfer (the bulk of the bytes) overlaps kernel 3/4; only the small per-env
         results (reward, cost, converged) are copied after kernel 5."""
         xp, e = self.xp, self.engine
-        if self._custom_solver is not None or self._custom_objective is not None:
+        if self._custom_solver is not None or self._custom_objective is not None or self.batched_constraints:
             raise NotImplementedError("step_host pipelines the built-in kernels; with a plug-in power flow or "
                                       "objective use step()")
         h = self.enable_host_io()
@@ -891,6 +915,8 @@ class BatchedOpfEnv:
         batch = e.nostats_batch()         # not an agent step: no contribution to the statistics
         e.pf_solve(batch)
         e.score(batch)
+        if (self._custom_objective is not None or self.batched_constraints) and self._custom_solver is None:
+            self._apply_plugins()         # plug-in objective / callable constraints see this power flow
         self.power_flow_available = True
         self._results = e
         return e.converged.bool()
@@ -945,7 +971,11 @@ class BatchedOpfEnv:
     def is_state_valid(self):
         self.ensure_power_flow_available()
         nc = max(len(self.constraints), 1)
-        return self._results.valids[:, :nc].bool().all(dim=1)
+        valid = self._results.valids[:, :nc].bool().all(dim=1)
+        if self.batched_constraints and self._results is self.engine and getattr(self, "_batched_metrics", None):
+            for m in self._batched_metrics:            # callable constraints of the last step
+                valid = valid & m[0]
+        return valid
 
     def get_objective(self):
         self.ensure_power_flow_available()
@@ -955,7 +985,12 @@ class BatchedOpfEnv:
         self.ensure_power_flow_available()
         nc = max(len(self.constraints), 1)
         r = self._results
-        return r.valids[:, :nc].bool(), r.violations[:, :nc], r.penalties[:, :nc]
+        out = (r.valids[:, :nc].bool(), r.violations[:, :nc], r.penalties[:, :nc])
+        if self.batched_constraints and r is self.engine and getattr(self, "_batched_metrics", None):
+            k = len(self.constraints)                  # the callable constraints' columns follow the kernel's
+            out = tuple(self.xp.cat([o[:, :k], self.xp.stack([m[i] for m in self._batched_metrics], dim=1)], dim=1)
+                        for i, o in enumerate(out))
+        return out
 
     def sample_objective_penalty(self, num_samples: int):
         """Feeds ``reward.estimate_reward_distribution`` (reference reward.py:181-216:

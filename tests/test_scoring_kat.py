@@ -97,8 +97,30 @@ def test_custom_constraint(net):            # :131-147, callable replaced by val
     net.res_sgen["p_mw"] = 3.0
     r = scoring.violation_metrics(con, net)
     assert not r["valid"] and r["violation"] == 0.5
-    with pytest.raises(NotImplementedError):
-        C.Constraint("sgen", "p_mw", get_values=lambda n: n.res_sgen.p_mw / 2)
+    with pytest.raises(ValueError):             # a callable constraint needs both callables
+        C.Constraint("sgen", "p_mw", get_values=lambda env: None)
+
+
+def test_custom_constraint_def_batched():   # reference tests/test_constraints.py:131-147 with BATCHED callables
+    import torch
+    from types import SimpleNamespace
+    env = SimpleNamespace(xp=torch, device=torch.device("cpu"), num_envs=2,
+                          res_sgen_p=torch.tensor([[1.5], [3.0]], dtype=torch.float64),
+                          max_p=torch.tensor([1.0], dtype=torch.float64))
+    con = C.Constraint("sgen", "p_mw", get_values=lambda env: env.res_sgen_p / 2,
+                       get_boundaries=lambda env: {"min": 0, "max": env.max_p})
+    assert con.is_batched_callable
+    valid, violation, penalty = con.batched_metrics(env)
+    assert valid.tolist() == [True, False]              # 1.5 / 2 = 0.75 inside [0, 1]; 3 / 2 - 1 = 0.5 outside
+    assert violation.tolist() == [0.0, 0.5] and penalty.tolist() == [-0.0, -0.5]
+    worst = C.Constraint("sgen", "p_mw", only_worst_case_violations=True, autoscale_violation=3.0, penalty_power=2.0,
+                         penalty_factor=0.5, violation_count_penalty=0.25,
+                         get_values=lambda env: torch.tensor([[0.0, 2.0, 4.0, -3.0]] * 2, dtype=torch.float64),
+                         get_boundaries=lambda env: {"min": torch.tensor([-1.0] * 4), "max": 1.0})
+    valid, violation, penalty = worst.batched_metrics(env)
+    # worst upper violation 3 + worst lower violation 2, autoscale 3 -> 15; three violations
+    assert not valid.any() and violation.tolist() == [15.0, 15.0]
+    assert penalty.tolist() == [-(15.0 ** 2 * 0.5 + 3 * 0.25)] * 2
 
 
 # ------------------------------------------------------------------ C.2 objective
