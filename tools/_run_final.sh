@@ -1,3 +1,4 @@
+# Developer script (gpurun): full GPU test suite, smoke, bench lines of the four configs and the reference arm -> gpurun_out/
 cd /root/repo
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/r02z_gpu_tests.log; cat gpurun_out/r02z_gpu_tests.log

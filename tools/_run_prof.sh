@@ -1,3 +1,4 @@
+# Developer script (gpurun): ncu captures behind profiles/r02z_* -- "a": kernels of a VoltageControl step, "b": k_pf_multi of ed64k + per-kernel DRAM traffic of a step
 cd /root/repo
 if [ "$1" = "a" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_pf_tree|k_score_warps|k_assemble_warps' -s 6 -c 3 -f -o gpurun_out/prof_step_r3a python tests/_prof_run.py > gpurun_out/prof_r3a.log 2>&1; tail -2 gpurun_out/prof_r3a.log
