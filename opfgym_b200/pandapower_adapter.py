@@ -5,8 +5,10 @@ in-repo ``Net`` container).  This is the last hop of INTEGRATION.md §1: with it
 exactly the matrices pandapower's own Newton-Raphson would solve (reference call site
 ``opfgym/opf_env.py:703``).
 
-STATUS: pandapower is not installable in the build image, so this module is exercised only by
-``tests/parity/test_vs_pandapower.py``, which skips without pandapower.  Everything taken from
+STATUS: pandapower is not installable in the build image: against the real package this module is exercised only
+by ``tests/parity/test_vs_pandapower.py``, which skips without pandapower; ``tests/test_pandapower_adapter_stub.py``
+runs it against a ``net._ppc`` / ``net._pd2ppc_lookups`` laid out the way the notes below describe (built from the
+oracle's own conversion), so that at least the reading logic is executed here.  Everything taken from
 pandapower's private attributes is marked [ext-mem] (from memory of pandapower 2.13/2.14):
 
 * ``net._ppc``: the external-numbered ppc -- ``bus``, ``gen``, ``branch`` (PYPOWER column order), ``baseMVA``;
@@ -28,8 +30,8 @@ class PandapowerPpcBuilder:
     """Same interface as ``opfgym_b200.ppc.PpcBuilder`` (``build``, ``element_bus``), fed by pandapower."""
 
     def __init__(self, net, **runpp_kwargs):
-        import pandapower as pp                       # noqa: F401  (fails loudly where pandapower is absent)
         if getattr(net, "_ppc", None) is None or net._ppc.get("bus") is None:
+            import pandapower as pp                   # fails loudly where pandapower is absent
             kw = dict(enforce_q_lims=True)
             kw.update(runpp_kwargs)
             try:
@@ -70,11 +72,10 @@ class PandapowerPpcBuilder:
             branch[:, P.BR_G], branch[:, P.BR_B] = y.real, y.imag
         else:
             branch[:, P.BR_B] = src[:, P.BR_B]
-            try:
-                from pandapower.pypower.idx_brch import BR_G as PP_BR_G
-                branch[:, P.BR_G] = src[:, PP_BR_G]
-            except ImportError:
-                pass
+            # pandapower >= 2.14 keeps the conductance in a column of its own, whose index only pandapower knows:
+            # no silent guess (a dropped conductance would be a different network)
+            from pandapower.pypower.idx_brch import BR_G as PP_BR_G
+            branch[:, P.BR_G] = src[:, PP_BR_G].real
 
         ranges = net._pd2ppc_lookups.get("branch", {})
         def element_rows(table):
@@ -117,10 +118,23 @@ class PandapowerPpcBuilder:
                 cap = float(tr.sn_mva) * float(tr.parallel) * float(tr.df)
                 rate_f[r] = float(tr.vn_hv_kv) / (base_kv[int(branch[r, P.F_BUS])] * cap)
                 rate_t[r] = float(tr.vn_lv_kv) / (base_kv[int(branch[r, P.T_BUS])] * cap)
-        unknown = keep_br.sum() - (self.line_branch >= 0).sum() - (self.trafo_branch >= 0).sum()
-        if unknown:
-            raise NotImplementedError(f"{unknown} ppc branches come from element tables this adapter does not "
-                                      "score (trafo3w / impedance / ...); their flows would have no result rows")
+        # Branches of other element tables (trafo3w: three rows each behind an auxiliary bus; impedance) are solved
+        # like any other row of pandapower's ppc; they have no result rows here (no res_trafo3w / res_impedance cells,
+        # loading factors 0).  An xward also injects power at its bus, which kernel 1 would not scatter: rejected.
+        self.other_branch_rows = {}
+        covered = (self.line_branch >= 0).sum() + (self.trafo_branch >= 0).sum()
+        for table in ranges:
+            if table in ("line", "trafo"):
+                continue
+            a, b = ranges[table]
+            rows = row_of[a:b][row_of[a:b] >= 0]
+            if table == "xward" and b > a:
+                raise NotImplementedError("net.xward: its constant-power part is not an injection kernel 1 knows")
+            self.other_branch_rows[table] = rows
+            covered += len(rows)
+        if covered != keep_br.sum():
+            raise NotImplementedError(f"{int(keep_br.sum() - covered)} rows of net._ppc['branch'] belong to no element "
+                                      "table of net._pd2ppc_lookups['branch']")
         eg, gn = net.ext_grid, net.gen
         vm = np.concatenate([eg.vm_pu.to_numpy(float), gn.vm_pu.to_numpy(float) if len(gn) else np.zeros(0)])
         self._ppc = P.Ppc(base_mva=float(ppc["baseMVA"]), bus=bus, gen=gen, branch=branch,
