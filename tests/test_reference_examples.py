@@ -10,7 +10,7 @@ environment against the oracle's power flow and the reference's reward arithmeti
 (``custom_constraint.py``: tests/test_custom_constraints.py; ``multi_stage.py``: test_multi_stage.py /
 test_golden_f3.py; ``security_constrained.py``: test_security_constrained.py; ``network_reconfiguration.py``:
 test_switch_cells.py / test_islands.py; ``stochastic_obs.py``: test_wrappers_mixed.py; ``non_simbench_net.py``:
-test_env_api.py ``normal_around_mean``.)"""
+test_ieee14_net.py.)"""
 import numpy as np
 import pytest
 import torch
