@@ -22,6 +22,14 @@ def _nets():
     yield "case14", pn.case14()
     yield "case30", pn.case30()
     yield "mv_oberrhein", pn.mv_oberrhein()
+    # ward + (symmetric) impedance elements: pins the [ext-mem] conversions of opfgym_b200/ppc.py and oracle/ppc_ref.py
+    # (tests/test_ward_impedance.py can only hold the two restatements against each other)
+    extra = pn.case14()
+    pp.create_ward(extra, 4, ps_mw=3.0, qs_mvar=1.0, pz_mw=2.0, qz_mvar=-1.5)
+    pp.create_ward(extra, 9, ps_mw=-1.0, qs_mvar=0.5, pz_mw=0.0, qz_mvar=2.0, in_service=False)
+    same_level = [b for b in extra.bus.index if extra.bus.vn_kv[b] == extra.bus.vn_kv[10] and b != 10]
+    pp.create_impedance(extra, 10, same_level[-1], rft_pu=0.02, xft_pu=0.07, sn_mva=50.0)
+    yield "case14+ward+impedance", extra
     try:
         import simbench as sb
         yield "1-MV-semiurb--1-sw", sb.get_simbench_net("1-MV-semiurb--1-sw")
@@ -34,7 +42,8 @@ def _to_container(net):
     """pandapower net -> the in-repo Net container (same tables; used by the oracle and by arm 3)."""
     from opfgym_b200 import net as N
     out = N.Net(sn_mva=float(net.sn_mva), f_hz=float(net.f_hz))
-    for table in ("bus", "line", "trafo", "switch", "load", "sgen", "storage", "gen", "ext_grid", "shunt"):
+    for table in ("bus", "line", "trafo", "impedance", "switch", "load", "sgen", "storage", "ward", "gen", "ext_grid",
+                  "shunt"):
         if table in net and len(net[table]):
             out[table] = net[table].copy()
     return out
